@@ -1,0 +1,113 @@
+"""ctypes binding of libgiwaxs_b200.so (the C ABI in include/giwaxs_b200.h).
+
+There is no CPU fallback: if the shared object is missing this module raises
+at import of the first symbol, and every compute call raises GxError when the
+library reports an error (no device, bad size, CUDA failure).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgiwaxs_b200.so")
+
+GX_OK = 0
+GX_ERR_INVALID = -1
+GX_ERR_CUDA = -2
+GX_ERR_UNSUPPORTED = -3
+GX_ERR_NO_DEVICE = -4
+GX_MAX_SPECIES = 16
+
+
+class GxError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("giwaxs_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+class Chord(ctypes.Structure):
+    """gx_chord (include/giwaxs_b200.h)."""
+    _fields_ = [(n, ctypes.c_double) for n in
+                ("hor", "ver", "stop1", "stop2", "stop12", "mid", "vcos", "rise",
+                 "tan_phi", "tan_theta", "cos_phi", "cos_theta")] + \
+               [("mode", ctypes.c_int32), ("pad", ctypes.c_int32)]
+
+
+_p = ctypes.c_void_p
+_i = ctypes.c_int
+_i64 = ctypes.c_int64
+_d = ctypes.c_double
+
+# name -> (restype, argtypes); every int-returning entry is error-checked
+_PROTOTYPES = {
+    "gx_abi_version": (_i, []),
+    "gx_last_error": (ctypes.c_char_p, []),
+    "gx_device_check": (_i, [_i]),
+    "gx_coords_minmax": (_i, [_p, _i64, _p, _p]),
+    "gx_atoms_sort_rows": (_i, [_p, _i64, _d, _d, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "gx_slice_yrange": (_i, [_p, _p, _i64, _p, _p, _i, _p, _p]),
+    "gx_slice_bbox": (_i, [_p, _p, _p, _i, _d, _p, _p, _p, _i, _p, _p, _p]),
+    "gx_atom_pixel_indices": (_i, [_p, _p, _p, _p, _i64, _i, _d, _d, _d, _d, _p, _p, _p]),
+    "gx_slice_vectors": (_i, [_p, _p, _i, _i, _d, _d, _d, _d, _d, _d, _i, _i, _p, _i, _p, _p, _p, _p]),
+    "gx_project_slices": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _d,
+                               _d, _d, _i, _i, _p, _p]),
+    "gx_fft_plan_bytes": (_i64, [_i]),
+    "gx_fft_plan_fill": (_i, [_i, _p]),
+    "gx_fft2_abs2_shift": (_i, [_p, _p, _p, _i, _i, _p, _d, _d, _p]),
+    "gx_slice_col_index": (_i, [_p, _p, _p, _p, _i, _i, _d, _d, _d, _i, _p, _p]),
+    "gx_axis_col_index": (_i, [_p, _p, _i, _d, _d, _d, _i, _p, _p]),
+    "gx_axis_row_index": (_i, [_p, _i, _d, _d, _d, _i, _p, _p]),
+    "gx_bin_slices": (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p]),
+    "gx_row_histogram": (_i, [_p, _i, _i, _p, _p]),
+    "gx_voxel_finalize": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _d, _p, _p]),
+    "gx_rotate_points": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p, _p]),
+    "gx_detector_accumulate": (_i, [_p, _i, _i, _i, _d, _d, _d, _d, _p, _p, _p, _i64, _p, _p, _i,
+                                    _p, _i, _p, _p]),
+    "gx_host_orientation_matrices": (_i, [_p, _p, _i, _p]),
+    "gx_detector_epilogue": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+}
+
+_UNCHECKED = {"gx_abi_version", "gx_last_error", "gx_fft_plan_bytes"}
+
+_cdll = None
+
+
+def exported_symbols():
+    """Names include/giwaxs_b200.h declares (used by the CPU-side load test)."""
+    return sorted(_PROTOTYPES)
+
+
+def cdll():
+    global _cdll
+    if _cdll is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "%s is missing: build it with `python -m giwaxsim_b200.build` "
+                "(nvcc, sm_100a). giwaxsim_b200 has no CPU fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _cdll = lib
+    return _cdll
+
+
+def last_error():
+    return cdll().gx_last_error().decode("utf-8", "replace")
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point and raise GxError on failure."""
+    rc = getattr(cdll(), name)(*args)
+    if name not in _UNCHECKED and rc != GX_OK:
+        raise GxError(rc, last_error())
+    return rc
+
+
+def ptr(t):
+    """Device (or host) pointer of a torch tensor / numpy array / None."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return ctypes.c_void_p(t.data_ptr())
+    return ctypes.c_void_p(t.ctypes.data)

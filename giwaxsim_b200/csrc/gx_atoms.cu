@@ -1,0 +1,376 @@
+// K0: per-atom prologue -- coordinate extents, phi-invariant z rows and the
+// row sort, per-rotation y' range and index bounding box, parity probe.
+// Everything here is fp64 and reproduces NumPy's rounding so that the integer
+// pixel indices equal the reference's bit for bit (voxelgrids.py:319-349).
+#include <limits.h>
+#include "gx_common.cuh"
+
+#define ATOM_THREADS 256
+
+// ---------------------------------------------------------------- min/max ----
+__global__ void minmax_init_kernel(unsigned long long *o)
+{
+    int i = threadIdx.x;
+    if (i < 6) o[i] = (i & 1) ? 0ull : ~0ull;   // even: running min, odd: running max
+}
+
+__global__ void __launch_bounds__(ATOM_THREADS)
+minmax_kernel(const double *__restrict__ c, int64_t A, unsigned long long *o)
+{
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double v = c[3 * i + k];
+            lo[k] = fmin(lo[k], v);
+            hi[k] = fmax(hi[k], v);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        for (int off = 16; off; off >>= 1) {
+            lo[k] = fmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], off));
+            hi[k] = fmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], off));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            atomicMin(&o[2 * k], gx_ord(lo[k]));
+            atomicMax(&o[2 * k + 1], gx_ord(hi[k]));
+        }
+    }
+}
+
+__global__ void minmax_decode_kernel(unsigned long long *o)
+{
+    int i = threadIdx.x;
+    if (i < 6) reinterpret_cast<double *>(o)[i] = gx_unord(o[i]);
+}
+
+extern "C" int gx_coords_minmax(const double *d_coords, int64_t A, double *d_out6, void *stream)
+{
+    GX_REQUIRE(d_coords && d_out6, "NULL pointer");
+    GX_REQUIRE(A > 0, "no atoms");
+    cudaStream_t st = gx_stream(stream);
+    unsigned long long *o = reinterpret_cast<unsigned long long *>(d_out6);
+    minmax_init_kernel<<<1, 32, 0, st>>>(o);
+    int64_t blocks = (A + ATOM_THREADS - 1) / ATOM_THREADS;
+    if (blocks > GX_SM_COUNT * 8) blocks = GX_SM_COUNT * 8;
+    minmax_kernel<<<(int)blocks, ATOM_THREADS, 0, st>>>(d_coords, A, o);
+    minmax_decode_kernel<<<1, 32, 0, st>>>(o);
+    return gx_check_launch("gx_coords_minmax");
+}
+
+// ------------------------------------------------------------- row sort ----
+__device__ __forceinline__ int atom_row(double z, double z_min, double r, double inv_r, int N)
+{
+    // (z - min) // r, as int; rows >= N are the "invalid" bin N
+    double q = gx_floordiv(__dsub_rn(z, z_min), r, inv_r);
+    return (q >= (double)N) ? N : (int)q;
+}
+
+__global__ void __launch_bounds__(ATOM_THREADS)
+row_hist_kernel(const double *__restrict__ c, int64_t A, double z_min, double r, int N, int32_t *hist)
+{
+    const double inv_r = 1.0 / r;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&hist[atom_row(c[3 * i + 2], z_min, r, inv_r, N)], 1);
+}
+
+// exclusive scan of n = N+1 bins by one block; also resets the cursors
+__global__ void __launch_bounds__(1024)
+row_scan_kernel(int32_t *hist_cursor, int32_t *row_start, int n)
+{
+    __shared__ int32_t warp_sums[32];
+    __shared__ int32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        int i = base + threadIdx.x;
+        int32_t v = (i < n) ? hist_cursor[i] : 0;
+        int32_t x = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            int32_t y = __shfl_up_sync(0xffffffffu, x, off);
+            if ((threadIdx.x & 31) >= off) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int32_t w = warp_sums[threadIdx.x];
+            for (int off = 1; off < 32; off <<= 1) {
+                int32_t y = __shfl_up_sync(0xffffffffu, w, off);
+                if (threadIdx.x >= off) w += y;
+            }
+            warp_sums[threadIdx.x] = w;
+        }
+        __syncthreads();
+        int32_t prefix = carry + ((threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0) + x - v;
+        if (i < n) { row_start[i] = prefix; hist_cursor[i] = prefix; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = prefix + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) row_start[n] = carry;
+}
+
+__global__ void __launch_bounds__(ATOM_THREADS)
+row_scatter_kernel(const double *__restrict__ c, int64_t A, double z_min, double r, int N,
+                   const uint8_t *__restrict__ species, const float2 *__restrict__ f,
+                   int32_t *cursor, double *xs, double *ys, int32_t *perm,
+                   uint8_t *species_out, float2 *f_out)
+{
+    const double inv_r = 1.0 / r;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A; i += (int64_t)gridDim.x * blockDim.x) {
+        int row = atom_row(c[3 * i + 2], z_min, r, inv_r, N);
+        int pos = atomicAdd(&cursor[row], 1);
+        xs[pos] = c[3 * i];
+        ys[pos] = c[3 * i + 1];
+        perm[pos] = (int32_t)i;
+        if (species) species_out[pos] = species[i];
+        if (f) f_out[pos] = f[i];
+    }
+}
+
+extern "C" int gx_atoms_sort_rows(const double *d_coords, int64_t A, double z_min, double r, int N,
+                                  const uint8_t *d_species, const gx_float2 *d_f,
+                                  double *d_xs, double *d_ys, int32_t *d_perm,
+                                  uint8_t *d_species_out, gx_float2 *d_f_out,
+                                  int32_t *d_row_start, int32_t *d_cursor, void *stream)
+{
+    GX_REQUIRE(d_coords && d_xs && d_ys && d_perm && d_row_start && d_cursor, "NULL pointer");
+    GX_REQUIRE(A > 0 && A < (int64_t)INT_MAX, "atom count must be in (0, 2^31)");
+    GX_REQUIRE(N >= 16 && r > 0.0, "bad grid size or voxel size");
+    GX_REQUIRE(!d_species || d_species_out, "d_species_out missing");
+    GX_REQUIRE(!d_f || d_f_out, "d_f_out missing");
+    cudaStream_t st = gx_stream(stream);
+    GX_CUDA(cudaMemsetAsync(d_cursor, 0, (size_t)(N + 2) * sizeof(int32_t), st));
+    int64_t blocks = (A + ATOM_THREADS - 1) / ATOM_THREADS;
+    if (blocks > GX_SM_COUNT * 8) blocks = GX_SM_COUNT * 8;
+    row_hist_kernel<<<(int)blocks, ATOM_THREADS, 0, st>>>(d_coords, A, z_min, r, N, d_cursor);
+    row_scan_kernel<<<1, 1024, 0, st>>>(d_cursor, d_row_start, N + 1);
+    row_scatter_kernel<<<(int)blocks, ATOM_THREADS, 0, st>>>(
+        d_coords, A, z_min, r, N, d_species, reinterpret_cast<const float2 *>(d_f), d_cursor, d_xs, d_ys,
+        d_perm, d_species_out, reinterpret_cast<float2 *>(d_f_out));
+    return gx_check_launch("gx_atoms_sort_rows");
+}
+
+// --------------------------------------------------------------- y range ----
+// min / max over all atoms of y' for a chunk of rotations.  Each thread keeps
+// YR_K atoms in registers and sweeps the rotations (sin/cos broadcast from
+// shared memory); warps merge into per-warp shared slots, one pair of global
+// atomics per (block, rotation) at the end.
+#define YR_K 8
+#define YR_CHUNK 256
+
+__global__ void yrange_init_kernel(unsigned long long *o, int n_phi)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * n_phi) o[i] = (i & 1) ? 0ull : ~0ull;
+}
+
+__global__ void __launch_bounds__(ATOM_THREADS)
+yrange_kernel(const double *__restrict__ xs, const double *__restrict__ ys, int64_t A,
+              const double *__restrict__ d_sin, const double *__restrict__ d_cos, int n_phi,
+              unsigned long long *o)
+{
+    __shared__ double s_sin[YR_CHUNK], s_cos[YR_CHUNK];
+    __shared__ double s_lo[YR_CHUNK][ATOM_THREADS / 32], s_hi[YR_CHUNK][ATOM_THREADS / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int p = threadIdx.x; p < n_phi; p += blockDim.x) {
+        s_sin[p] = d_sin[p];
+        s_cos[p] = d_cos[p];
+    }
+    for (int p = threadIdx.x; p < n_phi * (ATOM_THREADS / 32); p += blockDim.x) {
+        (&s_lo[0][0])[p] = INFINITY;
+        (&s_hi[0][0])[p] = -INFINITY;
+    }
+    __syncthreads();
+    const int64_t tile = (int64_t)ATOM_THREADS * YR_K;
+    for (int64_t base = (int64_t)blockIdx.x * tile; base < A; base += (int64_t)gridDim.x * tile) {
+        double x[YR_K], y[YR_K];
+        bool ok[YR_K];
+#pragma unroll
+        for (int k = 0; k < YR_K; ++k) {
+            int64_t i = base + (int64_t)k * ATOM_THREADS + threadIdx.x;
+            ok[k] = i < A;
+            x[k] = ok[k] ? xs[i] : 0.0;
+            y[k] = ok[k] ? ys[i] : 0.0;
+        }
+        for (int p = 0; p < n_phi; ++p) {
+            const double s = s_sin[p], c = s_cos[p];
+            double lo = INFINITY, hi = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < YR_K; ++k) {
+                double v = gx_rot_y(x[k], y[k], s, c);
+                if (ok[k]) { lo = fmin(lo, v); hi = fmax(hi, v); }
+            }
+            for (int off = 16; off; off >>= 1) {
+                lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+                hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+            }
+            if (lane == 0) {
+                s_lo[p][warp] = fmin(s_lo[p][warp], lo);
+                s_hi[p][warp] = fmax(s_hi[p][warp], hi);
+            }
+        }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < n_phi; p += blockDim.x) {
+        double lo = INFINITY, hi = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < ATOM_THREADS / 32; ++w) { lo = fmin(lo, s_lo[p][w]); hi = fmax(hi, s_hi[p][w]); }
+        atomicMin(&o[2 * p], gx_ord(lo));
+        atomicMax(&o[2 * p + 1], gx_ord(hi));
+    }
+}
+
+__global__ void yrange_decode_kernel(unsigned long long *o, int n_phi)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * n_phi) reinterpret_cast<double *>(o)[i] = gx_unord(o[i]);
+}
+
+extern "C" int gx_slice_yrange(const double *d_xs, const double *d_ys, int64_t A,
+                               const double *d_sin, const double *d_cos, int n_phi,
+                               double *d_yrange, void *stream)
+{
+    GX_REQUIRE(d_xs && d_ys && d_sin && d_cos && d_yrange, "NULL pointer");
+    GX_REQUIRE(A > 0 && n_phi > 0, "empty input");
+    cudaStream_t st = gx_stream(stream);
+    unsigned long long *o = reinterpret_cast<unsigned long long *>(d_yrange);
+    yrange_init_kernel<<<(2 * n_phi + 255) / 256, 256, 0, st>>>(o, n_phi);
+    const int64_t tile = (int64_t)ATOM_THREADS * YR_K;
+    int64_t blocks = (A + tile - 1) / tile;
+    if (blocks > GX_SM_COUNT * 2) blocks = GX_SM_COUNT * 2;
+    for (int p0 = 0; p0 < n_phi; p0 += YR_CHUNK) {
+        int n = n_phi - p0 < YR_CHUNK ? n_phi - p0 : YR_CHUNK;
+        yrange_kernel<<<(int)blocks, ATOM_THREADS, 0, st>>>(d_xs, d_ys, A, d_sin + p0, d_cos + p0, n, o + 2 * p0);
+    }
+    yrange_decode_kernel<<<(2 * n_phi + 255) / 256, 256, 0, st>>>(o, n_phi);
+    return gx_check_launch("gx_slice_yrange");
+}
+
+// ------------------------------------------------------------------ bbox ----
+// Fast path: when no atom can be clipped (all z rows < N and the largest y
+// index < N) the bbox is {0, floor-div of the y' span, first row, last row},
+// because NumPy's floor-divide is monotone.  Otherwise a full pass over the
+// atoms of that rotation evaluates the reference's valid mask.
+__global__ void bbox_fast_kernel(const double *__restrict__ yrange, const int32_t *__restrict__ row_start,
+                                 int N, double r, int n_phi, int32_t *bbox, int32_t *need_full)
+{
+    __shared__ int s_first, s_last;
+    if (threadIdx.x == 0) { s_first = INT_MAX; s_last = -1; }
+    __syncthreads();
+    int first = INT_MAX, last = -1;
+    for (int z = threadIdx.x; z < N; z += blockDim.x)
+        if (row_start[z + 1] > row_start[z]) { first = min(first, z); last = max(last, z); }
+    atomicMin(&s_first, first);
+    atomicMax(&s_last, last);
+    __syncthreads();
+    const bool z_clipped = row_start[N + 1] > row_start[N];
+    const double inv_r = 1.0 / r;
+    for (int p = threadIdx.x; p < n_phi; p += blockDim.x) {
+        double span = __dsub_rn(yrange[2 * p + 1], yrange[2 * p]);
+        double top = gx_floordiv(span, r, inv_r);
+        bool full = z_clipped || !(top < (double)N) || s_last < 0;
+        need_full[p] = full ? 1 : 0;
+        if (full) {
+            bbox[4 * p + 0] = INT_MAX; bbox[4 * p + 1] = -1; bbox[4 * p + 2] = INT_MAX; bbox[4 * p + 3] = -1;
+        } else {
+            bbox[4 * p + 0] = 0; bbox[4 * p + 1] = (int)top; bbox[4 * p + 2] = s_first; bbox[4 * p + 3] = s_last;
+        }
+    }
+}
+
+#define BBOX_ROWS 16
+__global__ void __launch_bounds__(ATOM_THREADS)
+bbox_full_kernel(const double *__restrict__ xs, const double *__restrict__ ys,
+                 const int32_t *__restrict__ row_start, int N, double r,
+                 const double *__restrict__ d_sin, const double *__restrict__ d_cos,
+                 const double *__restrict__ yrange, const int32_t *__restrict__ need_full, int32_t *bbox)
+{
+    const int p = blockIdx.y;
+    if (!need_full[p]) return;
+    const double s = d_sin[p], c = d_cos[p], shift = yrange[2 * p], inv_r = 1.0 / r;
+    int ylo = INT_MAX, yhi = -1, zlo = INT_MAX, zhi = -1;
+    const int z0 = blockIdx.x * BBOX_ROWS;
+    for (int z = z0; z < min(z0 + BBOX_ROWS, N); ++z) {
+        for (int i = row_start[z] + threadIdx.x; i < row_start[z + 1]; i += blockDim.x) {
+            double a = __dsub_rn(gx_rot_y(xs[i], ys[i], s, c), shift);
+            double q = gx_floordiv(a, r, inv_r);
+            if (q < (double)N) {
+                int yi = (int)q;
+                ylo = min(ylo, yi); yhi = max(yhi, yi); zlo = min(zlo, z); zhi = max(zhi, z);
+            }
+        }
+    }
+    for (int off = 16; off; off >>= 1) {
+        ylo = min(ylo, __shfl_xor_sync(0xffffffffu, ylo, off));
+        yhi = max(yhi, __shfl_xor_sync(0xffffffffu, yhi, off));
+        zlo = min(zlo, __shfl_xor_sync(0xffffffffu, zlo, off));
+        zhi = max(zhi, __shfl_xor_sync(0xffffffffu, zhi, off));
+    }
+    if ((threadIdx.x & 31) == 0 && yhi >= 0) {
+        atomicMin(&bbox[4 * p + 0], ylo); atomicMax(&bbox[4 * p + 1], yhi);
+        atomicMin(&bbox[4 * p + 2], zlo); atomicMax(&bbox[4 * p + 3], zhi);
+    }
+}
+
+__global__ void bbox_empty_kernel(int32_t *bbox, int n_phi)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n_phi && bbox[4 * p + 1] < 0) { bbox[4 * p] = -1; bbox[4 * p + 2] = -1; bbox[4 * p + 3] = -1; }
+}
+
+extern "C" int gx_slice_bbox(const double *d_xs, const double *d_ys, const int32_t *d_row_start, int N,
+                             double r, const double *d_sin, const double *d_cos, const double *d_yrange,
+                             int n_phi, int32_t *d_bbox, int32_t *d_scratch, void *stream)
+{
+    GX_REQUIRE(d_xs && d_ys && d_row_start && d_sin && d_cos && d_yrange && d_bbox && d_scratch, "NULL pointer");
+    GX_REQUIRE(n_phi > 0 && N >= 16, "bad sizes");
+    cudaStream_t st = gx_stream(stream);
+    int32_t *need_full = d_scratch;
+    bbox_fast_kernel<<<1, 1024, 0, st>>>(d_yrange, d_row_start, N, r, n_phi, d_bbox, need_full);
+    bbox_full_kernel<<<dim3((N + BBOX_ROWS - 1) / BBOX_ROWS, n_phi), ATOM_THREADS, 0, st>>>(
+        d_xs, d_ys, d_row_start, N, r, d_sin, d_cos, d_yrange, need_full, d_bbox);
+    bbox_empty_kernel<<<(n_phi + 255) / 256, 256, 0, st>>>(d_bbox, n_phi);
+    return gx_check_launch("gx_slice_bbox");
+}
+
+// ---------------------------------------------------------- parity probe ----
+__global__ void __launch_bounds__(ATOM_THREADS)
+pixel_index_kernel(const double *__restrict__ xs, const double *__restrict__ ys,
+                   const int32_t *__restrict__ perm, const int32_t *__restrict__ row_start,
+                   int64_t A, int N, double r, double s, double c, double shift,
+                   int64_t *y_idx, int64_t *z_idx)
+{
+    const double inv_r = 1.0 / r;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A; i += (int64_t)gridDim.x * blockDim.x) {
+        // row of sorted atom i: last z with row_start[z] <= i
+        int lo = 0, hi = N + 1;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (row_start[mid] <= (int32_t)i) lo = mid; else hi = mid;
+        }
+        double a = __dsub_rn(gx_rot_y(xs[i], ys[i], s, c), shift);
+        double q = gx_floordiv(a, r, inv_r);
+        int32_t o = perm[i];
+        y_idx[o] = (int64_t)q;
+        z_idx[o] = lo;
+    }
+}
+
+extern "C" int gx_atom_pixel_indices(const double *d_xs, const double *d_ys, const int32_t *d_perm,
+                                     const int32_t *d_row_start, int64_t A, int N, double r,
+                                     double sin_phi, double cos_phi, double y_shift,
+                                     int64_t *d_y_idx, int64_t *d_z_idx, void *stream)
+{
+    GX_REQUIRE(d_xs && d_ys && d_perm && d_row_start && d_y_idx && d_z_idx, "NULL pointer");
+    GX_REQUIRE(A > 0, "no atoms");
+    int64_t blocks = (A + ATOM_THREADS - 1) / ATOM_THREADS;
+    if (blocks > GX_SM_COUNT * 8) blocks = GX_SM_COUNT * 8;
+    pixel_index_kernel<<<(int)blocks, ATOM_THREADS, 0, gx_stream(stream)>>>(
+        d_xs, d_ys, d_perm, d_row_start, A, N, r, sin_phi, cos_phi, y_shift, d_y_idx, d_z_idx);
+    return gx_check_launch("gx_atom_pixel_indices");
+}

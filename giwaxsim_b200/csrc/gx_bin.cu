@@ -1,0 +1,193 @@
+// K3 / K3b: binning of slice intensities into the 3-D voxel grid and the
+// finalisation (average, crop, f0 weighting).
+//   voxelgrids.py:396-401,464-506 ; comparison.py:765-786 ; voxelgrids.py:16-48,828-857
+//
+// Index layout follows the reference: grids are [qy][qx][qz] with qz fastest.
+// A slice column fixes (iy,ix), a slice row fixes iz, so consecutive rows of
+// one column hit consecutive iz addresses: warps are laid out along rows and
+// the fp32 RED.ADDs coalesce.  Counts are rank-1 per slice (H[iy,ix] x m[iz]);
+// the driver keeps only H (u32, q_num^2) and m (q_num) unless the caller bins
+// with varying row tables, in which case the full 3-D u32 count grid is used.
+#include "gx_common.cuh"
+
+__device__ __forceinline__ int bin_index(double v, double qmin, double qmax, double dq, double inv_dq,
+                                         int q_num, bool &ok)
+{
+    ok = (v <= qmax) && (v >= qmin);
+    double q = gx_floordiv(__dsub_rn(v, qmin), dq, inv_dq);
+    int i = (int)q;
+    if (i < 0 || i >= q_num) ok = false;   // the reference would raise IndexError here
+    return i;
+}
+
+__global__ void slice_col_index_kernel(const double *__restrict__ xl, const double *__restrict__ xr,
+                                       const double *__restrict__ yl, const double *__restrict__ yr,
+                                       int N, double qmin, double qmax, double dq, int q_num, int32_t *col)
+{
+    const int p = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const double inv_dq = 1.0 / dq;
+    // np.linspace: step = (stop - start) / (N - 1), value = j*step + start, last = stop
+    const double x0 = xl[p], x1 = xr[p], y0 = yl[p], y1 = yr[p];
+    const double div = (double)(N - 1);
+    const double sx = __ddiv_rn(__dsub_rn(x1, x0), div), sy = __ddiv_rn(__dsub_rn(y1, y0), div);
+    const double qx = gx_linspace(j, N, x0, sx, x1), qy = gx_linspace(j, N, y0, sy, y1);
+    bool okx, oky;
+    const int ix = bin_index(qx, qmin, qmax, dq, inv_dq, q_num, okx);
+    const int iy = bin_index(qy, qmin, qmax, dq, inv_dq, q_num, oky);
+    col[(size_t)p * N + j] = (okx && oky) ? iy * q_num + ix : -1;
+}
+
+extern "C" int gx_slice_col_index(const double *d_qx_left, const double *d_qx_right,
+                                  const double *d_qy_left, const double *d_qy_right, int n_phi, int N,
+                                  double qmin, double qmax, double dq, int q_num, int32_t *d_col, void *stream)
+{
+    GX_REQUIRE(d_qx_left && d_qx_right && d_qy_left && d_qy_right && d_col, "NULL pointer");
+    GX_REQUIRE(n_phi > 0 && N > 1 && q_num > 0 && dq > 0.0, "bad sizes");
+    GX_REQUIRE((int64_t)q_num * q_num < 2147483647LL, "q_num too large");
+    slice_col_index_kernel<<<dim3((N + 255) / 256, n_phi), 256, 0, gx_stream(stream)>>>(
+        d_qx_left, d_qx_right, d_qy_left, d_qy_right, N, qmin, qmax, dq, q_num, d_col);
+    return gx_check_launch("gx_slice_col_index");
+}
+
+__global__ void axis_col_index_kernel(const double *__restrict__ qx, const double *__restrict__ qy, int n,
+                                      double qmin, double qmax, double dq, int q_num, int32_t *col)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double inv_dq = 1.0 / dq;
+    bool okx, oky;
+    const int ix = bin_index(qx[j], qmin, qmax, dq, inv_dq, q_num, okx);
+    const int iy = bin_index(qy[j], qmin, qmax, dq, inv_dq, q_num, oky);
+    col[j] = (okx && oky) ? iy * q_num + ix : -1;
+}
+
+extern "C" int gx_axis_col_index(const double *d_qx, const double *d_qy, int n, double qmin, double qmax,
+                                 double dq, int q_num, int32_t *d_col, void *stream)
+{
+    GX_REQUIRE(d_qx && d_qy && d_col, "NULL pointer");
+    GX_REQUIRE(n > 0 && q_num > 0 && dq > 0.0, "bad sizes");
+    axis_col_index_kernel<<<(n + 255) / 256, 256, 0, gx_stream(stream)>>>(d_qx, d_qy, n, qmin, qmax, dq, q_num, d_col);
+    return gx_check_launch("gx_axis_col_index");
+}
+
+__global__ void axis_row_index_kernel(const double *__restrict__ qz, int n, double qmin, double qmax,
+                                      double dq, int q_num, int32_t *row)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    bool ok;
+    const int iz = bin_index(qz[j], qmin, qmax, dq, 1.0 / dq, q_num, ok);
+    row[j] = ok ? iz : -1;
+}
+
+extern "C" int gx_axis_row_index(const double *d_qz, int n, double qmin, double qmax, double dq, int q_num,
+                                 int32_t *d_row, void *stream)
+{
+    GX_REQUIRE(d_qz && d_row, "NULL pointer");
+    GX_REQUIRE(n > 0 && q_num > 0 && dq > 0.0, "bad sizes");
+    axis_row_index_kernel<<<(n + 255) / 256, 256, 0, gx_stream(stream)>>>(d_qz, n, qmin, qmax, dq, q_num, d_row);
+    return gx_check_launch("gx_axis_row_index");
+}
+
+__global__ void row_histogram_kernel(const int32_t *__restrict__ row, int n, uint32_t *m)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n && row[j] >= 0) atomicAdd(&m[row[j]], 1u);
+}
+
+extern "C" int gx_row_histogram(const int32_t *d_row, int n, int q_num, uint32_t *d_m, void *stream)
+{
+    GX_REQUIRE(d_row && d_m && n > 0 && q_num > 0, "bad arguments");
+    cudaStream_t st = gx_stream(stream);
+    GX_CUDA(cudaMemsetAsync(d_m, 0, (size_t)q_num * sizeof(uint32_t), st));
+    row_histogram_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_row, n, d_m);
+    return gx_check_launch("gx_row_histogram");
+}
+
+// ------------------------------------------------------------ accumulate ----
+// block = 32 rows x 8 columns: lanes run along rows (contiguous iz) so the
+// REDs coalesce; the 8 columns of a block re-use the row indices.
+#define BIN_ROWS 32
+#define BIN_COLS 8
+__global__ void __launch_bounds__(BIN_ROWS * BIN_COLS)
+bin_slices_kernel(const float *__restrict__ iq, int rows, int cols, const int32_t *__restrict__ col,
+                  int col_stride, const int32_t *__restrict__ row, int q_num,
+                  float *sum, uint32_t *count3, uint32_t *count2)
+{
+    const int b = blockIdx.z;
+    const int r = blockIdx.y * BIN_ROWS + threadIdx.x;
+    const int c = blockIdx.x * BIN_COLS + threadIdx.y;
+    if (c >= cols) return;
+    const int yx = col[(size_t)b * col_stride + c];
+    if (yx < 0) return;
+    if (count2 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(&count2[yx], 1u);
+    if (r >= rows) return;
+    const int iz = row[r];
+    if (iz < 0) return;
+    const size_t v = (size_t)yx * q_num + iz;
+    atomicAdd(&sum[v], iq[((size_t)b * rows + r) * cols + c]);
+    if (count3) atomicAdd(&count3[v], 1u);
+}
+
+extern "C" int gx_bin_slices(const float *d_iq2d, int batch, int rows, int cols,
+                             const int32_t *d_col, int col_stride, const int32_t *d_row, int q_num,
+                             float *d_sum, uint32_t *d_count3, uint32_t *d_count2, void *stream)
+{
+    GX_REQUIRE(d_iq2d && d_col && d_row && d_sum, "NULL pointer");
+    GX_REQUIRE(d_count3 || d_count2, "one of d_count3 / d_count2 is required");
+    GX_REQUIRE(batch > 0 && rows > 0 && cols > 0 && q_num > 0, "bad sizes");
+    GX_REQUIRE(batch <= 65535, "batch too large for one launch");
+    dim3 grid((cols + BIN_COLS - 1) / BIN_COLS, (rows + BIN_ROWS - 1) / BIN_ROWS, batch);
+    bin_slices_kernel<<<grid, dim3(BIN_ROWS, BIN_COLS), 0, gx_stream(stream)>>>(
+        d_iq2d, rows, cols, d_col, col_stride, d_row, q_num, d_sum, d_count3, d_count2);
+    return gx_check_launch("gx_bin_slices");
+}
+
+// -------------------------------------------------------------- finalise ----
+struct Aff { double a[9]; double Z; };
+
+__global__ void __launch_bounds__(256)
+voxel_finalize_kernel(const float *__restrict__ sum, const uint32_t *__restrict__ count3,
+                      const uint32_t *__restrict__ count2, const uint32_t *__restrict__ m,
+                      int q_num, int lo, int V, const double *__restrict__ axis, Aff aff, float *iq)
+{
+    const size_t n = (size_t)V * V * V;
+    const double k = 1.0 / (16.0 * 3.14159265358979323846 * 3.14159265358979323846);
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (size_t)gridDim.x * blockDim.x) {
+        const int iz = (int)(o % V), ix = (int)((o / V) % V), iy = (int)(o / ((size_t)V * V));
+        const size_t yx = (size_t)(iy + lo) * q_num + (ix + lo);
+        const size_t v = yx * q_num + (iz + lo);
+        const double cnt = count3 ? (double)count3[v] : (double)count2[yx] * (double)m[iz + lo];
+        float out = 0.f;
+        if (cnt != 0.0) {
+            const double qx = axis[ix + lo], qy = axis[iy + lo], qz = axis[iz + lo];
+            const double q2 = (qx * qx + qy * qy + qz * qz) * k;
+            double f = aff.a[0] * exp(-aff.a[1] * q2) + aff.a[2] * exp(-aff.a[3] * q2) +
+                       aff.a[4] * exp(-aff.a[5] * q2) + aff.a[6] * exp(-aff.a[7] * q2) + aff.a[8];
+            f /= aff.Z;
+            out = (float)(((double)sum[v] / cnt) * f * f);
+        }
+        iq[o] = out;
+    }
+}
+
+extern "C" int gx_voxel_finalize(const float *d_sum, const uint32_t *d_count3, const uint32_t *d_count2,
+                                 const uint32_t *d_m, int q_num, int lo, int hi, const double *d_axis,
+                                 const double *h_aff9, double Z, float *d_iq, void *stream)
+{
+    GX_REQUIRE(d_sum && d_axis && h_aff9 && d_iq, "NULL pointer");
+    GX_REQUIRE(d_count3 || (d_count2 && d_m), "count grids missing");
+    GX_REQUIRE(q_num > 0 && lo >= 0 && hi > lo && hi <= q_num && Z != 0.0, "bad crop range");
+    Aff aff;
+    for (int i = 0; i < 9; ++i) aff.a[i] = h_aff9[i];
+    aff.Z = Z;
+    const int V = hi - lo;
+    const size_t n = (size_t)V * V * V;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > (size_t)GX_SM_COUNT * 16) blocks = (size_t)GX_SM_COUNT * 16;
+    voxel_finalize_kernel<<<(int)blocks, 256, 0, gx_stream(stream)>>>(d_sum, d_count3, d_count2, d_m, q_num,
+                                                                     lo, V, d_axis, aff, d_iq);
+    return gx_check_launch("gx_voxel_finalize");
+}

@@ -1,0 +1,306 @@
+// In-shared-memory 1-D complex FFT engine (fp32), radix 4/8/16 passes in
+// registers, used by every transform on the path (voxelgrids.py:388).
+//
+// The code is written against an explicit (tid, nthreads) pair instead of
+// threadIdx so that the very same templates compile for the host
+// (tests/host_emul) where the pass/permutation/twiddle logic is unit-tested
+// against numpy.fft without a GPU.
+//
+// Transform of length M = 2^L, in place, decimation in frequency:
+//   pass p has radix R_p and stride S_p = M / (R_0 ... R_p); butterfly b works
+//   on elements base + S_p*n, multiplies output k by W_{S_p R_p}^{t k} and
+//   stores it at base + S_p*k.  Natural-order input, digit-reversed output:
+//   X[k] with k = k_0 + R_0 k_1 + R_0 R_1 k_2 ... ends at S_0 k_0 + S_1 k_1 ...
+//   (gx_fft_pos).  Shared-memory addresses go through gx_phys() (one pad word
+//   every 16 and every 256 elements) which keeps every pass and the permuted
+//   read-out free of bank conflicts for the 16^k schedules.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define GX_HD __host__ __device__ __forceinline__
+#else
+#define GX_HD inline
+struct float2 { float x, y; };
+static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
+#endif
+
+// ---- radix schedule per log2(M) ------------------------------------------
+template <int L> struct GxSched;
+#define GX_SCHED(L_, NP_, A_, B_, C_, D_)                                        \
+    template <> struct GxSched<L_> {                                            \
+        enum { NP = NP_, R0 = A_, R1 = B_, R2 = C_, R3 = D_ };                  \
+    }
+GX_SCHED(4, 1, 16, 1, 1, 1);
+GX_SCHED(5, 2, 8, 4, 1, 1);
+GX_SCHED(6, 2, 8, 8, 1, 1);
+GX_SCHED(7, 2, 16, 8, 1, 1);
+GX_SCHED(8, 2, 16, 16, 1, 1);
+GX_SCHED(9, 3, 8, 8, 8, 1);
+GX_SCHED(10, 3, 16, 16, 4, 1);
+GX_SCHED(11, 3, 16, 16, 8, 1);
+GX_SCHED(12, 3, 16, 16, 16, 1);
+GX_SCHED(13, 4, 8, 16, 16, 4);
+#undef GX_SCHED
+
+// runtime view of the same table (host plan builder, tests)
+static inline int gx_sched_radices(int L, int r[4])
+{
+    switch (L) {
+#define GX_CASE(L_) case L_: r[0] = GxSched<L_>::R0; r[1] = GxSched<L_>::R1; \
+                             r[2] = GxSched<L_>::R2; r[3] = GxSched<L_>::R3; return GxSched<L_>::NP;
+        GX_CASE(4) GX_CASE(5) GX_CASE(6) GX_CASE(7) GX_CASE(8)
+        GX_CASE(9) GX_CASE(10) GX_CASE(11) GX_CASE(12) GX_CASE(13)
+#undef GX_CASE
+    default: return 0;
+    }
+}
+
+// ---- plan table layout (float2 units) --------------------------------------
+// [ twiddles pass 0 | pass 1 | ... ][ chirp N ][ bhat M ]   (last two: Bluestein)
+struct GxFftLayout {
+    int N, M, L, bluestein;
+    int tw_off[4];
+    int chirp_off, bhat_off, total;
+};
+
+static inline GxFftLayout gx_fft_layout(int N)
+{
+    GxFftLayout g;
+    g.N = N; g.M = 0; g.L = 0; g.bluestein = 0; g.total = 0;
+    g.chirp_off = g.bhat_off = 0;
+    for (int i = 0; i < 4; ++i) g.tw_off[i] = 0;
+    if (N < 16) return g;
+    int pow2 = (N & (N - 1)) == 0;
+    int M = N;
+    if (!pow2) { M = 1; while (M < 2 * N - 1) M <<= 1; g.bluestein = 1; }
+    int L = 0; while ((1 << L) < M) ++L;
+    if (L < 4 || L > 13) return g;
+    g.M = M; g.L = L;
+    int r[4]; int np = gx_sched_radices(L, r);
+    int off = 0, S = M;
+    for (int p = 0; p < np; ++p) {
+        S /= r[p];
+        g.tw_off[p] = off;
+        if (S > 1) off += (r[p] - 1) * S;
+    }
+    if (g.bluestein) { g.chirp_off = off; off += N; g.bhat_off = off; off += M; }
+    g.total = off;
+    return g;
+}
+
+// ---- addressing -----------------------------------------------------------
+GX_HD int gx_phys(int i) { return i + (i >> 4) + (i >> 8); }
+GX_HD int gx_phys_len(int M) { return M + (M >> 4) + (M >> 8) + 1; }
+
+template <int L> GX_HD int gx_fft_pos(int k)
+{
+    typedef GxSched<L> S;
+    constexpr int M = 1 << L;
+    int p = (k % S::R0) * (M / S::R0);
+    if (S::NP > 1) { k /= S::R0; p += (k % S::R1) * (M / S::R0 / S::R1); }
+    if (S::NP > 2) { k /= S::R1; p += (k % S::R2) * (M / S::R0 / S::R1 / S::R2); }
+    if (S::NP > 3) { k /= S::R2; p += (k % S::R3) * (M / S::R0 / S::R1 / S::R2 / S::R3); }
+    return p;
+}
+
+// ---- complex helpers -------------------------------------------------------
+GX_HD float2 gx_cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+GX_HD float2 gx_csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+GX_HD float2 gx_cmul(float2 a, float2 b)
+{
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+GX_HD float2 gx_mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+GX_HD float2 gx_conj(float2 a) { return make_float2(a.x, -a.y); }
+
+// forward DFTs (e^{-2 pi i nk/R}), in place, natural order in and out
+GX_HD void gx_dft2(float2 &a, float2 &b)
+{
+    float2 t = a; a = gx_cadd(t, b); b = gx_csub(t, b);
+}
+GX_HD void gx_dft4(float2 &v0, float2 &v1, float2 &v2, float2 &v3)
+{
+    float2 a0 = gx_cadd(v0, v2), a1 = gx_csub(v0, v2);
+    float2 a2 = gx_cadd(v1, v3), a3 = gx_mul_mi(gx_csub(v1, v3));
+    v0 = gx_cadd(a0, a2); v1 = gx_cadd(a1, a3);
+    v2 = gx_csub(a0, a2); v3 = gx_csub(a1, a3);
+}
+
+template <int R> struct GxDft;
+template <> struct GxDft<2> { static GX_HD void run(float2 *v) { gx_dft2(v[0], v[1]); } };
+template <> struct GxDft<4> { static GX_HD void run(float2 *v) { gx_dft4(v[0], v[1], v[2], v[3]); } };
+template <> struct GxDft<8> {
+    static GX_HD void run(float2 *v)
+    {
+        // n = 2a + b : DFT4 over a for b = 0,1 ; twiddle W8^{b k1} ; DFT2 over b
+        const float h = 0.70710678118654752440f;
+        gx_dft4(v[0], v[2], v[4], v[6]);   // b = 0 -> y0[k1] in v[0],v[2],v[4],v[6]
+        gx_dft4(v[1], v[3], v[5], v[7]);   // b = 1 -> y1[k1] in v[1],v[3],v[5],v[7]
+        // y1[k1] *= W8^{k1}
+        v[3] = make_float2((v[3].x + v[3].y) * h, (v[3].y - v[3].x) * h);     // W8^1 = (h,-h)
+        v[5] = gx_mul_mi(v[5]);                                               // W8^2 = -i
+        v[7] = make_float2((v[7].y - v[7].x) * h, -(v[7].x + v[7].y) * h);    // W8^3 = (-h,-h)
+        // X[k1 + 4 k2] = y0[k1] + (-1)^{k2} y1[k1]
+        float2 o[8];
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) {
+            o[k1] = gx_cadd(v[2 * k1], v[2 * k1 + 1]);
+            o[k1 + 4] = gx_csub(v[2 * k1], v[2 * k1 + 1]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = o[k];
+    }
+};
+template <> struct GxDft<16> {
+    static GX_HD void run(float2 *v)
+    {
+        // n = 4a + b : DFT4 over a ; twiddle W16^{b k1} ; DFT4 over b ; k = k1 + 4 k2
+        const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
+        const float h = 0.70710678118654752440f;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) gx_dft4(v[b], v[4 + b], v[8 + b], v[12 + b]);
+        // after this, y[b][k1] lives in v[4*k1 + b]
+        // W16^m = (cos(pi m/8), -sin(pi m/8))
+        v[4 * 1 + 1] = gx_cmul(v[4 * 1 + 1], make_float2(c1, -s1));    // m = 1
+        v[4 * 1 + 2] = gx_cmul(v[4 * 1 + 2], make_float2(h, -h));      // m = 2
+        v[4 * 1 + 3] = gx_cmul(v[4 * 1 + 3], make_float2(s1, -c1));    // m = 3
+        v[4 * 2 + 1] = gx_cmul(v[4 * 2 + 1], make_float2(h, -h));      // m = 2
+        v[4 * 2 + 2] = gx_mul_mi(v[4 * 2 + 2]);                        // m = 4
+        v[4 * 2 + 3] = gx_cmul(v[4 * 2 + 3], make_float2(-h, -h));     // m = 6
+        v[4 * 3 + 1] = gx_cmul(v[4 * 3 + 1], make_float2(s1, -c1));    // m = 3
+        v[4 * 3 + 2] = gx_cmul(v[4 * 3 + 2], make_float2(-h, -h));     // m = 6
+        v[4 * 3 + 3] = gx_cmul(v[4 * 3 + 3], make_float2(-c1, s1));    // m = 9
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1)
+            gx_dft4(v[4 * k1 + 0], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+        // now X[k1 + 4 k2] lives in v[4*k1 + k2]: transpose the 4x4 register tile
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = a + 1; b < 4; ++b) { float2 t = v[4 * a + b]; v[4 * a + b] = v[4 * b + a]; v[4 * b + a] = t; }
+    }
+};
+
+// ---- one pass over NBUF independent buffers of length M --------------------
+// s: shared array holding NBUF padded buffers, buffer j at s + j*BUFSTRIDE.
+// DIT == false: butterfly then twiddle (decimation in frequency, natural in ->
+//               digit-reversed out, passes run first to last);
+// DIT == true : twiddle then butterfly (decimation in time, digit-reversed in
+//               -> natural out, passes run last to first).  Same geometry and
+//               the same twiddle table W_{S R}^{t k}.
+template <int R, int S, int M, int NBUF, int BUFSTRIDE, bool DIT>
+GX_HD void gx_fft_pass(float2 *s, const float2 *tw, int tid, int nthreads)
+{
+    constexpr int NBFLY = M / R;
+    for (int w = tid; w < NBUF * NBFLY; w += nthreads) {
+        const int buf = w / NBFLY;
+        const int b = w - buf * NBFLY;
+        const int blk = b / S;
+        const int t = b - blk * S;
+        const int base = blk * (S * R) + t;
+        float2 *sb = s + buf * BUFSTRIDE;
+        float2 v[R];
+#pragma unroll
+        for (int n = 0; n < R; ++n) v[n] = sb[gx_phys(base + S * n)];
+        if (DIT && S > 1) {
+#pragma unroll
+            for (int k = 1; k < R; ++k) v[k] = gx_cmul(v[k], tw[(k - 1) * S + t]);
+        }
+        GxDft<R>::run(v);
+        if (!DIT && S > 1) {
+#pragma unroll
+            for (int k = 1; k < R; ++k) v[k] = gx_cmul(v[k], tw[(k - 1) * S + t]);
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) sb[gx_phys(base + S * k)] = v[k];
+    }
+}
+
+#if defined(__CUDACC__)
+#define GX_BLOCK_SYNC() __syncthreads()
+#define GX_DEV __device__ __forceinline__
+#else
+#define GX_BLOCK_SYNC() ((void)0)
+#define GX_DEV inline
+#endif
+
+// Forward transform of NBUF buffers, natural order in, coefficient k left at
+// slot gx_fft_pos<L>(k).  On the device every thread of the block calls this
+// (it contains __syncthreads); the host-emulation build calls it with
+// nthreads == 1, which runs the passes sequentially.
+template <int L, int NBUF, int BUFSTRIDE>
+GX_DEV void gx_fft_dif(float2 *s, const float2 *tw, const int *tw_off, int tid, int nthreads)
+{
+    typedef GxSched<L> Sc;
+    constexpr int M = 1 << L;
+    gx_fft_pass<Sc::R0, M / Sc::R0, M, NBUF, BUFSTRIDE, false>(s, tw + tw_off[0], tid, nthreads);
+    GX_BLOCK_SYNC();
+    if constexpr (Sc::NP > 1) {
+        gx_fft_pass<Sc::R1, M / Sc::R0 / Sc::R1, M, NBUF, BUFSTRIDE, false>(s, tw + tw_off[1], tid, nthreads);
+        GX_BLOCK_SYNC();
+    }
+    if constexpr (Sc::NP > 2) {
+        gx_fft_pass<Sc::R2, M / Sc::R0 / Sc::R1 / Sc::R2, M, NBUF, BUFSTRIDE, false>(s, tw + tw_off[2], tid, nthreads);
+        GX_BLOCK_SYNC();
+    }
+    if constexpr (Sc::NP > 3) {
+        gx_fft_pass<Sc::R3, M / Sc::R0 / Sc::R1 / Sc::R2 / Sc::R3, M, NBUF, BUFSTRIDE, false>(s, tw + tw_off[3], tid, nthreads);
+        GX_BLOCK_SYNC();
+    }
+}
+
+// Forward transform taking its input in the slot order gx_fft_dif leaves
+// (value for index k at slot gx_fft_pos<L>(k)) and producing natural order.
+template <int L, int NBUF, int BUFSTRIDE>
+GX_DEV void gx_fft_dit(float2 *s, const float2 *tw, const int *tw_off, int tid, int nthreads)
+{
+    typedef GxSched<L> Sc;
+    constexpr int M = 1 << L;
+    if constexpr (Sc::NP > 3) {
+        gx_fft_pass<Sc::R3, M / Sc::R0 / Sc::R1 / Sc::R2 / Sc::R3, M, NBUF, BUFSTRIDE, true>(s, tw + tw_off[3], tid, nthreads);
+        GX_BLOCK_SYNC();
+    }
+    if constexpr (Sc::NP > 2) {
+        gx_fft_pass<Sc::R2, M / Sc::R0 / Sc::R1 / Sc::R2, M, NBUF, BUFSTRIDE, true>(s, tw + tw_off[2], tid, nthreads);
+        GX_BLOCK_SYNC();
+    }
+    if constexpr (Sc::NP > 1) {
+        gx_fft_pass<Sc::R1, M / Sc::R0 / Sc::R1, M, NBUF, BUFSTRIDE, true>(s, tw + tw_off[1], tid, nthreads);
+        GX_BLOCK_SYNC();
+    }
+    gx_fft_pass<Sc::R0, M / Sc::R0, M, NBUF, BUFSTRIDE, true>(s, tw + tw_off[0], tid, nthreads);
+    GX_BLOCK_SYNC();
+}
+
+// Length-N DFT (N == M for powers of two, Bluestein otherwise) of NBUF buffers.
+// Input: natural order in slots [0,N) -- for Bluestein the caller has already
+// multiplied element n by chirp[n] and zeroed slots [N,M).
+// Output: read coefficient k with gx_dft_result<L>().
+template <int L, int NBUF, int BUFSTRIDE>
+GX_DEV void gx_dft_block(float2 *s, const GxFftLayout &g, const float2 *plan, int tid, int nthreads)
+{
+    constexpr int M = 1 << L;
+    gx_fft_dif<L, NBUF, BUFSTRIDE>(s, plan, g.tw_off, tid, nthreads);
+    if (g.bluestein) {
+        // circular convolution with the conjugate chirp: multiply by its spectrum
+        // (stored in slot order, 1/M folded in), conjugate, transform again
+        // (ifft(v) = conj(fft(conj v))).  The DIT flavour consumes slot order
+        // directly, so nothing has to be permuted.
+        const float2 *bhat = plan + g.bhat_off;
+        for (int w = tid; w < NBUF * M; w += nthreads) {
+            const int buf = w / M, p = w - buf * M;
+            float2 *sb = s + buf * BUFSTRIDE;
+            sb[gx_phys(p)] = gx_conj(gx_cmul(sb[gx_phys(p)], bhat[p]));
+        }
+        GX_BLOCK_SYNC();
+        gx_fft_dit<L, NBUF, BUFSTRIDE>(s, plan, g.tw_off, tid, nthreads);
+    }
+}
+
+template <int L>
+GX_HD float2 gx_dft_result(const float2 *sb, const GxFftLayout &g, const float2 *plan, int k)
+{
+    if (g.bluestein) return gx_cmul(plan[g.chirp_off + k], gx_conj(sb[gx_phys(k)]));
+    return sb[gx_phys(gx_fft_pos<L>(k))];
+}

@@ -1,0 +1,502 @@
+"""Host orchestration of the two hot-path stages on one GPU.
+
+Stage A (`SliceEngine`): atoms -> per-phi projection -> |FFT|^2 -> 3-D binning
+(reference: tools/comparison.py:673-788, tools/voxelgrids.py:311-506).
+Stage B (`DetectorEngine`): rotated detector planes gathered from the voxel
+grid and summed over orientations (tools/comparison.py:790-870,
+tools/detector.py:194-300).
+
+PyTorch is used for device buffers, streams and host<->device copies only; all
+arithmetic on the path runs in the hand-written kernels behind the C ABI
+(giwaxsim_b200/_lib.py).  Every angle-dependent scalar is evaluated here with
+the same NumPy expressions the reference uses, so the integer indices derived
+on the device are bit-identical to the reference's.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+
+_checked_devices = set()
+
+
+def resolve_device(device=None):
+    """torch.device of the GPU to use; fails loudly when there is none."""
+    if device is None:
+        if not torch.cuda.is_available():
+            # let the library produce its own message (no CPU fallback)
+            call("gx_device_check", 0)
+        device = torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    if device.index not in _checked_devices:
+        call("gx_device_check", device.index)
+        _checked_devices.add(device.index)
+    return device
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(a, device, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(device, non_blocking=True)
+
+
+# ---------------------------------------------------------------------------
+# species coding
+# ---------------------------------------------------------------------------
+def encode_values(values, max_species=_lib.GX_MAX_SPECIES):
+    """Code an array with few distinct entries as uint8 without sorting it.
+    Returns (codes uint8 [A], uniques list) or (None, None) when there are more
+    than `max_species` distinct values."""
+    values = np.asarray(values)
+    A = values.shape[0]
+    codes = np.full(A, 255, dtype=np.uint8)
+    uniques = []
+    todo = np.ones(A, dtype=bool)
+    while True:
+        first = int(np.argmax(todo))
+        if not todo[first]:
+            break
+        if len(uniques) == max_species:
+            return None, None
+        v = values[first]
+        hit = values == v
+        codes[hit] = len(uniques)
+        uniques.append(v)
+        todo &= ~hit
+    return codes, uniques
+
+
+# ---------------------------------------------------------------------------
+# stage A
+# ---------------------------------------------------------------------------
+class FftPlan:
+    """Device copy of the twiddle / chirp table for one transform length."""
+
+    _cache = {}
+
+    def __init__(self, N, device):
+        nbytes = call("gx_fft_plan_bytes", int(N))
+        if nbytes < 0:
+            raise _lib.GxError(int(nbytes), _lib.last_error())
+        host = np.zeros(max(nbytes // 4, 2), dtype=np.float32)
+        call("gx_fft_plan_fill", int(N), ptr(host))
+        self.N = int(N)
+        self.table = _dev(host, device)
+
+    @classmethod
+    def get(cls, N, device):
+        key = (int(N), device.index)
+        if key not in cls._cache:
+            cls._cache[key] = cls(N, device)
+        return cls._cache[key]
+
+
+def stage_a_geometry(bounds, r_voxel_size, q_voxel_size, max_q):
+    """Scalar set-up of voxelgridmaker_fitting (tools/comparison.py:705-731),
+    same NumPy expressions.  bounds = (x_bound, y_bound, z_bound)."""
+    max_q_diag = np.sqrt(2) * max_q
+    if max_q_diag > 2 * np.pi / r_voxel_size:
+        raise Exception('Max_q is non-physical for given voxel size')
+    grid_size = int(np.ceil(2 * np.pi / (q_voxel_size * r_voxel_size)))
+    if grid_size * r_voxel_size < np.min(bounds):
+        raise Exception('Calculated real-space bounds smaller than simulation. Please lower delta_q value')
+    max_q_diag = max_q_diag + max_q_diag % q_voxel_size
+    q_num = ((2 * max_q_diag / q_voxel_size) + 1).astype(int)
+    if q_num % 2 == 0:
+        q_num += 1
+    q_axis = np.linspace(-max_q_diag, max_q_diag, q_num)
+    delta_phi_rad = np.arctan(q_voxel_size / max_q_diag)
+    phi_num = np.ceil(2 * np.pi / delta_phi_rad).astype(int)
+    phis = np.linspace(0, 180 - (180 / phi_num), num=phi_num)
+    return grid_size, int(q_num), q_axis, phis
+
+
+def chord_constants(phis, hor_length, ver_length):
+    """Per-rotation constants of rectangular_collapse_lengths
+    (tools/voxelgrids.py:253-285), called there as (x_vals, y_bound, x_bound, phi)."""
+    arr = (_lib.Chord * len(phis))()
+    for i, phi in enumerate(phis):
+        hor, ver = hor_length, ver_length
+        if phi > 90:
+            phi = phi - 90
+            hor, ver = ver, hor
+        theta_rad = np.deg2rad(90 - phi)
+        phi_rad = np.deg2rad(phi)
+        c = arr[i]
+        c.hor, c.ver = hor, ver
+        if phi == 0:
+            c.mode = 0
+            continue
+        if phi == 90:
+            c.mode = 1
+            continue
+        c.mode = 2
+        vcos = ver * np.cos(theta_rad)
+        stop1 = vcos
+        stop2 = hor * np.cos(phi_rad)
+        if stop1 < stop2:
+            mid = ver / np.sin(theta_rad)
+        else:
+            stop1, stop2 = stop2, stop1
+            mid = hor / np.sin(phi_rad)
+        c.stop1, c.stop2, c.stop12, c.mid = stop1, stop2, stop1 + stop2, mid
+        c.vcos = vcos
+        c.rise = np.sqrt(ver ** 2 - vcos ** 2)
+        c.tan_phi, c.tan_theta = np.tan(phi_rad), np.tan(theta_rad)
+        c.cos_phi, c.cos_theta = np.cos(phi_rad), np.cos(theta_rad)
+    return arr
+
+
+def gaussian_weights(sigma):
+    """scipy.ndimage._gaussian_kernel1d(sigma, 0, int(4*sigma+0.5))."""
+    radius = int(4.0 * float(sigma) + 0.5)
+    sigma2 = float(sigma) * float(sigma)
+    x = np.arange(-radius, radius + 1)
+    w = np.exp(-0.5 / sigma2 * x ** 2)
+    return w / w.sum(), radius
+
+
+class AtomSet:
+    """Device-resident slab: atoms sorted by z pixel row (phi-invariant)."""
+
+    def __init__(self, coords, r_voxel_size, grid_size, device, species=None, table=None, f_values=None):
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        if coords.ndim != 2 or coords.shape[1] != 3 or coords.shape[0] == 0:
+            raise ValueError("coords must be a non-empty [A,3] array")
+        self.device = device
+        self.A = int(coords.shape[0])
+        self.N = int(grid_size)
+        self.r = float(r_voxel_size)
+        st = _stream()
+        d_coords = _dev(coords, device)
+        mm = torch.empty(6, dtype=torch.float64, device=device)
+        call("gx_coords_minmax", ptr(d_coords), self.A, ptr(mm), st)
+        self.minmax = mm.cpu().numpy()
+        self.bounds = tuple(self.minmax[2 * k + 1] - self.minmax[2 * k] for k in range(3))
+        self.n_species = 0
+        d_species = d_f = None
+        self.species = self.f = self.table = None
+        if species is not None:
+            self.n_species = len(table)
+            d_species = _dev(species, device)
+            self.species = torch.empty(self.A, dtype=torch.uint8, device=device)
+            self.table = _dev(np.asarray(table, dtype=np.complex128).astype(np.complex64).view(np.float32), device)
+        else:
+            d_f = _dev(np.asarray(f_values, dtype=np.complex128).astype(np.complex64).view(np.float32), device)
+            self.f = torch.empty(2 * self.A, dtype=torch.float32, device=device)
+        self.xs = torch.empty(self.A, dtype=torch.float64, device=device)
+        self.ys = torch.empty(self.A, dtype=torch.float64, device=device)
+        self.perm = torch.empty(self.A, dtype=torch.int32, device=device)
+        self.row_start = torch.empty(self.N + 2, dtype=torch.int32, device=device)
+        cursor = torch.empty(self.N + 2, dtype=torch.int32, device=device)
+        call("gx_atoms_sort_rows", ptr(d_coords), self.A, float(self.minmax[4]), self.r, self.N,
+             ptr(d_species), ptr(d_f), ptr(self.xs), ptr(self.ys), ptr(self.perm),
+             ptr(self.species), ptr(self.f), ptr(self.row_start), ptr(cursor), st)
+
+
+class SliceEngine:
+    """Runs phi slices of one slab into sum/count accumulators on one GPU."""
+
+    def __init__(self, coords, r_voxel_size, q_axis, grid_size, avg_voxel_f, x_bound, y_bound,
+                 fill_bkg, smooth, species=None, table=None, f_values=None, device=None,
+                 count3d=False, accumulators=None, atoms=None):
+        self.device = resolve_device(device)
+        with torch.cuda.device(self.device):
+            self.N = int(grid_size)
+            self.r = float(r_voxel_size)
+            self.atoms = atoms if atoms is not None else AtomSet(
+                coords, r_voxel_size, grid_size, self.device, species, table, f_values)
+            self.plan = FftPlan.get(self.N, self.device)
+            self.fill_bkg = bool(fill_bkg)
+            self.sigma = int(smooth) if smooth else 0
+            self.x_bound, self.y_bound = x_bound, y_bound
+            self.avg_voxel_f = complex(avg_voxel_f)
+            # voxelgrids.py:344 and :358 / :365
+            self.max_voxels = np.sqrt(x_bound ** 2 + y_bound ** 2) // r_voxel_size
+            ped = avg_voxel_f * self.max_voxels
+            self.has_pedestal = self.fill_bkg or self.sigma > 0
+            self.pedestal = complex(ped) if self.has_pedestal else 0j
+            self.q_axis = np.asarray(q_axis, dtype=np.float64)
+            self.q_num = int(self.q_axis.shape[0])
+            self.qmin, self.qmax = float(np.min(self.q_axis)), float(np.max(self.q_axis))
+            self.dq = float(np.diff(self.q_axis)[0])
+            # voxelgrids.py:382-385 (phi-invariant row axis) and its bin indices
+            self.q_fft = np.fft.fftshift(np.fft.fftfreq(self.N, d=r_voxel_size) * 2 * np.pi)
+            self.q_fft_max = np.max(self.q_fft)
+            dev = self.device
+            st = _stream()
+            self.row_index = torch.empty(self.N, dtype=torch.int32, device=dev)
+            call("gx_axis_row_index", ptr(_dev(self.q_fft, dev)), self.N, self.qmin, self.qmax, self.dq,
+                 self.q_num, ptr(self.row_index), st)
+            if accumulators is not None:
+                self.vsum, self.count3, self.count2 = accumulators
+            else:
+                self.vsum = torch.zeros(self.q_num ** 3, dtype=torch.float32, device=dev)
+                self.count3 = torch.zeros(self.q_num ** 3, dtype=torch.int32, device=dev) if count3d else None
+                self.count2 = None if count3d else torch.zeros(self.q_num ** 2, dtype=torch.int32, device=dev)
+            self.row_hist = torch.zeros(self.q_num, dtype=torch.int32, device=dev)
+            call("gx_row_histogram", ptr(self.row_index), self.N, self.q_num, ptr(self.row_hist), st)
+            if self.sigma > 0:
+                w, self.gauss_radius = gaussian_weights(self.sigma)
+                self.gauss = _dev(w, dev)
+            else:
+                self.gauss, self.gauss_radius = None, 0
+            self.slices_done = 0
+
+    # -- per-batch host scalars -------------------------------------------
+    def _phi_scalars(self, phis):
+        phis = np.asarray(phis, dtype=np.float64)
+        phi_rad = np.radians(phis)                       # utilities.py:305
+        sn, cs = np.sin(phi_rad), np.cos(phi_rad)
+        neg = np.deg2rad(-phis)                          # voxelgrids.py:396-399
+        right_qy = self.q_fft_max * np.cos(neg)
+        right_qx = -self.q_fft_max * np.sin(neg)
+        return sn, cs, -right_qx, right_qx, -right_qy, right_qy
+
+    def batch_size(self, budget_bytes=4 << 30):
+        per = 20 * self.N * self.N
+        return int(max(1, min(64, budget_bytes // per)))
+
+    def prepare(self, phis):
+        """Device-side per-rotation tables for a batch: y range, bbox, row vectors,
+        column indices.  Returns a dict of tensors (kept alive by the caller)."""
+        dev, N, n = self.device, self.N, len(phis)
+        a = self.atoms
+        st = _stream()
+        sn, cs, xl, xr, yl, yr = self._phi_scalars(phis)
+        t = dict(n=n)
+        t["sin"], t["cos"] = _dev(sn, dev), _dev(cs, dev)
+        t["yrange"] = torch.empty(2 * n, dtype=torch.float64, device=dev)
+        call("gx_slice_yrange", ptr(a.xs), ptr(a.ys), a.A, ptr(t["sin"]), ptr(t["cos"]), n, ptr(t["yrange"]), st)
+        t["bbox"] = torch.empty(4 * n, dtype=torch.int32, device=dev)
+        scratch = torch.empty(n, dtype=torch.int32, device=dev)
+        call("gx_slice_bbox", ptr(a.xs), ptr(a.ys), ptr(a.row_start), N, self.r, ptr(t["sin"]), ptr(t["cos"]),
+             ptr(t["yrange"]), n, ptr(t["bbox"]), ptr(scratch), st)
+        t["base"] = torch.empty(2 * n * N, dtype=torch.float32, device=dev)
+        d_chord = None
+        if self.fill_bkg:
+            ch = chord_constants(phis, self.y_bound, self.x_bound)
+            host = np.frombuffer(ch, dtype=np.uint8).copy()
+            t["chord"] = _dev(host, dev)
+            d_chord = t["chord"]
+        if self.sigma > 0:
+            t["my"] = torch.empty(n * N, dtype=torch.float32, device=dev)
+            t["mz"] = torch.empty(n * N, dtype=torch.float32, device=dev)
+        call("gx_slice_vectors", ptr(d_chord), ptr(t["bbox"]), n, N, self.r, float(self.max_voxels),
+             self.avg_voxel_f.real, self.avg_voxel_f.imag, self.pedestal.real, self.pedestal.imag,
+             int(self.fill_bkg), self.sigma, ptr(self.gauss), self.gauss_radius,
+             ptr(t["base"]), ptr(t.get("my")), ptr(t.get("mz")), st)
+        t["col"] = torch.empty(n * N, dtype=torch.int32, device=dev)
+        call("gx_slice_col_index", ptr(_dev(xl, dev)), ptr(_dev(xr, dev)), ptr(_dev(yl, dev)), ptr(_dev(yr, dev)),
+             n, N, self.qmin, self.qmax, self.dq, self.q_num, ptr(t["col"]), st)
+        return t
+
+    def project(self, t, grid):
+        a = self.atoms
+        call("gx_project_slices", ptr(a.xs), ptr(a.ys), ptr(a.species), ptr(a.f), ptr(a.row_start),
+             ptr(a.table), a.n_species, ptr(t["sin"]), ptr(t["cos"]), ptr(t["yrange"]), ptr(t["bbox"]),
+             ptr(t["base"]), ptr(t.get("my")), ptr(t.get("mz")), t["n"], self.N, self.r,
+             self.pedestal.real, self.pedestal.imag, int(self.fill_bkg), self.sigma, ptr(grid), _stream())
+
+    def fft(self, grid, work, iq2d, n):
+        call("gx_fft2_abs2_shift", ptr(grid), ptr(work), ptr(iq2d), n, self.N, ptr(self.plan.table),
+             0.0, 0.0, _stream())
+
+    def bin(self, t, iq2d):
+        call("gx_bin_slices", ptr(iq2d), t["n"], self.N, self.N, ptr(t["col"]), self.N, ptr(self.row_index),
+             self.q_num, ptr(self.vsum), ptr(self.count3), ptr(self.count2), _stream())
+
+    def check_bbox(self, t):
+        bb = t["bbox"].cpu().numpy().reshape(-1, 4)
+        if (bb[:, 1] < 0).any():
+            # the reference's np.min on an empty selection (voxelgrids.py:346)
+            raise ValueError("zero-size array to reduction operation minimum which has no identity")
+        return bb
+
+    def run(self, phis, capture=None):
+        """Accumulate the given phi slices.  capture: optional dict receiving
+        host copies of the per-slice intermediates (parity probes)."""
+        phis = np.asarray(phis, dtype=np.float64)
+        with torch.cuda.device(self.device):
+            B = self.batch_size()
+            N, dev = self.N, self.device
+            nb = min(B, len(phis))
+            grid = torch.empty(nb * N * N * 2, dtype=torch.float32, device=dev)
+            work = torch.empty_like(grid)
+            iq2d = torch.empty(nb * N * N, dtype=torch.float32, device=dev)
+            for i0 in range(0, len(phis), B):
+                chunk = phis[i0:i0 + B]
+                t = self.prepare(chunk)
+                self.check_bbox(t)
+                self.project(t, grid)
+                self.fft(grid, work, iq2d, t["n"])
+                self.bin(t, iq2d)
+                if capture is not None:
+                    n = t["n"]
+                    capture.setdefault("bbox", []).append(t["bbox"].cpu().numpy().reshape(n, 4))
+                    capture.setdefault("yrange", []).append(t["yrange"].cpu().numpy().reshape(n, 2))
+                    capture.setdefault("col", []).append(t["col"].cpu().numpy().reshape(n, N))
+                    if capture.get("want_grids"):
+                        g = grid[:n * N * N * 2].cpu().numpy().view(np.complex64).reshape(n, N, N)
+                        capture.setdefault("grid", []).append(g.copy())
+                        capture.setdefault("iq_2d", []).append(iq2d[:n * N * N].cpu().numpy().reshape(n, N, N).copy())
+                self.slices_done += len(chunk)
+            torch.cuda.current_stream().synchronize()
+
+    def atom_indices(self, phi):
+        """(y_idx, z_idx) int64 of every atom in original order for one phi (probe)."""
+        with torch.cuda.device(self.device):
+            t = self.prepare(np.array([phi], dtype=np.float64))
+            a = self.atoms
+            sn, cs, *_ = self._phi_scalars(np.array([phi], dtype=np.float64))
+            shift = float(t["yrange"][0].item())
+            y = torch.empty(a.A, dtype=torch.int64, device=self.device)
+            z = torch.empty(a.A, dtype=torch.int64, device=self.device)
+            call("gx_atom_pixel_indices", ptr(a.xs), ptr(a.ys), ptr(a.perm), ptr(a.row_start), a.A, self.N,
+                 self.r, float(sn[0]), float(cs[0]), shift, ptr(y), ptr(z), _stream())
+            return y.cpu().numpy(), z.cpu().numpy(), t["bbox"].cpu().numpy()
+
+    def counts(self):
+        """Per-voxel sample counts as an int64 host array [q,q,q]."""
+        q = self.q_num
+        if self.count3 is not None:
+            return self.count3.cpu().numpy().astype(np.int64).reshape(q, q, q)
+        # rank-1 form: every slice shares the row table, so
+        # count[iy,ix,iz] = (kept columns that hit (iy,ix), all slices) * (rows that hit iz)
+        h = self.count2.cpu().numpy().astype(np.int64).reshape(q, q)
+        m = self.row_hist.cpu().numpy().astype(np.int64)
+        return h[:, :, None] * m[None, None, :]
+
+    def sums(self):
+        q = self.q_num
+        return self.vsum.cpu().numpy().reshape(q, q, q)
+
+
+CARBON_Z = 6.0
+CARBON_AFF = (2.31, 20.8439, 1.02, 10.2075, 1.5886, 0.5687, 0.865, 51.6512, 0.2156)
+
+
+def crop_range(axis, max_val):
+    """downselect_voxelgrid's index range (tools/voxelgrids.py:36-46)."""
+    lim = max_val + np.abs(axis[1] - axis[0])
+    idx = np.where(np.abs(axis) < lim)[0]
+    return int(idx[0]), int(idx[-1]) + 1
+
+
+def finalize_voxels(vsum, count3, count2, row_hist, q_axis, max_q, device):
+    """sum/count, crop, carbon f0 weighting -> (iq fp32 device [V,V,V], axis)."""
+    q_num = int(q_axis.shape[0])
+    lo, hi = crop_range(q_axis, max_q)
+    V = hi - lo
+    with torch.cuda.device(device):
+        iq = torch.empty(V * V * V, dtype=torch.float32, device=device)
+        aff = np.asarray(CARBON_AFF, dtype=np.float64)
+        d_axis = _dev(q_axis, device)
+        call("gx_voxel_finalize", ptr(vsum), ptr(count3), ptr(count2), ptr(row_hist), q_num, lo, hi,
+             ptr(d_axis), ptr(aff), CARBON_Z, ptr(iq), _stream())
+        torch.cuda.current_stream().synchronize()
+    return iq.view(V, V, V), q_axis[lo:hi].copy()
+
+
+# ---------------------------------------------------------------------------
+# stage B
+# ---------------------------------------------------------------------------
+def orientation_tables(corners, psis, psi_w, phis, phi_w, thetas, theta_w):
+    """Rotation matrices [O,3,9] and weights [O] for the psi x phi x theta
+    product, psi outermost (tools/comparison.py:836-841, detector.py:234-244)."""
+    psis, phis, thetas = (np.asarray(a, dtype=np.float64) for a in (psis, phis, thetas))
+    ang = np.stack(np.meshgrid(psis, phis, thetas, indexing="ij"), axis=-1).reshape(-1, 3)
+    rad = np.radians(ang)
+    cs = np.empty((ang.shape[0], 6), dtype=np.float64)
+    cs[:, 0::2] = np.cos(rad)
+    cs[:, 1::2] = np.sin(rad)
+    R = np.empty((ang.shape[0], 3, 9), dtype=np.float64)
+    corners = np.ascontiguousarray(corners, dtype=np.float64)
+    call("gx_host_orientation_matrices", ptr(corners), ptr(cs), int(ang.shape[0]), ptr(R))
+    pw, fw, tw = (np.asarray(a, dtype=np.float64) for a in (psi_w, phi_w, theta_w))
+    w = ((pw[:, None, None] * fw[None, :, None]) * tw[None, None, :]).reshape(-1)
+    return R, np.ascontiguousarray(w)
+
+
+def grid_corners(det_x, det_y, det_z):
+    """p[0,0], p[0,-1], p[-1,0] as rows (detector.py:58-60)."""
+    if isinstance(det_x, torch.Tensor):
+        g = torch.stack([det_x, det_y, det_z])
+        return torch.stack([g[:, 0, 0], g[:, 0, -1], g[:, -1, 0]]).cpu().numpy()
+    return np.array([[g[0, 0] for g in (det_x, det_y, det_z)],
+                     [g[0, -1] for g in (det_x, det_y, det_z)],
+                     [g[-1, 0] for g in (det_x, det_y, det_z)]], dtype=np.float64)
+
+
+class DetectorEngine:
+    """Voxel grid resident on the device + accumulation of detector images."""
+
+    def __init__(self, iq, qx, qy, qz, device=None):
+        self.device = resolve_device(device)
+        with torch.cuda.device(self.device):
+            if isinstance(iq, torch.Tensor):
+                self.iq = iq.to(self.device, torch.float32).contiguous()
+            else:
+                self.iq = _dev(np.asarray(iq), self.device, torch.float32).contiguous()
+        self.shape = tuple(int(s) for s in self.iq.shape)
+        qx, qy, qz = (np.asarray(a, dtype=np.float64) for a in (qx, qy, qz))
+        self.mins = (float(np.min(qx)), float(np.min(qy)), float(np.min(qz)))
+        self.dq = float(np.diff(qz)[0])               # detector.py:213
+
+    def accumulate(self, det_x, det_y, det_z, R, w, image=None, probe=-1):
+        """image[P,P] (fp64, device) += sum_o w_o * iq[voxel(R_o p)]."""
+        dev = self.device
+        with torch.cuda.device(dev):
+            shape = det_x.shape
+            n_pix = int(np.prod(shape))
+            px, py, pz = (g if isinstance(g, torch.Tensor) else _dev(np.asarray(g, dtype=np.float64), dev)
+                          for g in (det_x, det_y, det_z))
+            if image is None:
+                image = torch.zeros(n_pix, dtype=torch.float64, device=dev)
+            index = torch.empty(n_pix, dtype=torch.int64, device=dev) if probe >= 0 else None
+            d_R, d_w = _dev(R, dev), _dev(w, dev)
+            Vy, Vx, Vz = self.shape
+            call("gx_detector_accumulate", ptr(self.iq), Vy, Vx, Vz, self.mins[0], self.mins[1], self.mins[2],
+                 self.dq, ptr(px), ptr(py), ptr(pz), n_pix, ptr(d_R), ptr(d_w), int(len(w)),
+                 ptr(image), int(probe), ptr(index), _stream())
+            torch.cuda.current_stream().synchronize()
+        return image, index
+
+
+def rotate_points(R, gx, gy, gz, device=None):
+    """R @ [x;y;z] on the device with the reference's fma chain.  NumPy grids in
+    -> NumPy grids out; device tensors in -> device tensors out."""
+    dev = resolve_device(device)
+    on_device = isinstance(gx, torch.Tensor)
+    shape = tuple(gx.shape)
+    with torch.cuda.device(dev):
+        if on_device:
+            src = [g.contiguous().view(-1) for g in (gx, gy, gz)]
+        else:
+            src = [_dev(np.asarray(g, dtype=np.float64).ravel(), dev) for g in (gx, gy, gz)]
+        out = [torch.empty_like(s) for s in src]
+        Rh = np.ascontiguousarray(R, dtype=np.float64)
+        call("gx_rotate_points", ptr(Rh), ptr(src[0]), ptr(src[1]), ptr(src[2]), int(src[0].numel()),
+             ptr(out[0]), ptr(out[1]), ptr(out[2]), _stream())
+        if on_device:
+            return tuple(o.view(shape) for o in out)
+        return tuple(o.cpu().numpy().reshape(shape) for o in out)
+
+
+def detector_epilogue(image, rows, cols, mirror, device, finish=True):
+    with torch.cuda.device(device):
+        out = torch.empty(rows * cols, dtype=torch.float64, device=device)
+        call("gx_detector_epilogue", ptr(image), int(rows), int(cols), int(bool(mirror)), int(bool(finish)),
+             ptr(out), _stream())
+        torch.cuda.current_stream().synchronize()
+    return out.view(rows, cols)

@@ -1,0 +1,128 @@
+"""Drop-in for the two pipeline drivers of the reference's tools/comparison.py.
+
+    voxelgridmaker_fitting   comparison.py:673-788   (stage A)
+    detectormaker_fitting    comparison.py:790-870   (stage B)
+
+Same signatures, return types (float64 NumPy arrays) and exceptions.  When
+torch.distributed is initialised with more than one rank, phi slices (stage A)
+and detector orientations (stage B) are sharded across ranks and the partial
+grids / images are combined with an all-reduce (NCCL over NVLink on GPUs), so
+every rank returns the full result.
+"""
+import numpy as np
+import torch
+
+from .. import engine, parallel
+from .detector import rotate_about_horizontal, rotate_about_normal, rotate_about_vertical
+from .utilities import ATOMIC_NUMBER, get_element_f1_f2_dict
+
+# device copy of the last voxel grid returned by voxelgridmaker_fitting, so a
+# following detectormaker_fitting(iq, ...) on the same array skips the upload
+_resident = {"host": None, "device": None}
+
+
+def species_table(elements, energy):
+    """(codes uint8 [A] or None, unique elements, complex f per unique element):
+    f = Z + f' + i f'' (comparison.py:735-739)."""
+    elements = np.asarray(elements)
+    codes, uniq = engine.encode_values(elements)
+    if codes is None:
+        uniq = list(np.unique(elements))
+    f1f2 = get_element_f1_f2_dict(energy, [str(e) for e in uniq])
+    table = [complex(f1f2[str(e)]) + ATOMIC_NUMBER[str(e)] for e in uniq]
+    return codes, uniq, table
+
+
+def voxelgridmaker_fitting(coords, elements, r_voxel_size, q_voxel_size, max_q, energy, num_cpus=None,
+                           fill_bkg=False, smooth=0, phis=None, return_state=False):
+    """3-D I(q) voxel grid of a slab by the projection-slice method.
+
+    Returns (iq[y,x,z], qx, qy, qz) as float64 arrays.  `num_cpus` is accepted
+    and ignored, as in the reference.  Extra keyword `phis` overrides the
+    reference-derived rotation list (benchmarks); `return_state` also returns
+    the engine (parity probes).
+    """
+    dev = engine.resolve_device()
+    coords = np.asarray(coords, dtype=np.float64)
+    # grid size first (needed to sort atoms by pixel row); bounds come back from the device
+    max_q_diag = np.sqrt(2) * max_q
+    if max_q_diag > 2 * np.pi / r_voxel_size:
+        raise Exception('Max_q is non-physical for given voxel size')
+    grid_size = int(np.ceil(2 * np.pi / (q_voxel_size * r_voxel_size)))
+    codes, uniq, table = species_table(elements, energy)
+    with torch.cuda.device(dev):
+        if codes is not None:
+            atoms = engine.AtomSet(coords, r_voxel_size, grid_size, dev, species=codes, table=table)
+            sum_f = np.sum(np.bincount(codes, minlength=len(table)) * np.asarray(table))
+        else:
+            lut = dict(zip([str(e) for e in uniq], table))
+            f_values = np.array([lut[str(e)] for e in elements], dtype=complex)
+            atoms = engine.AtomSet(coords, r_voxel_size, grid_size, dev, f_values=f_values)
+            sum_f = np.sum(f_values)
+    x_bound, y_bound, z_bound = atoms.bounds
+    grid_size, q_num, q_axis, ref_phis = engine.stage_a_geometry(atoms.bounds, r_voxel_size, q_voxel_size, max_q)
+    if phis is None:
+        phis = ref_phis
+    avg_voxel_f = (sum_f / (x_bound * y_bound * z_bound)) * r_voxel_size ** 3     # comparison.py:742-744
+    eng = engine.SliceEngine(None, r_voxel_size, q_axis, grid_size, avg_voxel_f, x_bound, y_bound,
+                             fill_bkg, smooth, device=dev, atoms=atoms)
+    rank, world = parallel.rank_world()
+    eng.run(parallel.shard(np.asarray(phis, dtype=np.float64), rank, world))
+    if world > 1:
+        parallel.all_reduce_sum([eng.vsum, eng.count2])
+    iq_dev, axis = engine.finalize_voxels(eng.vsum, None, eng.count2, eng.row_hist, q_axis, max_q, dev)
+    iq = iq_dev.cpu().to(torch.float64).numpy()
+    _resident["host"], _resident["device"] = iq, iq_dev
+    out = (iq, axis.copy(), axis.copy(), axis.copy())
+    return out + (eng,) if return_state else out
+
+
+def detector_base_device(num_pixels, max_q, angle_init_vals, angle_init_axs, dev):
+    """make_detector + the optional init rotations (comparison.py:798-818) with
+    the three coordinate grids kept on the device."""
+    h = np.linspace(-max_q, max_q, num_pixels)
+    v = np.linspace(-max_q, max_q, num_pixels)
+    with torch.cuda.device(dev):
+        dh, dv = engine._dev(h, dev), engine._dev(v, dev)
+        gy = dh.view(1, -1).expand(num_pixels, num_pixels).contiguous()
+        gz = dv.view(-1, 1).expand(num_pixels, num_pixels).contiguous()
+        gx = torch.zeros_like(gy)
+    rot = {"psi": rotate_about_normal, "phi": rotate_about_vertical, "theta": rotate_about_horizontal}
+    for val, ax in zip(angle_init_vals, angle_init_axs):
+        if ax in rot:
+            gx, gy, gz = rot[ax](gx, gy, gz, val)
+    return gx, gy, gz, h, v
+
+
+def detectormaker_fitting(iq, qx, qy, qz, num_pixels, max_q, angle_init_vals, angle_init_axs, psis,
+                          psi_weights_path, phis, phi_weights_path, thetas, theta_weights_path, mirror=True):
+    """2-D detector image summed over psi x phi x theta orientations.
+    Returns (det_sum[v,h], det_h, det_v) as float64 arrays."""
+    dev = engine.resolve_device()
+    gx, gy, gz, det_h, det_v = detector_base_device(num_pixels, max_q, angle_init_vals, angle_init_axs, dev)
+
+    psi_weights = np.load(psi_weights_path) if psi_weights_path else np.ones_like(psis) / len(psis)
+    phi_weights = np.load(phi_weights_path) if phi_weights_path else np.ones_like(phis) / len(phis)
+    theta_weights = np.load(theta_weights_path) if theta_weights_path else np.ones_like(thetas) / len(thetas)
+    assert len(psis) == len(psi_weights), 'psi weights length must equal psi_num'
+    assert len(phis) == len(phi_weights), 'phi weights length must equal phi_num'
+    assert len(thetas) == len(theta_weights), 'theta weights length must equal theta_num'
+    assert np.abs(1 - np.sum(psi_weights)) < 0.01, 'psi weights must sum to 1'
+    assert np.abs(1 - np.sum(phi_weights)) < 0.01, 'phi weights must sum to 1'
+    assert np.abs(1 - np.sum(theta_weights)) < 0.01, 'theta weights must sum to 1'
+
+    grid = _resident["device"] if (iq is _resident["host"] and _resident["device"] is not None
+                                   and _resident["device"].device == dev) else iq
+    det = engine.DetectorEngine(grid, qx, qy, qz, device=dev)
+    R, w = engine.orientation_tables(engine.grid_corners(gx, gy, gz), psis, psi_weights, phis, phi_weights,
+                                     thetas, theta_weights)
+    rank, world = parallel.rank_world()
+    sel = parallel.shard(np.arange(len(w)), rank, world)
+    with torch.cuda.device(dev):
+        image = torch.zeros(num_pixels * num_pixels, dtype=torch.float64, device=dev)
+    if len(sel):
+        det.accumulate(gx, gy, gz, np.ascontiguousarray(R[sel]), np.ascontiguousarray(w[sel]), image=image)
+    if world > 1:
+        parallel.all_reduce_sum([image])
+    out = engine.detector_epilogue(image, num_pixels, num_pixels, mirror, dev, finish=True)
+    return out.cpu().numpy(), det_h, det_v

@@ -1,0 +1,140 @@
+"""Helpers the hot-path entry points share: device "shared arrays" standing in
+for the reference's POSIX shared-memory accumulators, the scattering-factor
+lookup hook, and the axis-angle matrix.
+
+Reference: tools/utilities.py:222-245 (rotation_matrix), :342-366
+(get_element_f1_f2_dict), :378-398 (create_shared_array).
+"""
+import uuid
+
+import numpy as np
+import torch
+
+ATOMIC_NUMBER = {
+    'H': 1, 'He': 2, 'Li': 3, 'Be': 4, 'B': 5, 'C': 6, 'N': 7, 'O': 8, 'F': 9, 'Ne': 10, 'Na': 11,
+    'Mg': 12, 'Al': 13, 'Si': 14, 'P': 15, 'S': 16, 'Cl': 17, 'Ar': 18, 'K': 19, 'Ca': 20, 'Sc': 21,
+    'Ti': 22, 'V': 23, 'Cr': 24, 'Mn': 25, 'Fe': 26, 'Co': 27, 'Ni': 28, 'Cu': 29, 'Zn': 30, 'Ga': 31,
+    'Ge': 32, 'As': 33, 'Se': 34, 'Br': 35, 'Kr': 36, 'Rb': 37, 'Sr': 38, 'Y': 39, 'Zr': 40, 'Nb': 41,
+    'Mo': 42, 'Tc': 43, 'Ru': 44, 'Rh': 45, 'Pd': 46, 'Ag': 47, 'Cd': 48, 'In': 49, 'Sn': 50, 'Sb': 51,
+    'Te': 52, 'I': 53, 'Xe': 54, 'Cs': 55, 'Ba': 56, 'La': 57, 'Ce': 58, 'Pr': 59, 'Nd': 60, 'Pm': 61,
+    'Sm': 62, 'Eu': 63, 'Gd': 64, 'Tb': 65, 'Dy': 66, 'Ho': 67, 'Er': 68, 'Tm': 69, 'Yb': 70, 'Lu': 71,
+    'Hf': 72, 'Ta': 73, 'W': 74, 'Re': 75, 'Os': 76, 'Ir': 77, 'Pt': 78, 'Au': 79, 'Hg': 80, 'Tl': 81,
+    'Pb': 82, 'Bi': 83, 'Po': 84, 'At': 85, 'Rn': 86, 'Fr': 87, 'Ra': 88, 'Ac': 89, 'Th': 90, 'Pa': 91,
+    'U': 92}
+
+# Cromer-Mann a1,b1,...,a4,b4,c (International Tables C, table 6.1.1.4) for the
+# light elements; the path itself only ever uses carbon (comparison.py:785).
+CROMER_MANN = {
+    'H': (0.489918, 20.6593, 0.262003, 7.74039, 0.196767, 49.5519, 0.049879, 2.20159, 0.001305),
+    'C': (2.31, 20.8439, 1.02, 10.2075, 1.5886, 0.5687, 0.865, 51.6512, 0.2156),
+    'N': (12.2126, 0.0057, 3.1322, 9.8933, 2.0125, 28.9975, 1.1663, 0.5826, -11.529),
+    'O': (3.0485, 13.2771, 2.2868, 5.7011, 1.5463, 0.3239, 0.867, 32.9089, 0.2508),
+}
+
+_f1f2_provider = None
+
+
+def set_f1f2_provider(fn):
+    """Install fn(element, energy_eV) -> (f', f'') used instead of xraydb."""
+    global _f1f2_provider
+    _f1f2_provider = fn
+
+
+def get_element_f1_f2_dict(energy, elements):
+    """{element: f' + i f''} for the distinct elements (utilities.py:342-366).
+    Uses xraydb's Chantler tables like the reference unless a provider was
+    installed with set_f1f2_provider (the test/bench harness does, because
+    xraydb is not vendored)."""
+    out = {}
+    provider = _f1f2_provider
+    if provider is None:
+        try:
+            import xraydb
+        except ImportError as e:
+            raise ImportError("xraydb is required for the f'/f'' lookup (or call "
+                              "giwaxsim_b200.tools.utilities.set_f1f2_provider)") from e
+
+        def provider(el, en):
+            return xraydb.f1_chantler(el, en), xraydb.f2_chantler(el, en)
+    for element in set(elements):
+        try:
+            f1, f2 = provider(element, energy)
+            out[element] = f1 + 1j * f2
+        except KeyError:
+            print(f"Data for element '{element}' at energy {energy} eV not found.")
+    return out
+
+
+def rotation_matrix(u, theta):
+    """Axis-angle (Rodrigues) matrix, operations associated as in
+    utilities.py:222-245 so the entries are bit-identical."""
+    ux, uy, uz = u[0], u[1], u[2]
+    c, s = np.cos(theta), np.sin(theta)
+    k = 1 - c
+    return np.array([[c + ux ** 2 * k, ux * uy * k - uz * s, ux * uz * k + uy * s],
+                     [uy * ux * k + uz * s, c + uy ** 2 * k, uy * uz * k - ux * s],
+                     [uz * ux * k - uy * s, uz * uy * k + ux * s, c + uz ** 2 * k]])
+
+
+# ---------------------------------------------------------------------------
+# device accumulators addressed by name
+# ---------------------------------------------------------------------------
+_registry = {}
+
+
+class DeviceSharedArray:
+    """Stand-in for multiprocessing.shared_memory.SharedMemory on the GPU.
+
+    The reference creates float64 POSIX shared-memory blocks and hands their
+    *names* to the workers (comparison.py:747-750, :835-841).  Here the name
+    keys a device tensor owned by this object; its dtype is chosen by the first
+    worker that uses it (fp32 intensity sums, int32 counts, fp64 detector
+    image).  `.buf` returns a float64 host snapshot so the reference idiom
+    `np.ndarray(shape, dtype=np.float64, buffer=shm.buf)` keeps working for
+    reading results.
+    """
+
+    def __init__(self, shape, name=None):
+        self.shape = tuple(int(s) for s in np.atleast_1d(shape))
+        self.name = name or uuid.uuid4().hex[:29]
+        self.size = int(np.prod(self.shape)) * 8
+        self.tensor = None
+        self.aux = {}
+        _registry[self.name] = self
+
+    def device_tensor(self, dtype, device):
+        if self.tensor is None:
+            self.tensor = torch.zeros(int(np.prod(self.shape)), dtype=dtype, device=device)
+        elif self.tensor.dtype != dtype:
+            raise TypeError("shared array %s already holds %s, asked for %s"
+                            % (self.name, self.tensor.dtype, dtype))
+        return self.tensor
+
+    def to_numpy(self):
+        if self.tensor is None:
+            return np.zeros(self.shape, dtype=np.float64)
+        return self.tensor.detach().cpu().to(torch.float64).numpy().reshape(self.shape)
+
+    @property
+    def buf(self):
+        return memoryview(np.ascontiguousarray(self.to_numpy())).cast("B")
+
+    def close(self):
+        pass
+
+    def unlink(self):
+        _registry.pop(self.name, None)
+        self.tensor = None
+        self.aux = {}
+
+
+def create_shared_array(shape, name=None):
+    """utilities.py:378-398: zero-filled accumulator; here on the device."""
+    return DeviceSharedArray(shape, None)
+
+
+def lookup_shared_array(name):
+    try:
+        return _registry[name]
+    except KeyError:
+        raise FileNotFoundError("no device shared array named %r" % (name,)) from None

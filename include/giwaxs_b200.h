@@ -1,0 +1,220 @@
+/*
+ * giwaxs_b200 -- C ABI of the B200 (sm_100a) implementation of GIWAXSim's
+ * reciprocal-space hot path.
+ *
+ * The reference (tchaney97/giwaxsim) is pure Python; the interface this
+ * library replaces is the set of NumPy/SciPy calls inside
+ *   tools/voxelgrids.py:311-416  rotate_project_fft_coords   (one phi slice)
+ *   tools/voxelgrids.py:464-506  process_file2               (3-D binning)
+ *   tools/comparison.py:765-786  sum/count, crop, f0 weight  (finalise)
+ *   tools/detector.py:33-162     rotate_about_*              (plane rotation)
+ *   tools/detector.py:194-232    intersect_detector          (gather)
+ *   tools/detector.py:246-275    mirror_vertical_horizontal  (epilogue)
+ * and is bound from Python through ctypes (giwaxsim_b200/_lib.py; the stub a
+ * reference maintainer would add is shown in INTEGRATION.md).
+ *
+ * Conventions
+ *  - plain C: pointers, sizes and doubles only.  Pointers named d_* are
+ *    DEVICE pointers (the Python host passes torch tensor.data_ptr()); h_*
+ *    are host pointers.  `stream` is a cudaStream_t passed as void*
+ *    (NULL = legacy default stream).  Nothing here allocates device memory.
+ *  - every function returns GX_OK (0) or a negative GX_ERR_* code;
+ *    gx_last_error() returns a thread-local message for the last failure.
+ *  - angle-dependent scalars (sin, cos, linspace end points, chord-length
+ *    constants) are evaluated on the host with the same NumPy expressions the
+ *    reference uses and passed in as fp64, so that every integer index the
+ *    device derives is bit-identical to the reference's.
+ *  - there is no CPU fallback: without an sm_100 device every compute entry
+ *    point fails with GX_ERR_NO_DEVICE.
+ */
+#ifndef GIWAXS_B200_H
+#define GIWAXS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GX_ABI_VERSION 1
+
+#define GX_OK 0
+#define GX_ERR_INVALID (-1)     /* bad argument                              */
+#define GX_ERR_CUDA (-2)        /* CUDA runtime error (see gx_last_error)    */
+#define GX_ERR_UNSUPPORTED (-3) /* size outside what the kernels implement   */
+#define GX_ERR_NO_DEVICE (-4)   /* no sm_100 GPU visible                     */
+
+#define GX_MAX_SPECIES 16       /* distinct f-values on the counting path    */
+#define GX_FFT_MAX_LOG2 13      /* largest in-smem pow2 transform (8192)     */
+
+typedef struct gx_float2 { float x, y; } gx_float2;
+
+int gx_abi_version(void);
+const char *gx_last_error(void);
+/* GX_OK iff `device` exists, is compute capability 10.x and can run the
+ * embedded sm_100a image. */
+int gx_device_check(int device);
+
+/* ------------------------------------------------------------------ atoms */
+/* min/max of each coordinate column of an [A,3] fp64 array.
+ * d_out6 = {xmin,xmax,ymin,ymax,zmin,zmax}.      (comparison.py:712-714)   */
+int gx_coords_minmax(const double *d_coords, int64_t A, double *d_out6, void *stream);
+
+/* z pixel row of every atom (phi-invariant) and a counting sort by row.
+ *   z_idx = (z - z_min) // r ; rows >= N are "invalid" and sort last.
+ * Outputs: d_xs,d_ys [A] coordinates in row order; d_perm [A] original index
+ * of each sorted atom; d_species_out/d_f_out the permuted per-atom species
+ * code / complex64 f (either input may be NULL); d_row_start [N+2] with
+ * row_start[z]..row_start[z+1] the atoms of row z and row_start[N+1] == A.
+ * d_cursor is scratch of N+2 int32.          (voxelgrids.py:324,329,332)   */
+int gx_atoms_sort_rows(const double *d_coords, int64_t A, double z_min, double r, int N,
+                       const uint8_t *d_species, const gx_float2 *d_f,
+                       double *d_xs, double *d_ys, int32_t *d_perm,
+                       uint8_t *d_species_out, gx_float2 *d_f_out,
+                       int32_t *d_row_start, int32_t *d_cursor, void *stream);
+
+/* min and max over all atoms of y' = fma(y, cos, x*sin) for n_phi rotations.
+ * d_yrange [n_phi][2].                   (utilities.py:303-317, vg.py:323) */
+int gx_slice_yrange(const double *d_xs, const double *d_ys, int64_t A,
+                    const double *d_sin, const double *d_cos, int n_phi,
+                    double *d_yrange, void *stream);
+
+/* index bounding box {y_min,y_max,z_min,z_max} of the valid atoms of every
+ * rotation; -1 entries when no atom is valid.  d_scratch: n_phi int32.
+ *                                                        (vg.py:332-349)   */
+int gx_slice_bbox(const double *d_xs, const double *d_ys, const int32_t *d_row_start, int N,
+                  double r, const double *d_sin, const double *d_cos, const double *d_yrange,
+                  int n_phi, int32_t *d_bbox, int32_t *d_scratch, void *stream);
+
+/* per-atom pixel indices of ONE rotation in the ORIGINAL atom order (parity
+ * probe T1): y_idx, z_idx as the reference's astype(int) values.           */
+int gx_atom_pixel_indices(const double *d_xs, const double *d_ys, const int32_t *d_perm,
+                          const int32_t *d_row_start, int64_t A, int N, double r,
+                          double sin_phi, double cos_phi, double y_shift,
+                          int64_t *d_y_idx, int64_t *d_z_idx, void *stream);
+
+/* ------------------------------------------------ per-slice row vectors  */
+/* chord-length constants of rectangular_collapse_lengths (vg.py:253-285),
+ * evaluated on the host per rotation. */
+typedef struct gx_chord {
+    double hor, ver;          /* after the phi>90 swap                     */
+    double stop1, stop2, stop12, mid;
+    double vcos, rise, tan_phi, tan_theta, cos_phi, cos_theta;
+    int32_t mode;             /* 0: phi==0, 1: phi==90, 2: general         */
+    int32_t pad;
+} gx_chord;
+
+/* Builds, for n_phi rotations, the three length-N vectors the row kernel
+ * consumes:
+ *   d_base [n_phi][N] complex64 = num_missing[y]*avg_f - pedestal
+ *                                 (or -pedestal when !fill_bkg)
+ *   d_my, d_mz [n_phi][N] fp32  = Gaussian-smoothed box masks (smooth>0)
+ * h_gauss: host array of 2*radius+1 fp64 weights (scipy _gaussian_kernel1d).
+ *                                                   (vg.py:344-379)        */
+int gx_slice_vectors(const gx_chord *d_chord, const int32_t *d_bbox, int n_phi, int N, double r,
+                     double max_voxels, double avg_f_re, double avg_f_im,
+                     double pedestal_re, double pedestal_im,
+                     int fill_bkg, int smooth_sigma, const double *d_gauss, int gauss_radius,
+                     gx_float2 *d_base, float *d_my, float *d_mz, void *stream);
+
+/* ------------------------------------------------------ projection (K1)  */
+/* Scatter + background + edge blend for n_phi rotations; one CTA per
+ * (rotation,row), atoms counted per species in shared memory.
+ * d_table: species f-values (complex64, n_species <= GX_MAX_SPECIES), or
+ * n_species == 0 to use per-atom d_f (generic path).
+ * d_grid [n_phi][N][N] complex64 receives the reference's pre-FFT grid
+ * (rows = z, cols = y).                               (vg.py:338-379)      */
+int gx_project_slices(const double *d_xs, const double *d_ys, const uint8_t *d_species,
+                      const gx_float2 *d_f, const int32_t *d_row_start,
+                      const gx_float2 *d_table, int n_species,
+                      const double *d_sin, const double *d_cos, const double *d_yrange,
+                      const int32_t *d_bbox, const gx_float2 *d_base, const float *d_my,
+                      const float *d_mz, int n_phi, int N, double r,
+                      double pedestal_re, double pedestal_im, int fill_bkg, int smooth_sigma,
+                      gx_float2 *d_grid, void *stream);
+
+/* ------------------------------------------------------------- FFT (K2)  */
+/* Size in bytes of the plan table for transform length N (any N with
+ * 16 <= N, pow2 up to 8192 or Bluestein with 2N-1 <= 8192); <0 on error.   */
+int64_t gx_fft_plan_bytes(int N);
+/* Fill a HOST buffer of gx_fft_plan_bytes(N) bytes (twiddles, chirp, filter
+ * spectrum; all computed in fp64, stored fp32).  Copy it to the device and
+ * pass that pointer as d_plan below. */
+int gx_fft_plan_fill(int N, void *h_plan);
+
+/* |fftshift(fft2(grid))|^2 for `batch` N x N complex64 grids -> fp32.
+ * d_work: batch*N*N complex64 scratch.  dc_re/dc_im is added to the
+ * unshifted (0,0) coefficient before squaring (pedestal * N^2), or 0.
+ *                                                     (vg.py:388-392)      */
+int gx_fft2_abs2_shift(const gx_float2 *d_grid, gx_float2 *d_work, float *d_iq2d,
+                       int batch, int N, const void *d_plan, double dc_re, double dc_im,
+                       void *stream);
+
+/* ---------------------------------------------------------- binning (K3) */
+/* Column / row voxel indices of a slice.  Column j has
+ *   qx = linspace(qx_left, qx_right, N)[j], qy likewise (NumPy rounding);
+ * kept iff qmin <= q <= qmax on both; index = (q - qmin) // dq.
+ * d_col [n_phi][N] packs iy*q_num+ix, or -1 if masked.  (vg.py:396-401,475) */
+int gx_slice_col_index(const double *d_qx_left, const double *d_qx_right,
+                       const double *d_qy_left, const double *d_qy_right, int n_phi, int N,
+                       double qmin, double qmax, double dq, int q_num, int32_t *d_col, void *stream);
+/* Same from explicit axis values (process_file2's det_h_qx / det_h_qy).    */
+int gx_axis_col_index(const double *d_qx, const double *d_qy, int n, double qmin, double qmax,
+                      double dq, int q_num, int32_t *d_col, void *stream);
+/* Row index iz (or -1) from explicit qz values (det_v_qz).  (vg.py:476,499) */
+int gx_axis_row_index(const double *d_qz, int n, double qmin, double qmax, double dq, int q_num,
+                      int32_t *d_row, void *stream);
+
+/* Accumulate `batch` slices: sum[iy,ix,iz] += I ; and either the full 3-D
+ * count (d_count3 != NULL) or the rank-1 factor H[iy,ix] += 1 per kept
+ * column (d_count2 != NULL; the row factor is gx_row_histogram).
+ *                                                     (vg.py:484-503)      */
+int gx_bin_slices(const float *d_iq2d, int batch, int rows, int cols,
+                  const int32_t *d_col, int col_stride, const int32_t *d_row, int q_num,
+                  float *d_sum, uint32_t *d_count3, uint32_t *d_count2, void *stream);
+int gx_row_histogram(const int32_t *d_row, int n, int q_num, uint32_t *d_m, void *stream);
+
+/* iq = sum/count (0 where count == 0), cropped to [lo,hi)^3, times
+ * ((sum_i a_i exp(-b_i q^2/16pi^2) + c)/Z)^2.  count = count3, or
+ * count2[iy,ix]*m[iz] when d_count3 is NULL.  d_axis [q_num] fp64 voxel axis.
+ * d_iq [(hi-lo)^3] fp32.     (comparison.py:769-786, vg.py:16-48,828-857)  */
+int gx_voxel_finalize(const float *d_sum, const uint32_t *d_count3, const uint32_t *d_count2,
+                      const uint32_t *d_m, int q_num, int lo, int hi, const double *d_axis,
+                      const double *h_aff9, double Z, float *d_iq, void *stream);
+
+/* --------------------------------------------------------- detector (K4) */
+/* p <- R p for n points, R row-major 3x3, fma chain k=0,1,2.
+ *                                                  (detector.py:71,113,155) */
+int gx_rotate_points(const double *h_R9, const double *d_x, const double *d_y, const double *d_z,
+                     int64_t n, double *d_ox, double *d_oy, double *d_oz, void *stream);
+
+/* For every pixel and each of n_orient orientations: three sequential
+ * rotations (d_R [n_orient][3][9]), floor-bin to the voxel grid, clamp,
+ * gather, weight, accumulate into d_image (fp64, += semantics).
+ * d_iq [Vy][Vx][Vz] fp32.  d_index_out (optional) receives the clamped flat
+ * voxel index of every pixel for orientation `probe` (parity probe T7).
+ *                                       (detector.py:194-244, 289-298)     */
+int gx_detector_accumulate(const float *d_iq, int Vy, int Vx, int Vz,
+                           double qx_min, double qy_min, double qz_min, double dq,
+                           const double *d_px, const double *d_py, const double *d_pz, int64_t n_pix,
+                           const double *d_R, const double *d_w, int n_orient,
+                           double *d_image, int probe, int64_t *d_index_out, void *stream);
+
+/* Host helper: the three per-orientation rotation matrices, derived exactly
+ * as rotate_psi_phi_theta does from the current corner pixels.
+ * h_corners [3][3] = p[0,0], p[0,-1], p[-1,0] of the base detector;
+ * h_cs [n][6] = cos,sin of radians(psi), radians(phi), radians(theta)
+ * evaluated with NumPy; h_R [n][3][9].   (detector.py:58-68,104-110,146-152,
+ * utilities.py:222-245)                                                    */
+int gx_host_orientation_matrices(const double *h_corners, const double *h_cs, int n, double *h_R);
+
+/* mirror != 0: four-fold mirror with the odd-size centre rules
+ * (detector.py:246-275).  finish != 0: NaN/<=0 -> 1e-6, then *1e-6
+ * (comparison.py:859-868).  Out of place.                                  */
+int gx_detector_epilogue(const double *d_image, int rows, int cols, int mirror, int finish,
+                         double *d_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIWAXS_B200_H */

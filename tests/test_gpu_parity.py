@@ -1,0 +1,269 @@
+"""Parity of the CUDA path (through the C ABI) against the fixtures generated
+from the unmodified reference and against the CPU oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): atom pixel indices, q-bin indices and
+per-voxel counts BIT-EXACT; voxel-grid and detector intensities within 1e-4
+of the reference maximum (fp32 on the device).
+"""
+import numpy as np
+import pytest
+import torch
+
+from giwaxsim_b200 import engine
+from giwaxsim_b200.tools import comparison, detector, utilities, voxelgrids
+from oracle import giwaxs_oracle as ox
+
+pytestmark = pytest.mark.gpu
+
+TOL_GRID = 1e-5      # pre-FFT grid, relative to max |grid|
+TOL_INT = 1e-4       # intensities, relative to the reference maximum
+CASES = ["graphite262", "silicon256", "clipped128"]
+
+
+def _engine_for(g, count3d=False):
+    """SliceEngine on the fixture's slab with the reference-derived scalars."""
+    coords = g["coords"]
+    codes, uniq = engine.encode_values(g["f_values"])
+    b = g["bounds"]
+    return engine.SliceEngine(coords, float(g["r"]), g["q_axis"], int(g["grid_size"]), complex(g["avg_voxel_f"]),
+                              b[0], b[1], bool(g["fill_bkg"]), int(g["smooth"]), species=codes, table=uniq,
+                              count3d=count3d)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_T1_atom_pixel_indices_bit_exact(golden, name):
+    g = golden(name + ".npz")
+    eng = _engine_for(g)
+    N = int(g["grid_size"])
+    # bounds computed on the device equal NumPy's max - min
+    assert np.array_equal(np.array(eng.atoms.bounds), g["bounds"])
+    for i in g["probe"]:
+        y, z, bbox = eng.atom_indices(g["phis"][i])
+        ry, rz = g["y_idx_%d" % i], g["z_idx_%d" % i]
+        assert np.array_equal(y, ry)
+        assert np.array_equal(np.minimum(z, N), np.minimum(rz, N))
+        assert np.array_equal(bbox, g["bbox_%d" % i])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_T2_T3_T4_slice_intermediates(golden, name):
+    g = golden(name + ".npz")
+    eng = _engine_for(g)
+    N, q_num = int(g["grid_size"]), int(g["q_num"])
+    probe = [int(i) for i in g["probe"]]
+    cap = {"want_grids": True}
+    eng.run(g["phis"][probe], capture=cap)
+    grids, iqs, cols = cap["grid"][0], cap["iq_2d"][0], cap["col"][0]
+    row = eng.row_index.cpu().numpy()
+    for k, i in enumerate(probe):
+        ref_grid = g["grid_%d" % i]
+        err = np.abs(grids[k] - ref_grid).max() / float(g["grid_absmax_%d" % i])
+        assert err <= TOL_GRID, "pre-FFT grid slice %d: %.3g" % (i, err)
+        ref_iq = g["iq2d_%d" % i]
+        err = np.abs(iqs[k].astype(np.float64) - ref_iq).max() / float(g["iq2d_max_%d" % i])
+        assert err <= TOL_INT, "slice intensity %d: %.3g" % (i, err)
+        # q-bin indices: bit-exact
+        cm = g["colmask_%d" % i]
+        assert np.array_equal(cols[k] >= 0, cm)
+        assert np.array_equal(cols[k][cm], g["iy_%d" % i] * q_num + g["ix_%d" % i])
+        rm = g["rowmask_%d" % i]
+        assert np.array_equal(row >= 0, rm)
+        assert np.array_equal(row[rm], g["iz_%d" % i])
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("count3d", [False, True])
+def test_T5_accumulators(golden, name, count3d):
+    g = golden(name + ".npz")
+    eng = _engine_for(g, count3d=count3d)
+    eng.run(g["phis"])
+    assert np.array_equal(eng.counts(), g["vcnt"].astype(np.int64))          # bit-exact
+    err = np.abs(eng.sums().astype(np.float64) - g["vsum"]).max() / float(g["vsum_max"])
+    assert err <= TOL_INT, err
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_T6_voxelgridmaker_fitting(golden, name):
+    g = golden(name + ".npz")
+    iq, qx, qy, qz = comparison.voxelgridmaker_fitting(
+        g["coords"], g["elements"], float(g["r"]), float(g["q"]), float(g["max_q"]), float(g["energy"]),
+        fill_bkg=bool(g["fill_bkg"]), smooth=int(g["smooth"]))
+    assert iq.dtype == np.float64 and iq.shape == g["iq"].shape
+    for a in (qx, qy, qz):
+        assert np.array_equal(a, g["q_crop"])                                 # axes bit-exact
+    err = np.abs(iq - g["iq"]).max() / g["iq"].max()
+    assert err <= TOL_INT, err
+    assert np.array_equal(iq == 0, g["iq"] == 0)                              # empty voxels stay exactly 0
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_T7_detectormaker_fitting(golden, tag, tmp_path):
+    g = golden("detector.npz")
+    iq, q = g["iq"], g["q"]
+    P = int(g[tag + "_P"])
+    vals, axs = tuple(g[tag + "_vals"]), tuple(str(a) for a in g[tag + "_axs"])
+    paths = []
+    for k in ("_pw", "_fw", "_tw"):
+        p = str(tmp_path / (tag + k + ".npy"))
+        np.save(p, g[tag + k])
+        paths.append(p)
+    # base grids (make_detector + init rotations): bit-exact
+    gx, gy, gz, h, v = comparison.detector_base_device(P, float(g["max_q"]), vals, axs, engine.resolve_device())
+    for a, k in ((gx, "_gx"), (gy, "_gy"), (gz, "_gz")):
+        assert np.array_equal(a.cpu().numpy(), g[tag + k])
+    # per-orientation voxel indices: bit-exact
+    det = engine.DetectorEngine(iq, q, q, q)
+    R, w = engine.orientation_tables(engine.grid_corners(gx, gy, gz), g[tag + "_psis"], g[tag + "_pw"],
+                                     g[tag + "_phis"], g[tag + "_fw"], g[tag + "_thetas"], g[tag + "_tw"])
+    for o in g[tag + "_probes"]:
+        _, index = det.accumulate(gx, gy, gz, R, w, probe=int(o))
+        assert np.array_equal(index.cpu().numpy(), g["%s_index_%d" % (tag, o)])
+    raw, _ = det.accumulate(gx, gy, gz, R, w)
+    ref_raw = g[tag + "_raw"]
+    assert np.abs(raw.cpu().numpy().reshape(P, P) - ref_raw).max() <= TOL_INT * ref_raw.max()
+    out, dh, dv = comparison.detectormaker_fitting(iq, q, q, q, P, float(g["max_q"]), vals, axs, g[tag + "_psis"],
+                                                   paths[0], g[tag + "_phis"], paths[1], g[tag + "_thetas"],
+                                                   paths[2], mirror=bool(g[tag + "_mirror"]))
+    ref = g[tag + "_final"]
+    assert out.dtype == np.float64 and out.shape == ref.shape
+    assert np.abs(out - ref).max() <= TOL_INT * ref.max()
+    assert np.array_equal(dh, np.linspace(-float(g["max_q"]), float(g["max_q"]), P))
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_detector_module_functions(golden, tag):
+    """make_detector / rotate_about_* / intersect_detector / mirror as free functions."""
+    g = golden("detector.npz")
+    iq, q = g["iq"], g["q"]
+    P = int(g[tag + "_P"])
+    gx, gy, gz, h, v = detector.make_detector(float(g["max_q"]), P, float(g["max_q"]), P)
+    ox_base = ox.make_detector(float(g["max_q"]), P, float(g["max_q"]), P)
+    for a, b in zip((gx, gy, gz, h, v), ox_base):
+        assert np.array_equal(a, b)
+    rot = {"psi": detector.rotate_about_normal, "phi": detector.rotate_about_vertical,
+           "theta": detector.rotate_about_horizontal}
+    for val, ax in zip(g[tag + "_vals"], g[tag + "_axs"]):
+        if str(ax) in rot:
+            gx, gy, gz = rot[str(ax)](gx, gy, gz, float(val))
+    for a, k in ((gx, "_gx"), (gy, "_gy"), (gz, "_gz")):
+        assert np.array_equal(a, g[tag + k])
+    got = detector.intersect_detector(iq, q, q, q, gx, gy, gz)
+    ref = g[tag + "_intersect"]
+    assert np.abs(got - ref).max() <= 1e-6 * ref.max()          # fp32 copy of the same voxel
+    x2, y2, z2 = detector.rotate_psi_phi_theta(gx, gy, gz, 80.0, 33.0, 1.0)
+    ex = ox.rotate_psi_phi_theta(gx, gy, gz, 80.0, 33.0, 1.0)
+    assert all(np.array_equal(a, b) for a, b in zip((x2, y2, z2), ex))
+    m = detector.mirror_vertical_horizontal(g[tag + "_raw"])
+    assert np.abs(m - g[tag + "_mirrored"]).max() <= 1e-15 * g[tag + "_mirrored"].max()
+
+
+def test_worker_api_rotate_project_fft_coords(golden):
+    """The reference's per-slice worker signature with named accumulators."""
+    g = golden("clipped128.npz")
+    b = g["bounds"]
+    q_axis, q_num = g["q_axis"], int(g["q_num"])
+    shm_sum = utilities.create_shared_array((q_num,) * 3)
+    shm_cnt = utilities.create_shared_array((q_num,) * 3)
+    coords, f = g["coords"], g["f_values"]
+    phis = g["phis"][::9]
+    for phi in phis:
+        voxelgrids.rotate_project_fft_coords(
+            (coords, f, phi, int(g["grid_size"]), float(g["r"]), complex(g["avg_voxel_f"]), b[0], b[1], b[2],
+             bool(g["fill_bkg"]), int(g["smooth"]), q_axis, q_axis, q_axis, shm_sum.name, shm_cnt.name))
+    got_sum = np.ndarray((q_num,) * 3, dtype=np.float64, buffer=shm_sum.buf)
+    got_cnt = np.ndarray((q_num,) * 3, dtype=np.float64, buffer=shm_cnt.buf)
+    setup = ox.stage_a_setup(coords, f, float(g["r"]), float(g["q"]), float(g["max_q"]))
+    vsum, vcnt = np.zeros((q_num,) * 3), np.zeros((q_num,) * 3)
+    for phi in phis:
+        ox.run_slice(vsum, vcnt, coords, setup, float(g["r"]), phi, bool(g["fill_bkg"]), int(g["smooth"]))
+    assert np.array_equal(got_cnt, vcnt)
+    assert np.abs(got_sum - vsum).max() <= TOL_INT * vsum.max()
+    shm_sum.close(); shm_sum.unlink(); shm_cnt.close(); shm_cnt.unlink()
+
+
+def test_worker_api_process_file2_and_finalisers():
+    rng = np.random.default_rng(9)
+    N, q_num = 96, 31
+    q_axis = np.linspace(-1.55, 1.55, q_num)
+    iq_2d = rng.random((N, N)) * 1e5
+    hx = np.linspace(-1.1, 1.1, N)
+    hy = np.linspace(-1.9, 1.9, N)
+    vz = ox.fft_q_axis(N, 1.4)
+    shm_sum = utilities.create_shared_array((q_num,) * 3)
+    shm_cnt = utilities.create_shared_array((q_num,) * 3)
+    for _ in range(2):
+        voxelgrids.process_file2(iq_2d, hx, hy, vz, q_axis, q_axis, q_axis, shm_sum.name, shm_cnt.name)
+    vsum, vcnt = np.zeros((q_num,) * 3), np.zeros((q_num,) * 3)
+    for _ in range(2):
+        ox.bin_slice(vsum, vcnt, iq_2d, hx, hy, vz, q_axis)
+    assert np.array_equal(shm_cnt.to_numpy(), vcnt)
+    assert np.abs(shm_sum.to_numpy() - vsum).max() <= 1e-6 * vsum.max()
+    small, ax, ay, az = voxelgrids.downselect_voxelgrid(vsum, q_axis, q_axis, q_axis, 1.0)
+    lo, hi = ox.crop_range(q_axis, 1.0)
+    assert np.array_equal(small, vsum[lo:hi, lo:hi, lo:hi]) and np.array_equal(ax, q_axis[lo:hi])
+    got = voxelgrids.add_f0_q_3d(small, ax, ay, az, "C")
+    ref = small * ox.carbon_f0_factor(ax, ay, az)
+    assert np.abs(got - ref).max() <= 1e-6 * ref.max()
+
+
+def test_worker_api_generate_detector_ints(golden):
+    g = golden("detector.npz")
+    iq, q = g["iq"], g["q"]
+    P = 40
+    gx, gy, gz, _, _ = ox.detector_base(P, 2.0, (90.0, 90.0, 90.0), ("psi", "phi", "psi"))
+    shm = utilities.create_shared_array((P, P))
+    todo = [(80.0, 0.3, 10.0, 0.5, 0.0, 1.0), (90.0, 0.7, 100.0, 0.5, 1.0, 1.0)]
+    ref = np.zeros((P, P))
+    for psi, wp, phi, wf, theta, wt in todo:
+        detector.generate_detector_ints((iq, q, q, q, gx, gy, gz, psi, wp, phi, wf, theta, wt, shm.name))
+        part = ox.intersect_detector(iq, q, q, q, *ox.rotate_psi_phi_theta(gx, gy, gz, psi, phi, theta))
+        ref += part * (wp * wf * wt)
+    got = np.ndarray((P, P), dtype=np.float64, buffer=shm.buf)
+    assert np.abs(got - ref).max() <= 1e-6 * ref.max()
+    shm.unlink()
+
+
+@pytest.mark.parametrize("N", [16, 64, 100, 256, 262, 1024])
+def test_fft2_abs2_shift_against_numpy(N):
+    """K2 alone on random complex grids with a pedestal, pow2 and Bluestein sizes."""
+    from giwaxsim_b200._lib import call, ptr
+    dev = engine.resolve_device()
+    rng = np.random.default_rng(N)
+    batch = 3
+    x = (rng.normal(size=(batch, N, N)) + 1j * rng.normal(size=(batch, N, N)) + 5.0).astype(np.complex64)
+    plan = engine.FftPlan.get(N, dev)
+    d_x = torch.from_numpy(x.view(np.float32)).to(dev)
+    work = torch.empty_like(d_x)
+    out = torch.empty(batch * N * N, dtype=torch.float32, device=dev)
+    call("gx_fft2_abs2_shift", ptr(d_x), ptr(work), ptr(out), batch, N, ptr(plan.table), 0.0, 0.0, None)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().reshape(batch, N, N).astype(np.float64)
+    for b in range(batch):
+        ref = np.abs(np.fft.fftshift(np.fft.fftn(x[b].astype(np.complex128)))) ** 2
+        assert np.abs(got[b] - ref).max() <= TOL_INT * ref.max()
+        # away from the DC peak the error budget is much tighter in practice
+        off = ref < 1e-3 * ref.max()
+        assert np.abs(got[b] - ref)[off].max() <= 1e-4 * ref[off].max()
+
+
+def test_random_slab_against_oracle_many_species_and_generic_path():
+    """Seeded random slab: counting path (5 species) and the generic per-atom-f
+    path (> GX_MAX_SPECIES distinct values) against the oracle."""
+    rng = np.random.default_rng(77)
+    A = 5000
+    coords = rng.random((A, 3)) * [40.0, 25.0, 30.0]
+    r, q, max_q = 0.4, 2 * np.pi / (0.4 * 127.5), 1.2
+    for generic in (False, True):
+        if generic:
+            f = (rng.integers(1, 30, A) + rng.random(A) * 0.1 + 1j * rng.random(A) * 0.05)
+        else:
+            f = rng.choice(np.array([6.0049 + 0.0023j, 1.0 + 0j, 16.17 + 0.25j, 8.016 + 0.009j, 9.024 + 0.014j]), A)
+        iq, qx, qy, qz, vsum, vcnt, setup = ox.voxelgridmaker(coords, f, r, q, max_q, True, 4)
+        codes, uniq = engine.encode_values(f)
+        assert (codes is None) == generic
+        kw = dict(f_values=f) if generic else dict(species=codes, table=uniq)
+        eng = engine.SliceEngine(coords, r, setup["q_axis"], setup["grid_size"], setup["avg_voxel_f"],
+                                 setup["x_bound"], setup["y_bound"], True, 4, **kw)
+        eng.run(setup["phis"])
+        assert np.array_equal(eng.counts(), vcnt.astype(np.int64))
+        assert np.abs(eng.sums() - vsum).max() <= TOL_INT * vsum.max()

@@ -1,0 +1,147 @@
+"""CPU-side checks: the C-ABI library loads and exports what the header
+declares, the product refuses to run without a GPU, the host-evaluated scalars
+match the oracle, and the device FFT engine (compiled for the host) matches
+numpy.fft.  No kernel is launched here."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from giwaxsim_b200 import _lib, engine
+from oracle import giwaxs_oracle as ox
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "giwaxs_b200.h")).read()
+    declared = set(re.findall(r"\b(gx_[a-z0-9_]+)\s*\(", header))
+    declared.discard("gx_float2")
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), "libgiwaxs_b200.so does not export %s" % name
+    assert declared == set(_lib.exported_symbols())
+    assert _lib.cdll().gx_abi_version() == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="a GPU is present")
+def test_product_fails_loudly_without_gpu():
+    with pytest.raises(_lib.GxError) as e:
+        engine.resolve_device()
+    assert e.value.code == _lib.GX_ERR_NO_DEVICE
+    from giwaxsim_b200.tools.comparison import voxelgridmaker_fitting
+    with pytest.raises(_lib.GxError):
+        voxelgridmaker_fitting(np.random.rand(10, 3) * 10, np.array(["C"] * 10), 0.3, 0.1, 1.0, 12700.0)
+
+
+def test_unsupported_fft_size_is_an_error():
+    assert _lib.cdll().gx_fft_plan_bytes(5000) == _lib.GX_ERR_UNSUPPORTED
+    assert "unsupported" in _lib.last_error()
+    assert _lib.cdll().gx_fft_plan_bytes(8) == _lib.GX_ERR_UNSUPPORTED
+
+
+@pytest.fixture(scope="module")
+def fft_emul(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emul") / "libfft_emul.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so,
+                           os.path.join(ROOT, "tests", "host_emul", "fft_emul.cpp")])
+    return ctypes.CDLL(so)
+
+
+@pytest.mark.parametrize("N", [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 17, 131, 262, 524, 1048, 2095, 4095])
+def test_fft_engine_host_build_matches_numpy(fft_emul, N):
+    nbytes = _lib.cdll().gx_fft_plan_bytes(N)
+    assert nbytes >= 0          # N = 16 is a single radix-16 pass: empty table
+    plan = np.zeros(max(nbytes // 4, 2), np.float32)
+    _lib.call("gx_fft_plan_fill", N, _lib.ptr(plan))
+    rng = np.random.default_rng(N)
+    x = (rng.normal(size=N) + 1j * rng.normal(size=N) + 8.0).astype(np.complex64)
+    out = np.zeros(N, np.complex64)
+    assert fft_emul.emul_dft(N, _lib.ptr(plan), _lib.ptr(x), _lib.ptr(out)) == 0
+    ref = np.fft.fft(x.astype(np.complex128))
+    assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def test_orientation_matrices_match_oracle_chain():
+    gx, gy, gz, _, _ = ox.detector_base(33, 2.0, (90.0, 90.0, 90.0), ("psi", "phi", "psi"))
+    psis, phis, thetas = np.linspace(75, 90, 4), np.linspace(0, 179, 5), np.linspace(0, 1, 2)
+    w = [np.ones_like(a) / len(a) for a in (psis, phis, thetas)]
+    R, wt = engine.orientation_tables(engine.grid_corners(gx, gy, gz), psis, w[0], phis, w[1], thetas, w[2])
+    todo = ox.orientation_list(psis, w[0], phis, w[1], thetas, w[2])
+    assert len(todo) == R.shape[0]
+    for o, (psi, phi, theta, weight) in enumerate(todo):
+        g = (gx, gy, gz)
+        for step, (which, ang) in enumerate((("psi", psi), ("phi", phi), ("theta", theta))):
+            M = ox.axis_angle_matrix(ox.detector_axis(*g, which), np.radians(ang))
+            assert np.array_equal(M.ravel(), R[o, step]), (o, step)
+            g = ox.matvec3(M, *g)
+        assert wt[o] == weight
+
+
+def test_encode_values():
+    el = np.array(["C", "H", "C", "S", "H", "C"])
+    codes, uniq = engine.encode_values(el)
+    assert [str(u) for u in uniq] == ["C", "H", "S"] and codes.tolist() == [0, 1, 0, 2, 1, 0]
+    many = np.arange(40).astype(complex)
+    assert engine.encode_values(many) == (None, None)
+
+
+def test_stage_a_geometry_matches_oracle():
+    rng = np.random.default_rng(0)
+    coords = rng.random((50, 3)) * [30, 20, 25]
+    f = np.full(50, 6.0 + 0j)
+    for r, q, mq in [(0.3, 0.02, 2.0), (0.3, 0.01, 2.0), (0.25, 0.05, 1.0)]:
+        s = ox.stage_a_setup(coords, f, r, q, mq)
+        bounds = (s["x_bound"], s["y_bound"], s["z_bound"])
+        N, q_num, q_axis, phis = engine.stage_a_geometry(bounds, r, q, mq)
+        assert (N, q_num) == (s["grid_size"], s["q_num"])
+        assert np.array_equal(q_axis, s["q_axis"]) and np.array_equal(phis, s["phis"])
+    with pytest.raises(Exception, match="non-physical"):
+        engine.stage_a_geometry((1, 1, 1), 3.0, 0.1, 2.0)
+    with pytest.raises(Exception, match="smaller than simulation"):
+        engine.stage_a_geometry((500, 500, 500), 0.3, 0.1, 2.0)
+
+
+def _chord_from_constants(c, x):
+    """NumPy transcription of the device formula (gx_project.cu: chord_length)."""
+    if c.mode == 0:
+        return np.where(x < c.hor, c.ver, 0.0)
+    if c.mode == 1:
+        return np.where(x < c.ver, c.hor, 0.0)
+    with np.errstate(all="ignore"):
+        first = (c.rise + x * c.tan_phi) - (c.vcos - x) * c.tan_theta
+        last = (c.hor - ((x - c.vcos) / c.cos_phi)) / c.cos_theta
+    out = np.zeros_like(x)
+    m0 = x == 0
+    m1 = ~m0 & (x < c.stop1)
+    m2 = ~m0 & ~m1 & (x <= c.stop2)
+    m3 = ~m0 & ~m1 & ~m2 & (x < c.stop12)
+    out[m1] = first[m1]
+    out[m2] = c.mid
+    out[m3] = last[m3]
+    return out
+
+
+def test_chord_constants_reproduce_oracle_lengths():
+    x = np.arange(400) * 0.3
+    phis = np.array([0.0, 0.2, 30.0, 45.0, 77.7, 90.0, 90.2, 120.0, 179.8])
+    arr = engine.chord_constants(phis, 21.0, 14.0)
+    for i, phi in enumerate(phis):
+        assert np.array_equal(_chord_from_constants(arr[i], x), ox.chord_lengths(x, 21.0, 14.0, phi)), phi
+
+
+def test_gaussian_weights_match_scipy():
+    from scipy.ndimage import gaussian_filter1d
+    for sigma in (1, 5, 25):
+        w, radius = engine.gaussian_weights(sigma)
+        n = 4 * radius + 3
+        delta = np.zeros(n)
+        delta[n // 2] = 1.0
+        k = gaussian_filter1d(delta, sigma=sigma, mode="wrap")
+        assert np.array_equal(k[n // 2 - radius:n // 2 + radius + 1], w)
+        assert radius == int(4 * sigma + 0.5)

@@ -1,0 +1,63 @@
+"""world_size-2 gloo test of the N>1 host logic: round-robin sharding of phi
+slices / orientations and the all-reduce that combines per-rank partial grids
+(giwaxsim_b200/parallel.py).  The partial grids come from the CPU oracle here;
+on GPUs the same code path carries device tensors over NCCL."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from giwaxsim_b200 import parallel
+from oracle import giwaxs_oracle as ox
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, coords, f, r, q, max_q, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        assert parallel.rank_world() == (rank, world)
+        setup = ox.stage_a_setup(coords, f, r, q, max_q)
+        mine = parallel.shard(setup["phis"], rank, world)
+        q3 = (setup["q_num"],) * 3
+        vsum, vcnt = np.zeros(q3), np.zeros(q3)
+        for phi in mine:
+            ox.run_slice(vsum, vcnt, coords, setup, r, phi, True, 3)
+        t_sum = torch.from_numpy(vsum)
+        t_cnt = torch.from_numpy(vcnt.astype(np.int32))
+        parallel.all_reduce_sum([t_sum, None, t_cnt])
+        if rank == 0:
+            ret["sum"], ret["cnt"], ret["n"] = t_sum.numpy().copy(), t_cnt.numpy().copy(), len(mine)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_reduce_equal_serial():
+    rng = np.random.default_rng(2)
+    coords = rng.random((200, 3)) * [12.0, 9.0, 10.0]
+    f = np.full(200, 6.0049 + 0.0023j)
+    r, q, max_q = 0.3, 0.2, 1.0
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(2, _free_port(), coords, f, r, q, max_q, ret), nprocs=2, join=True)
+        got_sum, got_cnt, n0 = ret["sum"], ret["cnt"], ret["n"]
+    _, _, _, _, vsum, vcnt, setup = ox.voxelgridmaker(coords, f, r, q, max_q, True, 3)
+    assert n0 == len(setup["phis"][0::2])
+    assert np.array_equal(got_cnt, vcnt.astype(np.int32))               # integer counts: exact
+    assert np.abs(got_sum - vsum).max() <= 1e-12 * vsum.max()           # float sums: association only
+
+
+def test_shard_is_a_partition():
+    items = np.arange(23)
+    parts = [parallel.shard(items, r, 4) for r in range(4)]
+    assert sorted(np.concatenate(parts).tolist()) == items.tolist()
+    assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1

@@ -1,0 +1,62 @@
+"""Live pin of the oracle against the unmodified reference (only where the
+read-only checkout is mounted, i.e. in the build container)."""
+import numpy as np
+import pytest
+
+from oracle import ref_shim, giwaxs_oracle as ox
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not mounted")
+
+
+def _cluster(scale=(1.0, 1.0, 1.0), seed=3, n=300):
+    rng = np.random.default_rng(seed)
+    coords = rng.random((n, 3)) * np.array([14.0, 21.0, 11.0]) * np.array(scale)
+    elements = rng.choice(np.array(["C", "H", "S", "O"]), size=n)
+    return coords, elements
+
+
+@pytest.mark.parametrize("fill_bkg,smooth,scale", [(True, 4, (1, 1, 1)), (False, 0, (1, 1, 1)),
+                                                    (False, 2, (1, 1, 1)), (True, 3, (3.5, 2.0, 1.0))])
+def test_stage_a_bit_exact(fill_bkg, smooth, scale):
+    coords, elements = _cluster(scale)
+    r, q, max_q = 0.3, 0.11, 1.5
+    setup = ref_shim.stage_a_setup(coords, elements, r, q, max_q, 12700.0)
+    cap = {}
+    vsum, vcnt = ref_shim.run_slices_serial(coords, setup, r, fill_bkg, smooth, capture=cap)
+    ref_out = ref_shim.finalize_serial(vsum, vcnt, setup["q_axis"], max_q)
+    f = ox.f_values_for(elements)
+    iq, qx, qy, qz, osum, ocnt, osetup = ox.voxelgridmaker(coords, f, r, q, max_q, fill_bkg, smooth)
+    assert np.array_equal(vsum, osum) and np.array_equal(vcnt, ocnt)
+    assert np.array_equal(iq, ref_out[0]) and np.array_equal(qx, ref_out[1])
+    q3 = (osetup["q_num"],) * 3
+    for i in range(0, len(osetup["phis"]), 17):
+        out = {}
+        ox.run_slice(np.zeros(q3), np.zeros(q3), coords, osetup, r, osetup["phis"][i], fill_bkg, smooth, out=out)
+        assert np.array_equal(out["grid"], cap["grid"][i])
+        assert np.array_equal(out["iq_2d"], cap["iq_2d"][i])
+        assert np.array_equal(out["det_h_qx"], cap["det_h_qx"][i])
+        assert np.array_equal(out["det_h_qy"], cap["det_h_qy"][i])
+
+
+def test_chord_lengths_bit_exact():
+    ref = ref_shim.load()
+    x = np.arange(300) * 0.3
+    for phi in [0.0, 0.5, 12.25, 45.0, 89.9, 90.0, 90.3, 133.0, 179.8]:
+        for hor, ver in [(21.0, 14.0), (14.0, 21.0), (40.0, 3.0)]:
+            a = ref.voxelgrids.rectangular_collapse_lengths(x, hor, ver, np.float64(phi))
+            b = ox.chord_lengths(x, hor, ver, np.float64(phi))
+            assert np.array_equal(np.asarray(a, dtype=np.float64), b), (phi, hor, ver)
+
+
+@pytest.mark.parametrize("P,vals,axs,mirror", [(40, (90.0, 90.0, 90.0), ("psi", "phi", "psi"), True),
+                                               (41, (5.0, 0.0, 33.0), ("phi", "None", "theta"), True)])
+def test_stage_b_bit_exact(P, vals, axs, mirror):
+    rng = np.random.default_rng(11)
+    V = 31
+    iq = rng.random((V, V, V)) * 1e6
+    q = np.linspace(-2.1, 2.1, V)
+    psis, phis, thetas = np.linspace(70, 90, 3), np.linspace(0, 170, 4), np.linspace(0, 2, 2)
+    w = [np.ones_like(a) / len(a) for a in (psis, phis, thetas)]
+    a = ref_shim.detectormaker_serial(iq, q, q, q, P, 2.0, vals, axs, psis, w[0], phis, w[1], thetas, w[2], mirror=mirror)
+    b = ox.detectormaker(iq, q, q, q, P, 2.0, vals, axs, psis, w[0], phis, w[1], thetas, w[2], mirror=mirror)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
