@@ -236,7 +236,8 @@ class SliceEngine:
             dev = self.device
             st = _stream()
             self.row_index = torch.empty(self.N, dtype=torch.int32, device=dev)
-            call("gx_axis_row_index", ptr(_dev(self.q_fft, dev)), self.N, self.qmin, self.qmax, self.dq,
+            self.d_q_fft = _dev(self.q_fft, dev)
+            call("gx_axis_row_index", ptr(self.d_q_fft), self.N, self.qmin, self.qmax, self.dq,
                  self.q_num, ptr(self.row_index), st)
             if accumulators is not None:
                 self.vsum, self.count3, self.count2 = accumulators
@@ -297,7 +298,10 @@ class SliceEngine:
              int(self.fill_bkg), self.sigma, ptr(self.gauss), self.gauss_radius,
              ptr(t["base"]), ptr(t.get("my")), ptr(t.get("mz")), st)
         t["col"] = torch.empty(n * N, dtype=torch.int32, device=dev)
-        call("gx_slice_col_index", ptr(_dev(xl, dev)), ptr(_dev(xr, dev)), ptr(_dev(yl, dev)), ptr(_dev(yr, dev)),
+        # keep the four end-point arrays referenced until the launch: temporaries
+        # would be recycled by the caching allocator and alias each other
+        t["ends"] = [_dev(a, dev) for a in (xl, xr, yl, yr)]
+        call("gx_slice_col_index", ptr(t["ends"][0]), ptr(t["ends"][1]), ptr(t["ends"][2]), ptr(t["ends"][3]),
              n, N, self.qmin, self.qmax, self.dq, self.q_num, ptr(t["col"]), st)
         return t
 

@@ -75,11 +75,10 @@ def process_file2(iq_2d, det_h_qx, det_h_qy, det_v_qz, qx, qy, qz, voxel_grid_sh
         d_iq = engine._dev(iq_2d, dev, torch.float32).contiguous()
         col = torch.empty(cols, dtype=torch.int32, device=dev)
         row = torch.empty(rows, dtype=torch.int32, device=dev)
-        call("gx_axis_col_index", ptr(engine._dev(np.asarray(det_h_qx, dtype=np.float64), dev)),
-             ptr(engine._dev(np.asarray(det_h_qy, dtype=np.float64), dev)), cols, qmin_x, qmax_x, dq, q_num,
-             ptr(col), st)
-        call("gx_axis_row_index", ptr(engine._dev(np.asarray(det_v_qz, dtype=np.float64), dev)), rows,
-             qmin_x, qmax_x, dq, q_num, ptr(row), st)
+        d_hx, d_hy, d_vz = (engine._dev(np.asarray(a, dtype=np.float64), dev)
+                            for a in (det_h_qx, det_h_qy, det_v_qz))
+        call("gx_axis_col_index", ptr(d_hx), ptr(d_hy), cols, qmin_x, qmax_x, dq, q_num, ptr(col), st)
+        call("gx_axis_row_index", ptr(d_vz), rows, qmin_x, qmax_x, dq, q_num, ptr(row), st)
         call("gx_bin_slices", ptr(d_iq), 1, rows, cols, ptr(col), cols, ptr(row), q_num,
              ptr(vsum), ptr(vcnt), None, st)
         torch.cuda.current_stream().synchronize()
@@ -107,6 +106,7 @@ def add_f0_q_3d(iq, qx_axis, qy_axis, qz_axis, element):
         ones = torch.ones(V ** 3, dtype=torch.int32, device=dev)
         out = torch.empty(V ** 3, dtype=torch.float32, device=dev)
         aff = np.asarray(CROMER_MANN[element], dtype=np.float64)
-        call("gx_voxel_finalize", ptr(d_sum), ptr(ones), None, None, V, 0, V, ptr(engine._dev(qx_axis, dev)),
+        d_axis = engine._dev(qx_axis, dev)
+        call("gx_voxel_finalize", ptr(d_sum), ptr(ones), None, None, V, 0, V, ptr(d_axis),
              ptr(aff), float(ATOMIC_NUMBER[element]), ptr(out), engine._stream())
         return out.cpu().to(torch.float64).numpy().reshape(V, V, V)
