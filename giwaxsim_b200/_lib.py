@@ -96,11 +96,36 @@ def last_error():
     return cdll().gx_last_error().decode("utf-8", "replace")
 
 
+# kernels launched per entry point (bench.py reports the total as gpu_launches)
+_LAUNCHES = {
+    "gx_coords_minmax": 3, "gx_atoms_sort_rows": 3, "gx_slice_bbox": 3, "gx_atom_pixel_indices": 1,
+    "gx_slice_vectors": 1, "gx_project_slices": 1, "gx_fft2_abs2_shift": 2, "gx_slice_col_index": 1,
+    "gx_axis_col_index": 1, "gx_axis_row_index": 1, "gx_bin_slices": 1, "gx_row_histogram": 1,
+    "gx_voxel_finalize": 1, "gx_rotate_points": 1, "gx_detector_accumulate": 1, "gx_detector_epilogue": 1,
+    "gx_slices_fused": 2,
+}
+_launch_count = 0
+
+
+def reset_launch_count():
+    global _launch_count
+    _launch_count = 0
+
+
+def launch_count():
+    return _launch_count
+
+
 def call(name, *args):
     """Invoke an int-returning entry point and raise GxError on failure."""
+    global _launch_count
     rc = getattr(cdll(), name)(*args)
     if name not in _UNCHECKED and rc != GX_OK:
         raise GxError(rc, last_error())
+    if name == "gx_slice_yrange":
+        _launch_count += 2 + (int(args[5]) + 255) // 256
+    else:
+        _launch_count += _LAUNCHES.get(name, 0)
     return rc
 
 

@@ -338,13 +338,14 @@ class SliceEngine:
             grid = torch.empty(nb * N * N * 2, dtype=torch.float32, device=dev)
             work = torch.empty_like(grid)
             iq2d = torch.empty(nb * N * N, dtype=torch.float32, device=dev)
+            boxes = []
             for i0 in range(0, len(phis), B):
                 chunk = phis[i0:i0 + B]
-                t = self.prepare(chunk)
-                self.check_bbox(t)
-                self.project(t, grid)
-                self.fft(grid, work, iq2d, t["n"])
-                self.bin(t, iq2d)
+                t = self._timed("prepare", self.prepare, chunk)
+                boxes.append(t["bbox"])
+                self._timed("project", self.project, t, grid)
+                self._timed("fft2", self.fft, grid, work, iq2d, t["n"])
+                self._timed("bin", self.bin, t, iq2d)
                 if capture is not None:
                     n = t["n"]
                     capture.setdefault("bbox", []).append(t["bbox"].cpu().numpy().reshape(n, 4))
@@ -356,6 +357,27 @@ class SliceEngine:
                         capture.setdefault("iq_2d", []).append(iq2d[:n * N * N].cpu().numpy().reshape(n, N, N).copy())
                 self.slices_done += len(chunk)
             torch.cuda.current_stream().synchronize()
+            # one deferred host check for the whole run (keeps the launch queue full)
+            self.check_bbox({"bbox": torch.cat(boxes)})
+
+    timers = None
+
+    def _timed(self, name, fn, *args):
+        """Run fn; when self.timers is a dict, bracket it with CUDA events on the
+        launching stream (bench.py reads the per-kernel totals)."""
+        if self.timers is None:
+            return fn(*args)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn(*args)
+        e1.record()
+        self.timers.setdefault(name, []).append((e0, e1))
+        return out
+
+    def collect_timers(self):
+        """{kernel group: total ms} from the recorded event pairs."""
+        torch.cuda.synchronize()
+        return {k: float(sum(a.elapsed_time(b) for a, b in v)) for k, v in (self.timers or {}).items()}
 
     def atom_indices(self, phi):
         """(y_idx, z_idx) int64 of every atom in original order for one phi (probe)."""
