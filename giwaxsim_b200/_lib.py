@@ -32,6 +32,17 @@ class Chord(ctypes.Structure):
                [("mode", ctypes.c_int32), ("pad", ctypes.c_int32)]
 
 
+class FusedArgs(ctypes.Structure):
+    """gx_fused_args (include/giwaxs_b200.h)."""
+    _fields_ = [(n, ctypes.c_void_p) for n in
+                ("d_xs", "d_ys", "d_species", "d_f", "d_row_start", "d_table", "d_sin", "d_cos", "d_yrange",
+                 "d_bbox", "d_base", "d_my", "d_mz", "d_plan", "d_col", "d_colrange", "d_row_index",
+                 "d_work", "d_sum", "d_count2")] + \
+               [(n, ctypes.c_double) for n in ("r", "pedestal_re", "pedestal_im")] + \
+               [(n, ctypes.c_int32) for n in ("n_species", "n_phi", "N", "KC", "q_num", "row_lo", "row_hi",
+                                              "fill_bkg", "smooth_sigma", "pad")]
+
+
 _p = ctypes.c_void_p
 _i = ctypes.c_int
 _i64 = ctypes.c_int64
@@ -59,6 +70,8 @@ _PROTOTYPES = {
     "gx_bin_slices": (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p]),
     "gx_row_histogram": (_i, [_p, _i, _i, _p, _p]),
     "gx_voxel_finalize": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _d, _p, _p]),
+    "gx_slice_col_range": (_i, [_p, _i, _i, _p, _p]),
+    "gx_slices_fused": (_i, [_p, _p]),
     "gx_rotate_points": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "gx_detector_accumulate": (_i, [_p, _i, _i, _i, _d, _d, _d, _d, _p, _p, _p, _i64, _p, _p, _i,
                                     _p, _i, _p, _p]),
@@ -102,7 +115,7 @@ _LAUNCHES = {
     "gx_slice_vectors": 1, "gx_project_slices": 1, "gx_fft2_abs2_shift": 2, "gx_slice_col_index": 1,
     "gx_axis_col_index": 1, "gx_axis_row_index": 1, "gx_bin_slices": 1, "gx_row_histogram": 1,
     "gx_voxel_finalize": 1, "gx_rotate_points": 1, "gx_detector_accumulate": 1, "gx_detector_epilogue": 1,
-    "gx_slices_fused": 2,
+    "gx_slices_fused": 2, "gx_slice_col_range": 1,
 }
 _launch_count = 0
 

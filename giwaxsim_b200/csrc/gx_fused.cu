@@ -1,0 +1,326 @@
+// Fused stage-A slice pipeline: the production path of voxelgridmaker_fitting.
+//
+//   F1  slice_rows_fused   one CTA per (rotation, z-row):
+//         atoms of the row -> species counters in shared memory (ATOMS.ADD) ->
+//         complex row (background, edge blend, pedestal removed) -> 1-D FFT along
+//         y in the same shared memory -> only the q-columns the voxel box keeps
+//         are written (N x Kc complex64 instead of N x N).
+//   F2  slice_cols_fused   one CTA per (rotation, TC kept columns):
+//         column tile (rows of the atom band only; the rest is zero once the
+//         pedestal is removed) -> 1-D FFT along z -> |.|^2 of the kept q-rows ->
+//         fp32 RED.ADD straight into the 3-D voxel sum, u32 per-column count.
+//
+// What never touches HBM any more (reference: voxelgrids.py:338-392,464-503):
+// the zero-filled N x N grid, the scatter read-modify-writes, the pre-FFT grid,
+// the row-FFT output outside the kept columns, and the N x N intensity image.
+// The constant pedestal P of the background model is subtracted before the
+// transform (its spectrum is a delta) and P*N^2 is added back to the DC
+// coefficient in F2, which also keeps fp32 round-off away from the Bragg signal.
+//
+// Grid order: the rotation index is the fastest-varying block index, so the
+// CTAs resident at any moment work on the same few z-rows for all rotations of
+// the batch and the row's atoms are fetched from HBM once and re-read from L2.
+#include "gx_project.cuh"
+#include "gx_fft_engine.cuh"
+
+struct FusedArgs {
+    ProjArgs proj;
+    GxFftLayout lay;
+    const float2 *plan;
+    const int32_t *col;        // [n_phi][N] packed iy*q_num+ix or -1
+    const int32_t *colrange;   // [n_phi][2] first kept column, one past last
+    const int32_t *row_index;  // [N] iz or -1
+    int row_lo, row_hi;        // kept shifted rows [row_lo, row_hi)
+    float2 *work;              // [n_phi][N][KC]
+    int KC;
+    int q_num;
+    float *vsum;
+    uint32_t *count2;
+    float dc_re, dc_im;        // pedestal * N^2
+    int n_phi;
+};
+
+__device__ __forceinline__ void active_band(const ProjArgs &a, int p, int &za, int &zb)
+{
+    // rows whose pedestal-free content can be non-zero
+    const int z_min = a.bbox[4 * p + 2], z_max = a.bbox[4 * p + 3];
+    if (a.fill_bkg) { za = z_min; zb = z_max - 1; }
+    else if (a.sigma > 0) { za = 0; zb = a.N - 1; }
+    else { za = z_min; zb = z_max; }
+}
+
+// ------------------------------------------------------------------ F1 ----
+template <int L, bool SPECIES>
+__global__ void __launch_bounds__(PROJ_THREADS)
+slice_rows_fused(FusedArgs fa)
+{
+    constexpr int M = 1 << L;
+    constexpr int NT = PROJ_THREADS;
+    constexpr int PER = (M + NT - 1) / NT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *buf = reinterpret_cast<float2 *>(smem_raw);
+    uint32_t *words = reinterpret_cast<uint32_t *>(smem_raw);   // aliases buf (used strictly before it)
+    __shared__ float2 s_table[GX_MAX_SPECIES];
+    const ProjArgs &a = fa.proj;
+    const int p = blockIdx.x, z = blockIdx.y;
+    const int N = a.N, tid = threadIdx.x;
+    int za, zb;
+    active_band(a, p, za, zb);
+    if (z < za || z > zb) return;
+    const int jlo = fa.colrange[2 * p], jhi = fa.colrange[2 * p + 1];
+    if (jhi <= jlo) return;
+
+    const double s = a.sn[p], c = a.cs[p], shift = a.yrange[2 * p], r = a.r, inv_r = 1.0 / a.r;
+    const int beg = a.row_start[z], end = a.row_start[z + 1];
+    float2 px[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) px[j] = make_float2(0.f, 0.f);
+
+    if (SPECIES) {
+        if (tid < GX_MAX_SPECIES) s_table[tid] = tid < a.n_species ? a.table[tid] : make_float2(0.f, 0.f);
+        const int npair = (a.n_species + 1) >> 1;
+        const int nwords = npair * N;
+        for (int y = tid; y < nwords; y += NT) words[y] = 0u;
+        __syncthreads();
+        for (int c0 = beg; c0 < end; c0 += 65535) {
+            const int c1 = min(c0 + 65535, end);
+            for (int i = c0 + tid; i < c1; i += NT) {
+                double q = gx_floordiv(__dsub_rn(gx_rot_y(a.xs[i], a.ys[i], s, c), shift), r, inv_r);
+                if (q < (double)N) {
+                    const int sp = a.species[i];
+                    atomicAdd(&words[(sp >> 1) * N + (int)q], 1u << ((sp & 1) * 16));
+                }
+            }
+            __syncthreads();
+            const bool more = c1 < end;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const int y = tid + j * NT;
+                if (y < N) {
+                    for (int w = 0; w < npair; ++w) {
+                        const uint32_t cnt = words[w * N + y];
+                        if (cnt) {
+                            const float n0 = (float)(cnt & 0xffffu), n1 = (float)(cnt >> 16);
+                            const float2 f0 = s_table[2 * w], f1 = s_table[2 * w + 1];
+                            px[j].x += n0 * f0.x + n1 * f1.x;
+                            px[j].y += n0 * f0.y + n1 * f1.y;
+                            if (more) words[w * N + y] = 0u;
+                        }
+                    }
+                }
+            }
+            __syncthreads();   // all counter reads done before the next chunk / before buf is written
+        }
+    } else {
+        // generic per-atom f: accumulate straight into the (padded) row buffer
+        for (int y = tid; y < M; y += NT) buf[gx_phys(y)] = make_float2(0.f, 0.f);
+        __syncthreads();
+        for (int i = beg + tid; i < end; i += NT) {
+            double q = gx_floordiv(__dsub_rn(gx_rot_y(a.xs[i], a.ys[i], s, c), shift), r, inv_r);
+            if (q < (double)N) {
+                const float2 f = a.f[i];
+                float2 *dst = &buf[gx_phys((int)q)];
+                atomicAdd(&dst->x, f.x);
+                atomicAdd(&dst->y, f.y);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int y = tid + j * NT;
+            if (y < N) px[j] = buf[gx_phys(y)];
+        }
+        __syncthreads();
+    }
+
+    // complete the row (pedestal-free) and stage it for the transform
+    const int4 bb = make_int4(a.bbox[4 * p], a.bbox[4 * p + 1], a.bbox[4 * p + 2], a.bbox[4 * p + 3]);
+    const float mzv = a.sigma > 0 ? a.mz[(size_t)p * N + z] : 1.f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const int y = tid + j * NT;
+        if (y < M) {
+            float2 v = make_float2(0.f, 0.f);
+            if (y < N) {
+                v = finish_pixel(a, p, z, y, px[j], bb, mzv);
+                if (fa.lay.bluestein) v = gx_cmul(v, fa.plan[fa.lay.chirp_off + y]);
+            }
+            buf[gx_phys(y)] = v;
+        }
+    }
+    __syncthreads();
+    gx_dft_block<L, 1, 0>(buf, fa.lay, fa.plan, tid, NT);
+
+    // kept q-columns only; shifted column j holds unshifted coefficient j - N/2 (mod N)
+    float2 *dst = fa.work + ((size_t)p * N + z) * fa.KC;
+    const int half = N / 2;
+    for (int jj = tid; jj < jhi - jlo; jj += NT) {
+        int k = jlo + jj - half;
+        if (k < 0) k += N;
+        dst[jj] = gx_dft_result<L>(buf, fa.lay, fa.plan, k);
+    }
+}
+
+// ------------------------------------------------------------------ F2 ----
+template <int L, int TC>
+__global__ void __launch_bounds__(512)
+slice_cols_fused(FusedArgs fa)
+{
+    constexpr int M = 1 << L;
+    constexpr int BS0 = M + (M >> 4) + (M >> 8) + 1;
+    // buffer stride == 16/TC (mod 16) float2: the TC interleaved columns of a
+    // half-warp land on disjoint banks when the tile is loaded and read out
+    constexpr int WANT = (16 / TC) % 16;
+    constexpr int BS = BS0 + ((WANT - (BS0 % 16)) + 16) % 16;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *smem = reinterpret_cast<float2 *>(smem_raw);
+    const ProjArgs &a = fa.proj;
+    const int p = blockIdx.x, tile = blockIdx.y;
+    const int N = a.N, tid = threadIdx.x, nt = blockDim.x;
+    const int jlo = fa.colrange[2 * p], jhi = fa.colrange[2 * p + 1];
+    const int kc = jhi - jlo;
+    const int jj0 = tile * TC;
+    if (jj0 >= kc) return;
+    int za, zb;
+    active_band(a, p, za, zb);
+
+    const float2 *src = fa.work + (size_t)p * N * fa.KC + jj0;
+    for (int w = tid; w < TC * M; w += nt) {
+        const int cc = w % TC, n = w / TC;
+        float2 v = make_float2(0.f, 0.f);
+        if (n >= za && n <= zb && jj0 + cc < kc) {
+            v = src[(size_t)n * fa.KC + cc];
+            if (fa.lay.bluestein) v = gx_cmul(v, fa.plan[fa.lay.chirp_off + n]);
+        }
+        smem[cc * BS + gx_phys(n)] = v;
+    }
+    __syncthreads();
+    gx_dft_block<L, TC, BS>(smem, fa.lay, fa.plan, tid, nt);
+
+    const int half = N / 2;
+    const int kr = fa.row_hi - fa.row_lo;
+    for (int w = tid; w < TC * kr; w += nt) {
+        const int cc = w / kr, ii = w - cc * kr;
+        if (jj0 + cc >= kc) break;
+        const int j = jlo + jj0 + cc;
+        const int yx = fa.col[(size_t)p * N + j];
+        if (yx < 0) continue;
+        const int i = fa.row_lo + ii;
+        const int iz = fa.row_index[i];
+        if (ii == 0) atomicAdd(&fa.count2[yx], 1u);
+        if (iz < 0) continue;
+        int kz = i - half;
+        if (kz < 0) kz += N;
+        float2 v = gx_dft_result<L>(smem + cc * BS, fa.lay, fa.plan, kz);
+        if (kz == 0 && j == half) { v.x += fa.dc_re; v.y += fa.dc_im; }
+        atomicAdd(&fa.vsum[(size_t)yx * fa.q_num + iz], v.x * v.x + v.y * v.y);
+    }
+}
+
+// -------------------------------------------------------------- col range ----
+__global__ void __launch_bounds__(256)
+col_range_kernel(const int32_t *__restrict__ col, int N, int32_t *range)
+{
+    __shared__ int s_lo, s_hi;
+    const int p = blockIdx.x;
+    if (threadIdx.x == 0) { s_lo = N; s_hi = 0; }
+    __syncthreads();
+    int lo = N, hi = 0;
+    for (int j = threadIdx.x; j < N; j += blockDim.x)
+        if (col[(size_t)p * N + j] >= 0) { lo = min(lo, j); hi = max(hi, j + 1); }
+    atomicMin(&s_lo, lo);
+    atomicMax(&s_hi, hi);
+    __syncthreads();
+    if (threadIdx.x == 0) { range[2 * p] = s_lo; range[2 * p + 1] = s_hi; }
+}
+
+extern "C" int gx_slice_col_range(const int32_t *d_col, int n_phi, int N, int32_t *d_range, void *stream)
+{
+    GX_REQUIRE(d_col && d_range && n_phi > 0 && N > 0, "bad arguments");
+    col_range_kernel<<<n_phi, 256, 0, gx_stream(stream)>>>(d_col, N, d_range);
+    return gx_check_launch("gx_slice_col_range");
+}
+
+// ---------------------------------------------------------------- launch ----
+template <int L, int TC>
+static int launch_fused(const FusedArgs &fa, bool species, cudaStream_t st)
+{
+    constexpr int M = 1 << L;
+    constexpr int BS0 = M + (M >> 4) + (M >> 8) + 1;
+    constexpr int WANT = (16 / TC) % 16;
+    constexpr int BS = BS0 + ((WANT - (BS0 % 16)) + 16) % 16;
+    const int N = fa.proj.N;
+    size_t smem1 = (size_t)gx_phys_len(M) * sizeof(float2);
+    if (species) {
+        size_t w = (size_t)((fa.proj.n_species + 1) / 2) * N * sizeof(uint32_t);
+        if (w > smem1) smem1 = w;
+    }
+    const size_t smem2 = (size_t)BS * TC * sizeof(float2);
+    if (smem1 > 227 * 1024 || smem2 > 227 * 1024) {
+        gx_set_error("gx_slices_fused: shared memory need (%zu / %zu B) exceeds 227 KB", smem1, smem2);
+        return GX_ERR_UNSUPPORTED;
+    }
+    if (species) {
+        GX_CUDA(cudaFuncSetAttribute(slice_rows_fused<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        slice_rows_fused<L, true><<<dim3(fa.n_phi, N), PROJ_THREADS, smem1, st>>>(fa);
+    } else {
+        GX_CUDA(cudaFuncSetAttribute(slice_rows_fused<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        slice_rows_fused<L, false><<<dim3(fa.n_phi, N), PROJ_THREADS, smem1, st>>>(fa);
+    }
+    if (int e = gx_check_launch("slice_rows_fused")) return e;
+    GX_CUDA(cudaFuncSetAttribute(slice_cols_fused<L, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    int nt = TC * M / 16;
+    nt = nt < 64 ? 64 : (nt > 512 ? 512 : nt);
+    slice_cols_fused<L, TC><<<dim3(fa.n_phi, (fa.KC + TC - 1) / TC), nt, smem2, st>>>(fa);
+    return gx_check_launch("slice_cols_fused");
+}
+
+extern "C" int gx_slices_fused(const gx_fused_args *h, void *stream)
+{
+    GX_REQUIRE(h != NULL, "NULL argument block");
+    GX_REQUIRE(h->d_xs && h->d_ys && h->d_row_start && h->d_sin && h->d_cos && h->d_yrange && h->d_bbox &&
+               h->d_base && h->d_plan && h->d_col && h->d_colrange && h->d_row_index && h->d_work &&
+               h->d_sum && h->d_count2, "NULL pointer");
+    GX_REQUIRE(h->n_species >= 0 && h->n_species <= GX_MAX_SPECIES, "n_species out of range");
+    GX_REQUIRE(h->n_species == 0 ? h->d_f != NULL : (h->d_species != NULL && h->d_table != NULL),
+               "species/f inputs missing");
+    GX_REQUIRE(h->smooth_sigma <= 0 || (h->d_my && h->d_mz), "smooth needs mask buffers");
+    GX_REQUIRE(h->n_phi > 0 && h->n_phi <= 65535 && h->N >= 16 && h->KC > 0 && h->q_num > 0, "bad sizes");
+    GX_REQUIRE(h->row_lo >= 0 && h->row_hi <= h->N && h->row_lo <= h->row_hi, "bad kept-row range");
+    FusedArgs fa;
+    ProjArgs &a = fa.proj;
+    a.xs = h->d_xs; a.ys = h->d_ys; a.species = h->d_species; a.f = reinterpret_cast<const float2 *>(h->d_f);
+    a.row_start = h->d_row_start; a.table = reinterpret_cast<const float2 *>(h->d_table);
+    a.n_species = h->n_species; a.sn = h->d_sin; a.cs = h->d_cos; a.yrange = h->d_yrange; a.bbox = h->d_bbox;
+    a.base = reinterpret_cast<const float2 *>(h->d_base); a.my = h->d_my; a.mz = h->d_mz;
+    a.N = h->N; a.r = h->r; a.ped_re = (float)h->pedestal_re; a.ped_im = (float)h->pedestal_im;
+    a.fill_bkg = h->fill_bkg; a.sigma = h->smooth_sigma;
+    fa.lay = gx_fft_layout(h->N);
+    if (fa.lay.M == 0) { gx_set_error("gx_slices_fused: unsupported grid size %d", h->N); return GX_ERR_UNSUPPORTED; }
+    fa.plan = reinterpret_cast<const float2 *>(h->d_plan);
+    fa.col = h->d_col; fa.colrange = h->d_colrange; fa.row_index = h->d_row_index;
+    fa.row_lo = h->row_lo; fa.row_hi = h->row_hi;
+    fa.work = reinterpret_cast<float2 *>(h->d_work); fa.KC = h->KC; fa.q_num = h->q_num;
+    fa.vsum = h->d_sum; fa.count2 = h->d_count2;
+    const double n2 = (double)h->N * (double)h->N;
+    const bool has_ped = h->fill_bkg || h->smooth_sigma > 0;
+    fa.dc_re = has_ped ? (float)(h->pedestal_re * n2) : 0.f;
+    fa.dc_im = has_ped ? (float)(h->pedestal_im * n2) : 0.f;
+    fa.n_phi = h->n_phi;
+    const bool species = h->n_species > 0;
+    cudaStream_t st = gx_stream(stream);
+    switch (fa.lay.L) {
+    case 4: return launch_fused<4, 8>(fa, species, st);
+    case 5: return launch_fused<5, 8>(fa, species, st);
+    case 6: return launch_fused<6, 8>(fa, species, st);
+    case 7: return launch_fused<7, 8>(fa, species, st);
+    case 8: return launch_fused<8, 8>(fa, species, st);
+    case 9: return launch_fused<9, 8>(fa, species, st);
+    case 10: return launch_fused<10, 8>(fa, species, st);
+    case 11: return launch_fused<11, 8>(fa, species, st);
+    case 12: return launch_fused<12, 4>(fa, species, st);
+    case 13: return launch_fused<13, 2>(fa, species, st);
+    }
+    gx_set_error("gx_slices_fused: unsupported log2 size %d", fa.lay.L);
+    return GX_ERR_UNSUPPORTED;
+}

@@ -20,6 +20,12 @@ import torch
 from . import _lib
 from ._lib import call, ptr
 
+import os
+
+# GIWAXS_B200_STAGED=1 forces the unfused kernels (projection, 2-D FFT, binning
+# as separate launches) -- used to compare the two paths; both are CUDA.
+STAGED_ONLY = os.environ.get("GIWAXS_B200_STAGED", "0") == "1"
+
 _checked_devices = set()
 
 
@@ -253,6 +259,14 @@ class SliceEngine:
             else:
                 self.gauss, self.gauss_radius = None, 0
             self.slices_done = 0
+            # kept shifted rows form one interval (qz is monotone); kept columns of a
+            # slice are spaced 2*qmax_fft/(N-1) apart along a line through the voxel box
+            ri = self.row_index.cpu().numpy()
+            kept = np.where(ri >= 0)[0]
+            self.row_lo, self.row_hi = (int(kept[0]), int(kept[-1]) + 1) if len(kept) else (0, 0)
+            step = 2.0 * self.q_fft_max / (self.N - 1)
+            reach = max(abs(self.qmin), abs(self.qmax))
+            self.KC = int(min(self.N, (int(2.0 * np.sqrt(2.0) * reach / step) + 4 + 7) // 8 * 8))
 
     # -- per-batch host scalars -------------------------------------------
     def _phi_scalars(self, phis):
@@ -327,10 +341,60 @@ class SliceEngine:
             raise ValueError("zero-size array to reduction operation minimum which has no identity")
         return bb
 
-    def run(self, phis, capture=None):
-        """Accumulate the given phi slices.  capture: optional dict receiving
-        host copies of the per-slice intermediates (parity probes)."""
+    def fused_batch_size(self, budget_bytes=2 << 30):
+        return int(max(1, min(64, budget_bytes // (8 * self.N * self.KC))))
+
+    def fused(self, t, work):
+        """F1 + F2 for one prepared batch (gx_slices_fused)."""
+        a = self.atoms
+        n = t["n"]
+        t["colrange"] = torch.empty(2 * n, dtype=torch.int32, device=self.device)
+        call("gx_slice_col_range", ptr(t["col"]), n, self.N, ptr(t["colrange"]), _stream())
+        args = _lib.FusedArgs()
+        for name, tensor in (("d_xs", a.xs), ("d_ys", a.ys), ("d_species", a.species), ("d_f", a.f),
+                             ("d_row_start", a.row_start), ("d_table", a.table), ("d_sin", t["sin"]),
+                             ("d_cos", t["cos"]), ("d_yrange", t["yrange"]), ("d_bbox", t["bbox"]),
+                             ("d_base", t["base"]), ("d_my", t.get("my")), ("d_mz", t.get("mz")),
+                             ("d_plan", self.plan.table), ("d_col", t["col"]), ("d_colrange", t["colrange"]),
+                             ("d_row_index", self.row_index), ("d_work", work), ("d_sum", self.vsum),
+                             ("d_count2", self.count2)):
+            setattr(args, name, None if tensor is None else tensor.data_ptr())
+        args.r = self.r
+        args.pedestal_re, args.pedestal_im = self.pedestal.real, self.pedestal.imag
+        args.n_species, args.n_phi, args.N, args.KC, args.q_num = a.n_species, n, self.N, self.KC, self.q_num
+        args.row_lo, args.row_hi = self.row_lo, self.row_hi
+        args.fill_bkg, args.smooth_sigma = int(self.fill_bkg), self.sigma
+        call("gx_slices_fused", ctypes.byref(args), _stream())
+
+    def run_fused(self, phis):
+        """Production path: two fused launches per batch, nothing N x N in HBM."""
         phis = np.asarray(phis, dtype=np.float64)
+        if self.count2 is None:
+            raise ValueError("the fused path accumulates rank-1 counts (count3d=False)")
+        with torch.cuda.device(self.device):
+            B = self.fused_batch_size()
+            work = torch.empty(min(B, len(phis)) * self.N * self.KC * 2, dtype=torch.float32, device=self.device)
+            boxes = []
+            for i0 in range(0, len(phis), B):
+                chunk = phis[i0:i0 + B]
+                t = self._timed("prepare", self.prepare, chunk)
+                boxes.append(t["bbox"])
+                self._timed("fused", self.fused, t, work)
+                self.slices_done += len(chunk)
+            torch.cuda.current_stream().synchronize()
+            self.check_bbox({"bbox": torch.cat(boxes)})
+
+    def run(self, phis, capture=None, staged=None):
+        """Accumulate the given phi slices.  capture: optional dict receiving
+        host copies of the per-slice intermediates (parity probes; forces the
+        staged kernels, which materialise the pre-FFT grid and |FFT|^2 image)."""
+        phis = np.asarray(phis, dtype=np.float64)
+        if len(phis) == 0:
+            return
+        if staged is None:
+            staged = capture is not None or self.count2 is None or STAGED_ONLY
+        if not staged:
+            return self.run_fused(phis)
         with torch.cuda.device(self.device):
             B = self.batch_size()
             N, dev = self.N, self.device

@@ -182,6 +182,40 @@ int gx_voxel_finalize(const float *d_sum, const uint32_t *d_count3, const uint32
                       const uint32_t *d_m, int q_num, int lo, int hi, const double *d_axis,
                       const double *h_aff9, double Z, float *d_iq, void *stream);
 
+/* ------------------------------------------- fused slice pipeline (A) -- */
+/* [first, one-past-last) kept column of every rotation from the table that
+ * gx_slice_col_index wrote (the kept set is one interval).  d_range [n_phi][2] */
+int gx_slice_col_range(const int32_t *d_col, int n_phi, int N, int32_t *d_range, void *stream);
+
+/* Everything rotate_project_fft_coords + process_file2 do for a batch of
+ * rotations (voxelgrids.py:311-416,464-506), in two launches: per-row scatter +
+ * background + blend + FFT along y with only the kept q-columns written to
+ * d_work [n_phi][N][KC] complex64; per-column-tile FFT along z + |.|^2 +
+ * accumulation into d_sum [q_num^3] fp32 and d_count2 [q_num^2] u32 (the count
+ * of voxel (iy,ix,iz) is d_count2[iy,ix] * m[iz], m from gx_row_histogram).
+ * The per-rotation tables are those of gx_slice_yrange / gx_slice_bbox /
+ * gx_slice_vectors / gx_slice_col_index / gx_slice_col_range; row_lo/row_hi
+ * bound the kept shifted rows of d_row_index. */
+typedef struct gx_fused_args {
+    const double *d_xs, *d_ys;
+    const uint8_t *d_species;
+    const gx_float2 *d_f;
+    const int32_t *d_row_start;
+    const gx_float2 *d_table;
+    const double *d_sin, *d_cos, *d_yrange;
+    const int32_t *d_bbox;
+    const gx_float2 *d_base;
+    const float *d_my, *d_mz;
+    const void *d_plan;
+    const int32_t *d_col, *d_colrange, *d_row_index;
+    gx_float2 *d_work;
+    float *d_sum;
+    uint32_t *d_count2;
+    double r, pedestal_re, pedestal_im;
+    int32_t n_species, n_phi, N, KC, q_num, row_lo, row_hi, fill_bkg, smooth_sigma, pad;
+} gx_fused_args;
+int gx_slices_fused(const gx_fused_args *h_args, void *stream);
+
 /* --------------------------------------------------------- detector (K4) */
 /* p <- R p for n points, R row-major 3x3, fma chain k=0,1,2.
  *                                                  (detector.py:71,113,155) */

@@ -50,3 +50,6 @@ timed("project", lambda: eng.project(t["t"], grid))
 timed("fft2", lambda: eng.fft(grid, work, iq2d, len(sel)))
 timed("bin", lambda: eng.bin(t["t"], iq2d))
 print("atoms", n_atoms, "N", N, "q_num", q_num, "slices", len(sel), "bbox", t["t"]["bbox"][:4].tolist())
+work = torch.empty(len(sel) * N * eng.KC * 2, dtype=torch.float32, device=dev)
+timed("fused", lambda: eng.fused(t["t"], work))
+print("KC", eng.KC, "rows kept", eng.row_lo, eng.row_hi)
