@@ -199,22 +199,49 @@ GX_HD void gx_fft_pass(float2 *s, const float2 *tw, int tid, int nthreads)
         const int blk = b / S;
         const int t = b - blk * S;
         const int base = blk * (S * R) + t;
-        float2 *sb = s + buf * BUFSTRIDE;
+        // gx_phys(base + S*n) == gx_phys(base) + gx_phys(S*n) for every schedule in
+        // GxSched (no carries across the pad boundaries; checked exhaustively by
+        // tests/host_emul), so the R addresses are one register plus immediates.
+        float2 *sb = s + buf * BUFSTRIDE + gx_phys(base);
+        const float2 *twt = tw + t;
         float2 v[R];
 #pragma unroll
-        for (int n = 0; n < R; ++n) v[n] = sb[gx_phys(base + S * n)];
+        for (int n = 0; n < R; ++n) v[n] = sb[gx_phys(S * n)];
         if (DIT && S > 1) {
 #pragma unroll
-            for (int k = 1; k < R; ++k) v[k] = gx_cmul(v[k], tw[(k - 1) * S + t]);
+            for (int k = 1; k < R; ++k) v[k] = gx_cmul(v[k], twt[(k - 1) * S]);
         }
         GxDft<R>::run(v);
         if (!DIT && S > 1) {
 #pragma unroll
-            for (int k = 1; k < R; ++k) v[k] = gx_cmul(v[k], tw[(k - 1) * S + t]);
+            for (int k = 1; k < R; ++k) v[k] = gx_cmul(v[k], twt[(k - 1) * S]);
         }
 #pragma unroll
-        for (int k = 0; k < R; ++k) sb[gx_phys(base + S * k)] = v[k];
+        for (int k = 0; k < R; ++k) sb[gx_phys(S * k)] = v[k];
     }
+}
+
+// exhaustive check of the address identity used above (host tests)
+template <int R, int S, int M>
+static inline int gx_fft_pass_offsets_ok()
+{
+    for (int b = 0; b < M / R; ++b) {
+        const int blk = b / S, t = b - blk * S, base = blk * (S * R) + t;
+        for (int n = 0; n < R; ++n)
+            if (gx_phys(base + S * n) != gx_phys(base) + gx_phys(S * n)) return 0;
+    }
+    return 1;
+}
+template <int L>
+static inline int gx_fft_offsets_ok()
+{
+    typedef GxSched<L> Sc;
+    constexpr int M = 1 << L;
+    int ok = gx_fft_pass_offsets_ok<Sc::R0, M / Sc::R0, M>();
+    if constexpr (Sc::NP > 1) ok &= gx_fft_pass_offsets_ok<Sc::R1, M / Sc::R0 / Sc::R1, M>();
+    if constexpr (Sc::NP > 2) ok &= gx_fft_pass_offsets_ok<Sc::R2, M / Sc::R0 / Sc::R1 / Sc::R2, M>();
+    if constexpr (Sc::NP > 3) ok &= gx_fft_pass_offsets_ok<Sc::R3, M / Sc::R0 / Sc::R1 / Sc::R2 / Sc::R3, M>();
+    return ok;
 }
 
 #if defined(__CUDACC__)
@@ -277,12 +304,14 @@ GX_DEV void gx_fft_dit(float2 *s, const float2 *tw, const int *tw_off, int tid, 
 // Input: natural order in slots [0,N) -- for Bluestein the caller has already
 // multiplied element n by chirp[n] and zeroed slots [N,M).
 // Output: read coefficient k with gx_dft_result<L>().
-template <int L, int NBUF, int BUFSTRIDE>
+// BLUE: -1 decide at run time from g.bluestein, 0 / 1 fixed at compile time (the
+// hot kernels are instantiated per flavour so no test sits in their loops).
+template <int L, int NBUF, int BUFSTRIDE, int BLUE = -1>
 GX_DEV void gx_dft_block(float2 *s, const GxFftLayout &g, const float2 *plan, int tid, int nthreads)
 {
     constexpr int M = 1 << L;
     gx_fft_dif<L, NBUF, BUFSTRIDE>(s, plan, g.tw_off, tid, nthreads);
-    if (g.bluestein) {
+    if (BLUE < 0 ? g.bluestein != 0 : BLUE != 0) {
         // circular convolution with the conjugate chirp: multiply by its spectrum
         // (stored in slot order, 1/M folded in), conjugate, transform again
         // (ifft(v) = conj(fft(conj v))).  The DIT flavour consumes slot order
@@ -298,9 +327,10 @@ GX_DEV void gx_dft_block(float2 *s, const GxFftLayout &g, const float2 *plan, in
     }
 }
 
-template <int L>
+template <int L, int BLUE = -1>
 GX_HD float2 gx_dft_result(const float2 *sb, const GxFftLayout &g, const float2 *plan, int k)
 {
-    if (g.bluestein) return gx_cmul(plan[g.chirp_off + k], gx_conj(sb[gx_phys(k)]));
+    if (BLUE < 0 ? g.bluestein != 0 : BLUE != 0)
+        return gx_cmul(plan[g.chirp_off + k], gx_conj(sb[gx_phys(k)]));
     return sb[gx_phys(gx_fft_pos<L>(k))];
 }

@@ -50,13 +50,17 @@ __device__ __forceinline__ void active_band(const ProjArgs &a, int p, int &za, i
 }
 
 // ------------------------------------------------------------------ F1 ----
-template <int L, bool SPECIES>
-__global__ void __launch_bounds__(PROJ_THREADS)
+// BLUE == false: N is a power of two (N == M): pixels are owned four at a time
+// (128-bit counter reads, 128-bit loads of the per-rotation vectors).
+// BLUE == true : arbitrary N < M through Bluestein; scalar pixel ownership.
+template <int L, bool SPECIES, bool BLUE>
+__global__ void __launch_bounds__(PROJ_THREADS, (L >= 13) ? 2 : 4)
 slice_rows_fused(FusedArgs fa)
 {
     constexpr int M = 1 << L;
     constexpr int NT = PROJ_THREADS;
-    constexpr int PER = (M + NT - 1) / NT;
+    constexpr int VW = BLUE ? 1 : 4;                       // pixels per ownership group
+    constexpr int PER = (M / VW + NT - 1) / NT;            // groups per thread
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *buf = reinterpret_cast<float2 *>(smem_raw);
     uint32_t *words = reinterpret_cast<uint32_t *>(smem_raw);   // aliases buf (used strictly before it)
@@ -70,53 +74,66 @@ slice_rows_fused(FusedArgs fa)
     const int jlo = fa.colrange[2 * p], jhi = fa.colrange[2 * p + 1];
     if (jhi <= jlo) return;
 
-    const double s = a.sn[p], c = a.cs[p], shift = a.yrange[2 * p], r = a.r, inv_r = 1.0 / a.r;
+    const double s = a.sn[p], c = a.cs[p], shift = a.yrange[2 * p];
     const int beg = a.row_start[z], end = a.row_start[z + 1];
-    float2 px[PER];
+    const float mzv = a.mz[(size_t)p * N + z];
+    const int NP = (N + 3) & ~3;                           // counter plane stride (words)
+    float2 px[PER][VW];
 #pragma unroll
-    for (int j = 0; j < PER; ++j) px[j] = make_float2(0.f, 0.f);
+    for (int j = 0; j < PER; ++j)
+#pragma unroll
+        for (int e = 0; e < VW; ++e) px[j][e] = make_float2(0.f, 0.f);
 
     if (SPECIES) {
         if (tid < GX_MAX_SPECIES) s_table[tid] = tid < a.n_species ? a.table[tid] : make_float2(0.f, 0.f);
         const int npair = (a.n_species + 1) >> 1;
-        const int nwords = npair * N;
-        for (int y = tid; y < nwords; y += NT) words[y] = 0u;
+        uint4 *words4 = reinterpret_cast<uint4 *>(smem_raw);
+        for (int y = tid; y < npair * (NP / 4); y += NT) words4[y] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
         for (int c0 = beg; c0 < end; c0 += 65535) {
             const int c1 = min(c0 + 65535, end);
-            for (int i = c0 + tid; i < c1; i += NT) {
-                double q = gx_floordiv(__dsub_rn(gx_rot_y(a.xs[i], a.ys[i], s, c), shift), r, inv_r);
-                if (q < (double)N) {
-                    const int sp = a.species[i];
-                    atomicAdd(&words[(sp >> 1) * N + (int)q], 1u << ((sp & 1) * 16));
-                }
-            }
+            scatter_species(a, c0, c1, s, c, shift, words, NP);
             __syncthreads();
             const bool more = c1 < end;
 #pragma unroll
             for (int j = 0; j < PER; ++j) {
-                const int y = tid + j * NT;
-                if (y < N) {
+                const int g = tid + j * NT;
+                if (g * VW < N) {
                     for (int w = 0; w < npair; ++w) {
-                        const uint32_t cnt = words[w * N + y];
-                        if (cnt) {
-                            const float n0 = (float)(cnt & 0xffffu), n1 = (float)(cnt >> 16);
-                            const float2 f0 = s_table[2 * w], f1 = s_table[2 * w + 1];
-                            px[j].x += n0 * f0.x + n1 * f1.x;
-                            px[j].y += n0 * f0.y + n1 * f1.y;
-                            if (more) words[w * N + y] = 0u;
+                        const float2 f0 = s_table[2 * w], f1 = s_table[2 * w + 1];
+                        if (BLUE) {
+                            const uint32_t cnt = words[w * NP + g];
+                            if (cnt) {
+                                const float n0 = (float)(cnt & 0xffffu), n1 = (float)(cnt >> 16);
+                                px[j][0].x += n0 * f0.x + n1 * f1.x;
+                                px[j][0].y += n0 * f0.y + n1 * f1.y;
+                                if (more) words[w * NP + g] = 0u;
+                            }
+                        } else {
+                            const uint4 cv = words4[w * (NP / 4) + g];
+                            if (cv.x | cv.y | cv.z | cv.w) {
+                                const uint32_t cc[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float n0 = (float)(cc[e] & 0xffffu), n1 = (float)(cc[e] >> 16);
+                                    px[j][e].x += n0 * f0.x + n1 * f1.x;
+                                    px[j][e].y += n0 * f0.y + n1 * f1.y;
+                                }
+                                if (more) words4[w * (NP / 4) + g] = make_uint4(0u, 0u, 0u, 0u);
+                            }
                         }
                     }
                 }
             }
-            __syncthreads();   // all counter reads done before the next chunk / before buf is written
+            __syncthreads();   // every counter read is done before the next chunk / before buf is written
         }
     } else {
         // generic per-atom f: accumulate straight into the (padded) row buffer
+        const double r = a.r, inv_r = 1.0 / a.r;
         for (int y = tid; y < M; y += NT) buf[gx_phys(y)] = make_float2(0.f, 0.f);
         __syncthreads();
         for (int i = beg + tid; i < end; i += NT) {
-            double q = gx_floordiv(__dsub_rn(gx_rot_y(a.xs[i], a.ys[i], s, c), shift), r, inv_r);
+            const double q = atom_y_pixel(a.xs[i], a.ys[i], s, c, shift, r, inv_r);
             if (q < (double)N) {
                 const float2 f = a.f[i];
                 float2 *dst = &buf[gx_phys((int)q)];
@@ -126,30 +143,43 @@ slice_rows_fused(FusedArgs fa)
         }
         __syncthreads();
 #pragma unroll
-        for (int j = 0; j < PER; ++j) {
-            const int y = tid + j * NT;
-            if (y < N) px[j] = buf[gx_phys(y)];
-        }
+        for (int j = 0; j < PER; ++j)
+#pragma unroll
+            for (int e = 0; e < VW; ++e) {
+                const int y = (tid + j * NT) * VW + e;
+                if (y < N) px[j][e] = buf[gx_phys(y)];
+            }
         __syncthreads();
     }
 
     // complete the row (pedestal-free) and stage it for the transform
-    const int4 bb = make_int4(a.bbox[4 * p], a.bbox[4 * p + 1], a.bbox[4 * p + 2], a.bbox[4 * p + 3]);
-    const float mzv = a.sigma > 0 ? a.mz[(size_t)p * N + z] : 1.f;
+    const size_t vo = (size_t)p * N;
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
-        const int y = tid + j * NT;
-        if (y < M) {
-            float2 v = make_float2(0.f, 0.f);
-            if (y < N) {
-                v = finish_pixel(a, p, z, y, px[j], bb, mzv);
-                if (fa.lay.bluestein) v = gx_cmul(v, fa.plan[fa.lay.chirp_off + y]);
+        const int g = tid + j * NT;
+        if (BLUE) {
+            if (g < M) {
+                float2 v = make_float2(0.f, 0.f);
+                if (g < N) {
+                    v = finish_pixel(px[j][0], a.base[vo + g], mzv * a.my[vo + g]);
+                    v = gx_cmul(v, fa.plan[fa.lay.chirp_off + g]);
+                }
+                buf[gx_phys(g)] = v;
             }
-            buf[gx_phys(y)] = v;
+        } else if (g * 4 < N) {
+            const int y0 = g * 4;
+            const float4 b01 = *reinterpret_cast<const float4 *>(a.base + vo + y0);
+            const float4 b23 = *reinterpret_cast<const float4 *>(a.base + vo + y0 + 2);
+            const float4 m4 = *reinterpret_cast<const float4 *>(a.my + vo + y0);
+            float2 *dst = buf + gx_phys(y0);               // 4 consecutive pixels stay contiguous when padded
+            dst[0] = finish_pixel(px[j][0], make_float2(b01.x, b01.y), mzv * m4.x);
+            dst[1] = finish_pixel(px[j][1], make_float2(b01.z, b01.w), mzv * m4.y);
+            dst[2] = finish_pixel(px[j][2], make_float2(b23.x, b23.y), mzv * m4.z);
+            dst[3] = finish_pixel(px[j][3], make_float2(b23.z, b23.w), mzv * m4.w);
         }
     }
     __syncthreads();
-    gx_dft_block<L, 1, 0>(buf, fa.lay, fa.plan, tid, NT);
+    gx_dft_block<L, 1, 0, BLUE ? 1 : 0>(buf, fa.lay, fa.plan, tid, NT);
 
     // kept q-columns only; shifted column j holds unshifted coefficient j - N/2 (mod N)
     float2 *dst = fa.work + ((size_t)p * N + z) * fa.KC;
@@ -157,12 +187,12 @@ slice_rows_fused(FusedArgs fa)
     for (int jj = tid; jj < jhi - jlo; jj += NT) {
         int k = jlo + jj - half;
         if (k < 0) k += N;
-        dst[jj] = gx_dft_result<L>(buf, fa.lay, fa.plan, k);
+        dst[jj] = gx_dft_result<L, BLUE ? 1 : 0>(buf, fa.lay, fa.plan, k);
     }
 }
 
 // ------------------------------------------------------------------ F2 ----
-template <int L, int TC>
+template <int L, int TC, bool BLUE>
 __global__ void __launch_bounds__(512)
 slice_cols_fused(FusedArgs fa)
 {
@@ -190,12 +220,12 @@ slice_cols_fused(FusedArgs fa)
         float2 v = make_float2(0.f, 0.f);
         if (n >= za && n <= zb && jj0 + cc < kc) {
             v = src[(size_t)n * fa.KC + cc];
-            if (fa.lay.bluestein) v = gx_cmul(v, fa.plan[fa.lay.chirp_off + n]);
+            if (BLUE) v = gx_cmul(v, fa.plan[fa.lay.chirp_off + n]);
         }
         smem[cc * BS + gx_phys(n)] = v;
     }
     __syncthreads();
-    gx_dft_block<L, TC, BS>(smem, fa.lay, fa.plan, tid, nt);
+    gx_dft_block<L, TC, BS, BLUE ? 1 : 0>(smem, fa.lay, fa.plan, tid, nt);
 
     const int half = N / 2;
     const int kr = fa.row_hi - fa.row_lo;
@@ -211,7 +241,7 @@ slice_cols_fused(FusedArgs fa)
         if (iz < 0) continue;
         int kz = i - half;
         if (kz < 0) kz += N;
-        float2 v = gx_dft_result<L>(smem + cc * BS, fa.lay, fa.plan, kz);
+        float2 v = gx_dft_result<L, BLUE ? 1 : 0>(smem + cc * BS, fa.lay, fa.plan, kz);
         if (kz == 0 && j == half) { v.x += fa.dc_re; v.y += fa.dc_im; }
         atomicAdd(&fa.vsum[(size_t)yx * fa.q_num + iz], v.x * v.x + v.y * v.y);
     }
@@ -250,9 +280,10 @@ static int launch_fused(const FusedArgs &fa, bool species, cudaStream_t st)
     constexpr int WANT = (16 / TC) % 16;
     constexpr int BS = BS0 + ((WANT - (BS0 % 16)) + 16) % 16;
     const int N = fa.proj.N;
+    const bool blue = fa.lay.bluestein != 0;
     size_t smem1 = (size_t)gx_phys_len(M) * sizeof(float2);
     if (species) {
-        size_t w = (size_t)((fa.proj.n_species + 1) / 2) * N * sizeof(uint32_t);
+        size_t w = (size_t)((fa.proj.n_species + 1) / 2) * ((N + 3) & ~3) * sizeof(uint32_t);
         if (w > smem1) smem1 = w;
     }
     const size_t smem2 = (size_t)BS * TC * sizeof(float2);
@@ -260,18 +291,29 @@ static int launch_fused(const FusedArgs &fa, bool species, cudaStream_t st)
         gx_set_error("gx_slices_fused: shared memory need (%zu / %zu B) exceeds 227 KB", smem1, smem2);
         return GX_ERR_UNSUPPORTED;
     }
-    if (species) {
-        GX_CUDA(cudaFuncSetAttribute(slice_rows_fused<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-        slice_rows_fused<L, true><<<dim3(fa.n_phi, N), PROJ_THREADS, smem1, st>>>(fa);
-    } else {
-        GX_CUDA(cudaFuncSetAttribute(slice_rows_fused<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-        slice_rows_fused<L, false><<<dim3(fa.n_phi, N), PROJ_THREADS, smem1, st>>>(fa);
-    }
+    const dim3 grid1(fa.n_phi, N);
+#define GX_LAUNCH_ROWS(SP, BL)                                                                              \
+    do {                                                                                                    \
+        GX_CUDA(cudaFuncSetAttribute(slice_rows_fused<L, SP, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)smem1));                                                          \
+        slice_rows_fused<L, SP, BL><<<grid1, PROJ_THREADS, smem1, st>>>(fa);                               \
+    } while (0)
+    if (species && blue) GX_LAUNCH_ROWS(true, true);
+    else if (species) GX_LAUNCH_ROWS(true, false);
+    else if (blue) GX_LAUNCH_ROWS(false, true);
+    else GX_LAUNCH_ROWS(false, false);
+#undef GX_LAUNCH_ROWS
     if (int e = gx_check_launch("slice_rows_fused")) return e;
-    GX_CUDA(cudaFuncSetAttribute(slice_cols_fused<L, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     int nt = TC * M / 16;
     nt = nt < 64 ? 64 : (nt > 512 ? 512 : nt);
-    slice_cols_fused<L, TC><<<dim3(fa.n_phi, (fa.KC + TC - 1) / TC), nt, smem2, st>>>(fa);
+    const dim3 grid2(fa.n_phi, (fa.KC + TC - 1) / TC);
+    if (blue) {
+        GX_CUDA(cudaFuncSetAttribute(slice_cols_fused<L, TC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        slice_cols_fused<L, TC, true><<<grid2, nt, smem2, st>>>(fa);
+    } else {
+        GX_CUDA(cudaFuncSetAttribute(slice_cols_fused<L, TC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        slice_cols_fused<L, TC, false><<<grid2, nt, smem2, st>>>(fa);
+    }
     return gx_check_launch("slice_cols_fused");
 }
 
@@ -284,7 +326,7 @@ extern "C" int gx_slices_fused(const gx_fused_args *h, void *stream)
     GX_REQUIRE(h->n_species >= 0 && h->n_species <= GX_MAX_SPECIES, "n_species out of range");
     GX_REQUIRE(h->n_species == 0 ? h->d_f != NULL : (h->d_species != NULL && h->d_table != NULL),
                "species/f inputs missing");
-    GX_REQUIRE(h->smooth_sigma <= 0 || (h->d_my && h->d_mz), "smooth needs mask buffers");
+    GX_REQUIRE(h->d_my && h->d_mz, "mask vectors missing");
     GX_REQUIRE(h->n_phi > 0 && h->n_phi <= 65535 && h->N >= 16 && h->KC > 0 && h->q_num > 0, "bad sizes");
     GX_REQUIRE(h->row_lo >= 0 && h->row_hi <= h->N && h->row_lo <= h->row_hi, "bad kept-row range");
     FusedArgs fa;

@@ -64,6 +64,7 @@ slice_vectors_kernel(const gx_chord *__restrict__ chord, const int32_t *__restri
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const size_t o = (size_t)p * N + i;
+    const int y_min = bbox[4 * p + 0], y_max = bbox[4 * p + 1], z_min = bbox[4 * p + 2], z_max = bbox[4 * p + 3];
     if (fill_bkg) {
         const gx_chord k = chord[p];
         const double inv_r = 1.0 / r;
@@ -76,13 +77,22 @@ slice_vectors_kernel(const gx_chord *__restrict__ chord, const int32_t *__restri
     } else {
         base[o] = make_float2((float)-ped_re, (float)-ped_im);
     }
+    float vy = 1.f, vz = 1.f;
     if (sigma > 0) {
         int lo, hi;
-        py_slice(bbox[4 * p + 0] + sigma, bbox[4 * p + 1] - sigma, N, lo, hi);
-        my[o] = smoothed_box(i, lo, hi, N, gauss, radius);
-        py_slice(bbox[4 * p + 2] + sigma, bbox[4 * p + 3] - sigma, N, lo, hi);
-        mz[o] = smoothed_box(i, lo, hi, N, gauss, radius);
+        py_slice(y_min + sigma, y_max - sigma, N, lo, hi);
+        vy = smoothed_box(i, lo, hi, N, gauss, radius);
+        py_slice(z_min + sigma, z_max - sigma, N, lo, hi);
+        vz = smoothed_box(i, lo, hi, N, gauss, radius);
     }
+    if (fill_bkg) {
+        // voxelgrids.py:358-361: rows < z_min or >= z_max and columns <= y_min or
+        // >= y_max are overwritten with the pedestal, i.e. are 0 relative to it
+        if (!(i > y_min && i < y_max)) vy = 0.f;
+        if (!(i >= z_min && i < z_max)) vz = 0.f;
+    }
+    my[o] = vy;
+    mz[o] = vz;
 }
 
 extern "C" int gx_slice_vectors(const gx_chord *d_chord, const int32_t *d_bbox, int n_phi, int N, double r,
@@ -91,9 +101,9 @@ extern "C" int gx_slice_vectors(const gx_chord *d_chord, const int32_t *d_bbox, 
                                 int fill_bkg, int smooth_sigma, const double *d_gauss, int gauss_radius,
                                 gx_float2 *d_base, float *d_my, float *d_mz, void *stream)
 {
-    GX_REQUIRE(d_bbox && d_base, "NULL pointer");
+    GX_REQUIRE(d_bbox && d_base && d_my && d_mz, "NULL pointer");
     GX_REQUIRE(!fill_bkg || d_chord, "fill_bkg needs chord constants");
-    GX_REQUIRE(smooth_sigma <= 0 || (d_gauss && d_my && d_mz), "smooth needs weights and mask buffers");
+    GX_REQUIRE(smooth_sigma <= 0 || d_gauss, "smooth needs Gaussian weights");
     GX_REQUIRE(n_phi > 0 && N >= 16, "bad sizes");
     slice_vectors_kernel<<<dim3((N + 255) / 256, n_phi), 256, 0, gx_stream(stream)>>>(
         d_chord, d_bbox, N, r, max_voxels, avg_f_re, avg_f_im, pedestal_re, pedestal_im, fill_bkg,
@@ -101,6 +111,8 @@ extern "C" int gx_slice_vectors(const gx_chord *d_chord, const int32_t *d_bbox, 
     return gx_check_launch("gx_slice_vectors");
 }
 
+// ------------------------------------------------------- staged row kernel ----
+// Writes the reference's pre-FFT grid (parity probe T2 and the unfused path).
 template <bool SPECIES>
 __global__ void __launch_bounds__(PROJ_THREADS)
 project_rows_kernel(ProjArgs a, float2 *grid)
@@ -110,15 +122,51 @@ project_rows_kernel(ProjArgs a, float2 *grid)
     uint32_t *words = reinterpret_cast<uint32_t *>(acc + a.N);
     __shared__ float2 s_table[GX_MAX_SPECIES];
     const int z = blockIdx.x, p = blockIdx.y;
-    if (SPECIES && threadIdx.x < GX_MAX_SPECIES)
-        s_table[threadIdx.x] = threadIdx.x < a.n_species ? a.table[threadIdx.x] : make_float2(0.f, 0.f);
-    scatter_row<SPECIES>(a, p, z, acc, words, s_table);
-    const int4 bb = make_int4(a.bbox[4 * p], a.bbox[4 * p + 1], a.bbox[4 * p + 2], a.bbox[4 * p + 3]);
-    const float mzv = a.sigma > 0 ? a.mz[(size_t)p * a.N + z] : 1.f;
+    const int N = a.N, tid = threadIdx.x, nt = blockDim.x;
+    const int npair = (a.n_species + 1) >> 1;
+    const double s = a.sn[p], c = a.cs[p], shift = a.yrange[2 * p];
+    if (SPECIES && tid < GX_MAX_SPECIES) s_table[tid] = tid < a.n_species ? a.table[tid] : make_float2(0.f, 0.f);
+    for (int y = tid; y < N; y += nt) acc[y] = make_float2(0.f, 0.f);
+    if (SPECIES) for (int y = tid; y < npair * N; y += nt) words[y] = 0u;
+    __syncthreads();
+    const int beg = a.row_start[z], end = a.row_start[z + 1];
+    if (SPECIES) {
+        for (int c0 = beg; c0 < end; c0 += 65535) {      // 16-bit counters cannot wrap
+            scatter_species(a, c0, min(c0 + 65535, end), s, c, shift, words, N);
+            __syncthreads();
+            for (int y = tid; y < N; y += nt) {
+                float2 v = acc[y];
+                for (int w = 0; w < npair; ++w) {
+                    const uint32_t cnt = words[w * N + y];
+                    if (cnt) {
+                        const float n0 = (float)(cnt & 0xffffu), n1 = (float)(cnt >> 16);
+                        const float2 f0 = s_table[2 * w], f1 = s_table[2 * w + 1];
+                        v.x += n0 * f0.x + n1 * f1.x;
+                        v.y += n0 * f0.y + n1 * f1.y;
+                        words[w * N + y] = 0u;
+                    }
+                }
+                acc[y] = v;
+            }
+            __syncthreads();
+        }
+    } else {
+        const double r = a.r, inv_r = 1.0 / a.r;
+        for (int i = beg + tid; i < end; i += nt) {
+            const double q = atom_y_pixel(a.xs[i], a.ys[i], s, c, shift, r, inv_r);
+            if (q < (double)N) {
+                const float2 f = a.f[i];
+                atomicAdd(&acc[(int)q].x, f.x);
+                atomicAdd(&acc[(int)q].y, f.y);
+            }
+        }
+        __syncthreads();
+    }
+    const float mzv = a.mz[(size_t)p * N + z];
     const bool has_ped = a.fill_bkg || a.sigma > 0;
-    float2 *dst = grid + ((size_t)p * a.N + z) * a.N;
-    for (int y = threadIdx.x; y < a.N; y += blockDim.x) {
-        float2 v = finish_pixel(a, p, z, y, acc[y], bb, mzv);
+    float2 *dst = grid + ((size_t)p * N + z) * N;
+    for (int y = tid; y < N; y += nt) {
+        float2 v = finish_pixel(acc[y], a.base[(size_t)p * N + y], mzv * a.my[(size_t)p * N + y]);
         if (has_ped) { v.x += a.ped_re; v.y += a.ped_im; }
         dst[y] = v;
     }
@@ -133,10 +181,10 @@ extern "C" int gx_project_slices(const double *d_xs, const double *d_ys, const u
                                  double pedestal_re, double pedestal_im, int fill_bkg, int smooth_sigma,
                                  gx_float2 *d_grid, void *stream)
 {
-    GX_REQUIRE(d_xs && d_ys && d_row_start && d_sin && d_cos && d_yrange && d_bbox && d_base && d_grid, "NULL pointer");
+    GX_REQUIRE(d_xs && d_ys && d_row_start && d_sin && d_cos && d_yrange && d_bbox && d_base && d_my && d_mz &&
+               d_grid, "NULL pointer");
     GX_REQUIRE(n_species >= 0 && n_species <= GX_MAX_SPECIES, "n_species out of range");
     GX_REQUIRE(n_species == 0 ? d_f != NULL : (d_species != NULL && d_table != NULL), "species/f inputs missing");
-    GX_REQUIRE(smooth_sigma <= 0 || (d_my && d_mz), "smooth needs mask buffers");
     GX_REQUIRE(n_phi > 0 && N >= 16, "bad sizes");
     ProjArgs a;
     a.xs = d_xs; a.ys = d_ys; a.species = d_species; a.f = reinterpret_cast<const float2 *>(d_f);

@@ -304,9 +304,9 @@ class SliceEngine:
             host = np.frombuffer(ch, dtype=np.uint8).copy()
             t["chord"] = _dev(host, dev)
             d_chord = t["chord"]
-        if self.sigma > 0:
-            t["my"] = torch.empty(n * N, dtype=torch.float32, device=dev)
-            t["mz"] = torch.empty(n * N, dtype=torch.float32, device=dev)
+        # blend mask x "inside the atom box" indicator per column / per row
+        t["my"] = torch.empty(n * N, dtype=torch.float32, device=dev)
+        t["mz"] = torch.empty(n * N, dtype=torch.float32, device=dev)
         call("gx_slice_vectors", ptr(d_chord), ptr(t["bbox"]), n, N, self.r, float(self.max_voxels),
              self.avg_voxel_f.real, self.avg_voxel_f.imag, self.pedestal.real, self.pedestal.imag,
              int(self.fill_bkg), self.sigma, ptr(self.gauss), self.gauss_radius,

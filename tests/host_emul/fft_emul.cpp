@@ -44,3 +44,12 @@ extern "C" int emul_dft(int N, const float *plan, const float *in, float *out)
     }
     return 0;
 }
+
+// 1 iff the "one base register + immediate offsets" addressing used by
+// gx_fft_pass is exact for every pass of every schedule.
+extern "C" int emul_offsets_ok()
+{
+    return gx_fft_offsets_ok<4>() & gx_fft_offsets_ok<5>() & gx_fft_offsets_ok<6>() & gx_fft_offsets_ok<7>() &
+           gx_fft_offsets_ok<8>() & gx_fft_offsets_ok<9>() & gx_fft_offsets_ok<10>() & gx_fft_offsets_ok<11>() &
+           gx_fft_offsets_ok<12>() & gx_fft_offsets_ok<13>();
+}

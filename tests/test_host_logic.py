@@ -145,3 +145,9 @@ def test_gaussian_weights_match_scipy():
         k = gaussian_filter1d(delta, sigma=sigma, mode="wrap")
         assert np.array_equal(k[n // 2 - radius:n // 2 + radius + 1], w)
         assert radius == int(4 * sigma + 0.5)
+
+
+def test_fft_pass_address_identity(fft_emul):
+    """gx_phys(base + S*n) == gx_phys(base) + gx_phys(S*n) for every butterfly of every
+    pass of every schedule (the kernels rely on it for immediate-offset addressing)."""
+    assert fft_emul.emul_offsets_ok() == 1
