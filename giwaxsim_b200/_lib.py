@@ -56,6 +56,8 @@ _PROTOTYPES = {
     "gx_coords_minmax": (_i, [_p, _i64, _p, _p]),
     "gx_atoms_sort_rows": (_i, [_p, _i64, _d, _d, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gx_slice_yrange": (_i, [_p, _p, _i64, _p, _p, _i, _p, _p]),
+    "gx_extreme_atoms": (_i, [_p, _p, _i64, _p, _p, _p, _i, _p, _p]),
+    "gx_hull_filter": (_i, [_p, _p, _i64, _p, _i, _d, _p, _p, _p, _i, _p]),
     "gx_slice_bbox": (_i, [_p, _p, _p, _i, _d, _p, _p, _p, _i, _p, _p, _p]),
     "gx_atom_pixel_indices": (_i, [_p, _p, _p, _p, _i64, _i, _d, _d, _d, _d, _p, _p, _p]),
     "gx_slice_vectors": (_i, [_p, _p, _i, _i, _d, _d, _d, _d, _d, _d, _i, _i, _p, _i, _p, _p, _p, _p]),
@@ -115,7 +117,7 @@ _LAUNCHES = {
     "gx_slice_vectors": 1, "gx_project_slices": 1, "gx_fft2_abs2_shift": 2, "gx_slice_col_index": 1,
     "gx_axis_col_index": 1, "gx_axis_row_index": 1, "gx_bin_slices": 1, "gx_row_histogram": 1,
     "gx_voxel_finalize": 1, "gx_rotate_points": 1, "gx_detector_accumulate": 1, "gx_detector_epilogue": 1,
-    "gx_slices_fused": 2, "gx_slice_col_range": 1,
+    "gx_slices_fused": 2, "gx_slice_col_range": 1, "gx_extreme_atoms": 1, "gx_hull_filter": 1,
 }
 _launch_count = 0
 

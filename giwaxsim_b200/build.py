@@ -18,7 +18,7 @@ SOURCES = ["gx_api.cu", "gx_atoms.cu", "gx_project.cu", "gx_fft.cu", "gx_bin.cu"
            "gx_fused.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
-         "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=default", "--expt-relaxed-constexpr",
+         "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=default", "--expt-relaxed-constexpr", "-DGX_TWP=1",
          "-Xptxas", "-v"]
 
 

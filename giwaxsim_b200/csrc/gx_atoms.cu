@@ -374,3 +374,80 @@ extern "C" int gx_atom_pixel_indices(const double *d_xs, const double *d_ys, con
         d_xs, d_ys, d_perm, d_row_start, A, N, r, sin_phi, cos_phi, y_shift, d_y_idx, d_z_idx);
     return gx_check_launch("gx_atom_pixel_indices");
 }
+
+// ------------------------------------------------- extreme-atom candidates ----
+// min/max of y' over all atoms is needed for every rotation (voxelgrids.py:323)
+// but only atoms on (or within eps of) the boundary of the 2-D convex hull of
+// the (x, y) positions can attain it.  The host builds an inner polygon from the
+// atoms that are extreme along a few dozen directions (gx_extreme_atoms), and
+// gx_hull_filter keeps the atoms that are not strictly inside it by more than
+// eps: if an atom is at distance d inside a polygon whose vertices are atoms,
+// some vertex beats it by at least d in every direction, so dropping it cannot
+// change any rounded min or max as long as d >> 1 ulp of the coordinates.
+__global__ void __launch_bounds__(ATOM_THREADS)
+extreme_atoms_kernel(const double *__restrict__ xs, const double *__restrict__ ys, int64_t A,
+                     const double *__restrict__ d_sin, const double *__restrict__ d_cos,
+                     const double *__restrict__ yrange, int n, int32_t *index)
+{
+    __shared__ double s_sin[64], s_cos[64], s_lo[64], s_hi[64];
+    for (int p = threadIdx.x; p < n; p += blockDim.x) {
+        s_sin[p] = d_sin[p]; s_cos[p] = d_cos[p]; s_lo[p] = yrange[2 * p]; s_hi[p] = yrange[2 * p + 1];
+    }
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = xs[i], y = ys[i];
+        for (int p = 0; p < n; ++p) {
+            const double v = gx_rot_y(x, y, s_sin[p], s_cos[p]);
+            if (v == s_lo[p]) atomicMin(&index[2 * p], (int32_t)i);
+            if (v == s_hi[p]) atomicMin(&index[2 * p + 1], (int32_t)i);
+        }
+    }
+}
+
+extern "C" int gx_extreme_atoms(const double *d_xs, const double *d_ys, int64_t A,
+                                const double *d_sin, const double *d_cos, const double *d_yrange, int n,
+                                int32_t *d_index, void *stream)
+{
+    GX_REQUIRE(d_xs && d_ys && d_sin && d_cos && d_yrange && d_index, "NULL pointer");
+    GX_REQUIRE(A > 0 && n > 0 && n <= 64, "need 1..64 directions");
+    cudaStream_t st = gx_stream(stream);
+    GX_CUDA(cudaMemsetAsync(d_index, 0x7f, (size_t)2 * n * sizeof(int32_t), st));
+    int64_t blocks = (A + ATOM_THREADS - 1) / ATOM_THREADS;
+    if (blocks > GX_SM_COUNT * 8) blocks = GX_SM_COUNT * 8;
+    extreme_atoms_kernel<<<(int)blocks, ATOM_THREADS, 0, st>>>(d_xs, d_ys, A, d_sin, d_cos, d_yrange, n, d_index);
+    return gx_check_launch("gx_extreme_atoms");
+}
+
+__global__ void __launch_bounds__(ATOM_THREADS)
+hull_filter_kernel(const double *__restrict__ xs, const double *__restrict__ ys, int64_t A,
+                   const double *__restrict__ edges, int m, double eps, int32_t *count,
+                   double *xs_out, double *ys_out, int capacity)
+{
+    __shared__ double s_e[64 * 3];
+    for (int k = threadIdx.x; k < 3 * m; k += blockDim.x) s_e[k] = edges[k];
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = xs[i], y = ys[i];
+        double depth = INFINITY;                 // signed distance to the nearest edge, inside > 0
+        for (int k = 0; k < m; ++k) depth = fmin(depth, s_e[3 * k] * x + s_e[3 * k + 1] * y + s_e[3 * k + 2]);
+        if (!(depth > eps)) {
+            const int slot = atomicAdd(count, 1);
+            if (slot < capacity) { xs_out[slot] = x; ys_out[slot] = y; }
+        }
+    }
+}
+
+extern "C" int gx_hull_filter(const double *d_xs, const double *d_ys, int64_t A, const double *d_edges, int m,
+                              double eps, int32_t *d_count, double *d_xs_out, double *d_ys_out, int capacity,
+                              void *stream)
+{
+    GX_REQUIRE(d_xs && d_ys && d_edges && d_count && d_xs_out && d_ys_out, "NULL pointer");
+    GX_REQUIRE(A > 0 && m >= 3 && m <= 64 && capacity > 0 && eps > 0.0, "bad polygon or capacity");
+    cudaStream_t st = gx_stream(stream);
+    GX_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int32_t), st));
+    int64_t blocks = (A + ATOM_THREADS - 1) / ATOM_THREADS;
+    if (blocks > GX_SM_COUNT * 8) blocks = GX_SM_COUNT * 8;
+    hull_filter_kernel<<<(int)blocks, ATOM_THREADS, 0, st>>>(d_xs, d_ys, A, d_edges, m, eps, d_count, d_xs_out,
+                                                             d_ys_out, capacity);
+    return gx_check_launch("gx_hull_filter");
+}

@@ -182,6 +182,41 @@ template <> struct GxDft<16> {
     }
 };
 
+// ---- twiddles of one butterfly ---------------------------------------------
+// v[k] *= W^{t k}, k = 1..R-1, table row k-1 at twt[(k-1)*S].
+// TWP == 0: every factor is read from the table (fp32-rounded exact values).
+// TWP == 1: only W^t, W^2t, W^4t, W^8t are read; the others are products of at
+//           most three of them.  4 loads instead of 15 per radix-16 butterfly --
+//           the kernels are bound by the L1/shared-memory pipe, not by FMA -- at
+//           the price of twiddles accurate to ~2e-7 instead of 6e-8.
+#ifndef GX_TWP
+#define GX_TWP 0
+#endif
+template <int R, int S, int TWP>
+GX_HD void gx_apply_twiddles(float2 *v, const float2 *twt)
+{
+    if (TWP == 0 || R <= 4) {
+#pragma unroll
+        for (int k = 1; k < R; ++k) v[k] = gx_cmul(v[k], twt[(k - 1) * S]);
+    } else {
+        const float2 w1 = twt[0], w2 = twt[S], w4 = twt[3 * S];
+        const float2 w3 = gx_cmul(w1, w2), w5 = gx_cmul(w1, w4), w6 = gx_cmul(w2, w4), w7 = gx_cmul(w3, w4);
+        v[1] = gx_cmul(v[1], w1); v[2] = gx_cmul(v[2], w2); v[3] = gx_cmul(v[3], w3); v[4] = gx_cmul(v[4], w4);
+        v[5] = gx_cmul(v[5], w5); v[6] = gx_cmul(v[6], w6); v[7] = gx_cmul(v[7], w7);
+        if (R > 8) {
+            const float2 w8 = twt[7 * S];
+            v[8 % R] = gx_cmul(v[8 % R], w8);
+            v[9 % R] = gx_cmul(v[9 % R], gx_cmul(w1, w8));
+            v[10 % R] = gx_cmul(v[10 % R], gx_cmul(w2, w8));
+            v[11 % R] = gx_cmul(v[11 % R], gx_cmul(w3, w8));
+            v[12 % R] = gx_cmul(v[12 % R], gx_cmul(w4, w8));
+            v[13 % R] = gx_cmul(v[13 % R], gx_cmul(w5, w8));
+            v[14 % R] = gx_cmul(v[14 % R], gx_cmul(w6, w8));
+            v[15 % R] = gx_cmul(v[15 % R], gx_cmul(w7, w8));
+        }
+    }
+}
+
 // ---- one pass over NBUF independent buffers of length M --------------------
 // s: shared array holding NBUF padded buffers, buffer j at s + j*BUFSTRIDE.
 // DIT == false: butterfly then twiddle (decimation in frequency, natural in ->
@@ -189,7 +224,7 @@ template <> struct GxDft<16> {
 // DIT == true : twiddle then butterfly (decimation in time, digit-reversed in
 //               -> natural out, passes run last to first).  Same geometry and
 //               the same twiddle table W_{S R}^{t k}.
-template <int R, int S, int M, int NBUF, int BUFSTRIDE, bool DIT>
+template <int R, int S, int M, int NBUF, int BUFSTRIDE, bool DIT, int TWP = GX_TWP>
 GX_HD void gx_fft_pass(float2 *s, const float2 *tw, int tid, int nthreads)
 {
     constexpr int NBFLY = M / R;
@@ -203,22 +238,30 @@ GX_HD void gx_fft_pass(float2 *s, const float2 *tw, int tid, int nthreads)
         // GxSched (no carries across the pad boundaries; checked exhaustively by
         // tests/host_emul), so the R addresses are one register plus immediates.
         float2 *sb = s + buf * BUFSTRIDE + gx_phys(base);
-        const float2 *twt = tw + t;
         float2 v[R];
 #pragma unroll
         for (int n = 0; n < R; ++n) v[n] = sb[gx_phys(S * n)];
-        if (DIT && S > 1) {
-#pragma unroll
-            for (int k = 1; k < R; ++k) v[k] = gx_cmul(v[k], twt[(k - 1) * S]);
-        }
+        if (DIT && S > 1) gx_apply_twiddles<R, S, TWP>(v, tw + t);
         GxDft<R>::run(v);
-        if (!DIT && S > 1) {
-#pragma unroll
-            for (int k = 1; k < R; ++k) v[k] = gx_cmul(v[k], twt[(k - 1) * S]);
-        }
+        if (!DIT && S > 1) gx_apply_twiddles<R, S, TWP>(v, tw + t);
 #pragma unroll
         for (int k = 0; k < R; ++k) sb[gx_phys(S * k)] = v[k];
     }
+}
+
+// First DIF pass of one butterfly whose R0 inputs are already in registers
+// (element n of butterfly t is x[t + S0*n]): butterfly, twiddle, store.  Lets
+// a producer hand its row to the transform without a shared-memory round trip.
+template <int L, int TWP = GX_TWP>
+GX_HD void gx_fft_pass0_from_regs(float2 *v, float2 *s, const float2 *tw, int t)
+{
+    typedef GxSched<L> Sc;
+    constexpr int R = Sc::R0, S = (1 << L) / Sc::R0;
+    GxDft<R>::run(v);
+    if (S > 1) gx_apply_twiddles<R, S, TWP>(v, tw + t);
+    float2 *sb = s + gx_phys(t);
+#pragma unroll
+    for (int k = 0; k < R; ++k) sb[gx_phys(S * k)] = v[k];
 }
 
 // exhaustive check of the address identity used above (host tests)
@@ -256,6 +299,26 @@ static inline int gx_fft_offsets_ok()
 // slot gx_fft_pos<L>(k).  On the device every thread of the block calls this
 // (it contains __syncthreads); the host-emulation build calls it with
 // nthreads == 1, which runs the passes sequentially.
+// passes 1 .. NP-1 of the DIF transform (pass 0 done by the caller)
+template <int L, int NBUF, int BUFSTRIDE>
+GX_DEV void gx_fft_dif_tail(float2 *s, const float2 *tw, const int *tw_off, int tid, int nthreads)
+{
+    typedef GxSched<L> Sc;
+    constexpr int M = 1 << L;
+    if constexpr (Sc::NP > 1) {
+        gx_fft_pass<Sc::R1, M / Sc::R0 / Sc::R1, M, NBUF, BUFSTRIDE, false>(s, tw + tw_off[1], tid, nthreads);
+        GX_BLOCK_SYNC();
+    }
+    if constexpr (Sc::NP > 2) {
+        gx_fft_pass<Sc::R2, M / Sc::R0 / Sc::R1 / Sc::R2, M, NBUF, BUFSTRIDE, false>(s, tw + tw_off[2], tid, nthreads);
+        GX_BLOCK_SYNC();
+    }
+    if constexpr (Sc::NP > 3) {
+        gx_fft_pass<Sc::R3, M / Sc::R0 / Sc::R1 / Sc::R2 / Sc::R3, M, NBUF, BUFSTRIDE, false>(s, tw + tw_off[3], tid, nthreads);
+        GX_BLOCK_SYNC();
+    }
+}
+
 template <int L, int NBUF, int BUFSTRIDE>
 GX_DEV void gx_fft_dif(float2 *s, const float2 *tw, const int *tw_off, int tid, int nthreads)
 {
@@ -306,11 +369,14 @@ GX_DEV void gx_fft_dit(float2 *s, const float2 *tw, const int *tw_off, int tid, 
 // Output: read coefficient k with gx_dft_result<L>().
 // BLUE: -1 decide at run time from g.bluestein, 0 / 1 fixed at compile time (the
 // hot kernels are instantiated per flavour so no test sits in their loops).
-template <int L, int NBUF, int BUFSTRIDE, int BLUE = -1>
+// PASS0_DONE: the caller already ran the first DIF pass (gx_fft_pass0_from_regs)
+// and synchronised.
+template <int L, int NBUF, int BUFSTRIDE, int BLUE = -1, bool PASS0_DONE = false>
 GX_DEV void gx_dft_block(float2 *s, const GxFftLayout &g, const float2 *plan, int tid, int nthreads)
 {
     constexpr int M = 1 << L;
-    gx_fft_dif<L, NBUF, BUFSTRIDE>(s, plan, g.tw_off, tid, nthreads);
+    if (PASS0_DONE) gx_fft_dif_tail<L, NBUF, BUFSTRIDE>(s, plan, g.tw_off, tid, nthreads);
+    else gx_fft_dif<L, NBUF, BUFSTRIDE>(s, plan, g.tw_off, tid, nthreads);
     if (BLUE < 0 ? g.bluestein != 0 : BLUE != 0) {
         // circular convolution with the conjugate chirp: multiply by its spectrum
         // (stored in slot order, 1/M folded in), conjugate, transform again

@@ -23,6 +23,10 @@
 #include "gx_project.cuh"
 #include "gx_fft_engine.cuh"
 
+#ifndef GX_F1_MINBLOCKS
+#define GX_F1_MINBLOCKS 4   // CTAs/SM the row kernel is compiled for (3 would leave ~84 KB of L1: measured no faster)
+#endif
+
 struct FusedArgs {
     ProjArgs proj;
     GxFftLayout lay;
@@ -50,17 +54,20 @@ __device__ __forceinline__ void active_band(const ProjArgs &a, int p, int &za, i
 }
 
 // ------------------------------------------------------------------ F1 ----
-// BLUE == false: N is a power of two (N == M): pixels are owned four at a time
-// (128-bit counter reads, 128-bit loads of the per-rotation vectors).
-// BLUE == true : arbitrary N < M through Bluestein; scalar pixel ownership.
+// Pixel ownership follows the first FFT pass: butterfly t of pass 0 combines the
+// pixels t + S0*n (n < R0), so the thread that runs butterfly t also gathers the
+// species counts of exactly those pixels, completes them in registers and feeds
+// them straight into its radix-R0 butterfly: the finished row is never written
+// to shared memory in natural order and never read back by pass 0.
 template <int L, bool SPECIES, bool BLUE>
-__global__ void __launch_bounds__(PROJ_THREADS, (L >= 13) ? 2 : 4)
+__global__ void __launch_bounds__(PROJ_THREADS, (L >= 13) ? 2 : GX_F1_MINBLOCKS)
 slice_rows_fused(FusedArgs fa)
 {
+    typedef GxSched<L> Sc;
     constexpr int M = 1 << L;
     constexpr int NT = PROJ_THREADS;
-    constexpr int VW = BLUE ? 1 : 4;                       // pixels per ownership group
-    constexpr int PER = (M / VW + NT - 1) / NT;            // groups per thread
+    constexpr int R0 = Sc::R0, S0 = M / R0;
+    constexpr int NB0 = (S0 + NT - 1) / NT;                // pass-0 butterflies per thread
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *buf = reinterpret_cast<float2 *>(smem_raw);
     uint32_t *words = reinterpret_cast<uint32_t *>(smem_raw);   // aliases buf (used strictly before it)
@@ -78,11 +85,11 @@ slice_rows_fused(FusedArgs fa)
     const int beg = a.row_start[z], end = a.row_start[z + 1];
     const float mzv = a.mz[(size_t)p * N + z];
     const int NP = (N + 3) & ~3;                           // counter plane stride (words)
-    float2 px[PER][VW];
+    float2 px[NB0][R0];
 #pragma unroll
-    for (int j = 0; j < PER; ++j)
+    for (int i = 0; i < NB0; ++i)
 #pragma unroll
-        for (int e = 0; e < VW; ++e) px[j][e] = make_float2(0.f, 0.f);
+        for (int n = 0; n < R0; ++n) px[i][n] = make_float2(0.f, 0.f);
 
     if (SPECIES) {
         if (tid < GX_MAX_SPECIES) s_table[tid] = tid < a.n_species ? a.table[tid] : make_float2(0.f, 0.f);
@@ -95,31 +102,22 @@ slice_rows_fused(FusedArgs fa)
             scatter_species(a, c0, c1, s, c, shift, words, NP);
             __syncthreads();
             const bool more = c1 < end;
+            for (int w = 0; w < npair; ++w) {
+                const float2 f0 = s_table[2 * w], f1 = s_table[2 * w + 1];
+                uint32_t *plane = words + w * NP;
 #pragma unroll
-            for (int j = 0; j < PER; ++j) {
-                const int g = tid + j * NT;
-                if (g * VW < N) {
-                    for (int w = 0; w < npair; ++w) {
-                        const float2 f0 = s_table[2 * w], f1 = s_table[2 * w + 1];
-                        if (BLUE) {
-                            const uint32_t cnt = words[w * NP + g];
+                for (int i = 0; i < NB0; ++i) {
+                    const int t = tid + i * NT;
+#pragma unroll
+                    for (int n = 0; n < R0; ++n) {
+                        const int y = t + S0 * n;
+                        if (t < S0 && y < N) {
+                            const uint32_t cnt = plane[y];
                             if (cnt) {
                                 const float n0 = (float)(cnt & 0xffffu), n1 = (float)(cnt >> 16);
-                                px[j][0].x += n0 * f0.x + n1 * f1.x;
-                                px[j][0].y += n0 * f0.y + n1 * f1.y;
-                                if (more) words[w * NP + g] = 0u;
-                            }
-                        } else {
-                            const uint4 cv = words4[w * (NP / 4) + g];
-                            if (cv.x | cv.y | cv.z | cv.w) {
-                                const uint32_t cc[4] = {cv.x, cv.y, cv.z, cv.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float n0 = (float)(cc[e] & 0xffffu), n1 = (float)(cc[e] >> 16);
-                                    px[j][e].x += n0 * f0.x + n1 * f1.x;
-                                    px[j][e].y += n0 * f0.y + n1 * f1.y;
-                                }
-                                if (more) words4[w * (NP / 4) + g] = make_uint4(0u, 0u, 0u, 0u);
+                                px[i][n].x += n0 * f0.x + n1 * f1.x;
+                                px[i][n].y += n0 * f0.y + n1 * f1.y;
+                                if (more) plane[y] = 0u;
                             }
                         }
                     }
@@ -143,43 +141,37 @@ slice_rows_fused(FusedArgs fa)
         }
         __syncthreads();
 #pragma unroll
-        for (int j = 0; j < PER; ++j)
+        for (int i = 0; i < NB0; ++i)
 #pragma unroll
-            for (int e = 0; e < VW; ++e) {
-                const int y = (tid + j * NT) * VW + e;
-                if (y < N) px[j][e] = buf[gx_phys(y)];
+            for (int n = 0; n < R0; ++n) {
+                const int t = tid + i * NT, y = t + S0 * n;
+                if (t < S0 && y < N) px[i][n] = buf[gx_phys(y)];
             }
         __syncthreads();
     }
 
-    // complete the row (pedestal-free) and stage it for the transform
+    // complete the pixels (pedestal-free) in registers and run the first pass on them
     const size_t vo = (size_t)p * N;
+    const float2 *tw0 = fa.plan + fa.lay.tw_off[0];
 #pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        const int g = tid + j * NT;
-        if (BLUE) {
-            if (g < M) {
+    for (int i = 0; i < NB0; ++i) {
+        const int t = tid + i * NT;
+        if (t < S0) {
+#pragma unroll
+            for (int n = 0; n < R0; ++n) {
+                const int y = t + S0 * n;
                 float2 v = make_float2(0.f, 0.f);
-                if (g < N) {
-                    v = finish_pixel(px[j][0], a.base[vo + g], mzv * a.my[vo + g]);
-                    v = gx_cmul(v, fa.plan[fa.lay.chirp_off + g]);
+                if (y < N) {
+                    v = finish_pixel(px[i][n], a.base[vo + y], mzv * a.my[vo + y]);
+                    if (BLUE) v = gx_cmul(v, fa.plan[fa.lay.chirp_off + y]);
                 }
-                buf[gx_phys(g)] = v;
+                px[i][n] = v;
             }
-        } else if (g * 4 < N) {
-            const int y0 = g * 4;
-            const float4 b01 = *reinterpret_cast<const float4 *>(a.base + vo + y0);
-            const float4 b23 = *reinterpret_cast<const float4 *>(a.base + vo + y0 + 2);
-            const float4 m4 = *reinterpret_cast<const float4 *>(a.my + vo + y0);
-            float2 *dst = buf + gx_phys(y0);               // 4 consecutive pixels stay contiguous when padded
-            dst[0] = finish_pixel(px[j][0], make_float2(b01.x, b01.y), mzv * m4.x);
-            dst[1] = finish_pixel(px[j][1], make_float2(b01.z, b01.w), mzv * m4.y);
-            dst[2] = finish_pixel(px[j][2], make_float2(b23.x, b23.y), mzv * m4.z);
-            dst[3] = finish_pixel(px[j][3], make_float2(b23.z, b23.w), mzv * m4.w);
+            gx_fft_pass0_from_regs<L>(px[i], buf, tw0, t);
         }
     }
     __syncthreads();
-    gx_dft_block<L, 1, 0, BLUE ? 1 : 0>(buf, fa.lay, fa.plan, tid, NT);
+    gx_dft_block<L, 1, 0, BLUE ? 1 : 0, true>(buf, fa.lay, fa.plan, tid, NT);
 
     // kept q-columns only; shifted column j holds unshifted coefficient j - N/2 (mod N)
     float2 *dst = fa.work + ((size_t)p * N + z) * fa.KC;

@@ -25,6 +25,9 @@ import os
 # GIWAXS_B200_STAGED=1 forces the unfused kernels (projection, 2-D FFT, binning
 # as separate launches) -- used to compare the two paths; both are CUDA.
 STAGED_ONLY = os.environ.get("GIWAXS_B200_STAGED", "0") == "1"
+# GIWAXS_B200_FULL_RANGE=1 computes min/max of y' over all atoms instead of the
+# convex-hull candidates (cross-check of the candidate reduction).
+USE_ALL_ATOMS_FOR_RANGE = os.environ.get("GIWAXS_B200_FULL_RANGE", "0") == "1"
 
 _checked_devices = set()
 
@@ -127,40 +130,43 @@ def stage_a_geometry(bounds, r_voxel_size, q_voxel_size, max_q):
     return grid_size, int(q_num), q_axis, phis
 
 
+CHORD_DTYPE = np.dtype([(n, np.float64) for n in
+                        ("hor", "ver", "stop1", "stop2", "stop12", "mid", "vcos", "rise",
+                         "tan_phi", "tan_theta", "cos_phi", "cos_theta")] +
+                       [("mode", np.int32), ("pad", np.int32)])
+assert CHORD_DTYPE.itemsize == ctypes.sizeof(_lib.Chord)
+
+
 def chord_constants(phis, hor_length, ver_length):
     """Per-rotation constants of rectangular_collapse_lengths
-    (tools/voxelgrids.py:253-285), called there as (x_vals, y_bound, x_bound, phi)."""
-    arr = (_lib.Chord * len(phis))()
-    for i, phi in enumerate(phis):
-        hor, ver = hor_length, ver_length
-        if phi > 90:
-            phi = phi - 90
-            hor, ver = ver, hor
-        theta_rad = np.deg2rad(90 - phi)
-        phi_rad = np.deg2rad(phi)
-        c = arr[i]
-        c.hor, c.ver = hor, ver
-        if phi == 0:
-            c.mode = 0
-            continue
-        if phi == 90:
-            c.mode = 1
-            continue
-        c.mode = 2
+    (tools/voxelgrids.py:253-285), called there as (x_vals, y_bound, x_bound, phi).
+    Vectorised over the rotations with the same element-wise NumPy operations
+    the reference applies to scalars; returns a structured array laid out as
+    gx_chord."""
+    phis = np.asarray(phis, dtype=np.float64)
+    out = np.zeros(len(phis), dtype=CHORD_DTYPE)
+    swap = phis > 90
+    phi = np.where(swap, phis - 90, phis)
+    hor = np.where(swap, np.float64(ver_length), np.float64(hor_length))
+    ver = np.where(swap, np.float64(hor_length), np.float64(ver_length))
+    theta_rad = np.deg2rad(90 - phi)
+    phi_rad = np.deg2rad(phi)
+    out["hor"], out["ver"] = hor, ver
+    out["mode"] = np.where(phi == 0, 0, np.where(phi == 90, 1, 2))
+    with np.errstate(all="ignore"):
         vcos = ver * np.cos(theta_rad)
-        stop1 = vcos
-        stop2 = hor * np.cos(phi_rad)
-        if stop1 < stop2:
-            mid = ver / np.sin(theta_rad)
-        else:
-            stop1, stop2 = stop2, stop1
-            mid = hor / np.sin(phi_rad)
-        c.stop1, c.stop2, c.stop12, c.mid = stop1, stop2, stop1 + stop2, mid
-        c.vcos = vcos
-        c.rise = np.sqrt(ver ** 2 - vcos ** 2)
-        c.tan_phi, c.tan_theta = np.tan(phi_rad), np.tan(theta_rad)
-        c.cos_phi, c.cos_theta = np.cos(phi_rad), np.cos(theta_rad)
-    return arr
+        s1 = vcos
+        s2 = hor * np.cos(phi_rad)
+        first = s1 < s2
+        out["mid"] = np.where(first, ver / np.sin(theta_rad), hor / np.sin(phi_rad))
+        out["stop1"] = np.where(first, s1, s2)
+        out["stop2"] = np.where(first, s2, s1)
+        out["stop12"] = out["stop1"] + out["stop2"]
+        out["vcos"] = vcos
+        out["rise"] = np.sqrt(ver ** 2 - vcos ** 2)
+        out["tan_phi"], out["tan_theta"] = np.tan(phi_rad), np.tan(theta_rad)
+        out["cos_phi"], out["cos_theta"] = np.cos(phi_rad), np.cos(theta_rad)
+    return out
 
 
 def gaussian_weights(sigma):
@@ -208,6 +214,72 @@ class AtomSet:
         call("gx_atoms_sort_rows", ptr(d_coords), self.A, float(self.minmax[4]), self.r, self.N,
              ptr(d_species), ptr(d_f), ptr(self.xs), ptr(self.ys), ptr(self.perm),
              ptr(self.species), ptr(self.f), ptr(self.row_start), ptr(cursor), st)
+        self._cand = None
+
+    def candidates(self):
+        """(xs, ys, count) of the atoms that can be extreme in y' (built lazily, once)."""
+        if self._cand is None:
+            self._cand = (self.xs, self.ys, self.A) if USE_ALL_ATOMS_FOR_RANGE else extreme_candidates(self)
+        return self._cand
+
+
+def convex_polygon(points):
+    """Counter-clockwise convex hull (Andrew's monotone chain) of a few 2-D points."""
+    pts = sorted(set(map(tuple, np.asarray(points, dtype=np.float64))))
+    if len(pts) < 3:
+        return np.asarray(pts)
+
+    def cross(o, a, b):
+        return (a[0] - o[0]) * (b[1] - o[1]) - (a[1] - o[1]) * (b[0] - o[0])
+
+    lower, upper = [], []
+    for p in pts:
+        while len(lower) >= 2 and cross(lower[-2], lower[-1], p) <= 0:
+            lower.pop()
+        lower.append(p)
+    for p in reversed(pts):
+        while len(upper) >= 2 and cross(upper[-2], upper[-1], p) <= 0:
+            upper.pop()
+        upper.append(p)
+    return np.asarray(lower[:-1] + upper[:-1])
+
+
+def extreme_candidates(atoms, n_dir=32, capacity=1 << 20):
+    """Subset of atoms that can attain min/max of y' for some rotation: those not
+    strictly inside (by eps) the polygon spanned by the atoms that are extreme
+    along 2*n_dir directions.  Returns (xs, ys, count) device tensors; falls back
+    to all atoms for degenerate (collinear) slabs."""
+    dev, A = atoms.device, atoms.A
+    st = _stream()
+    theta = np.linspace(0.0, np.pi, n_dir, endpoint=False)
+    d_sn, d_cs = _dev(np.sin(theta), dev), _dev(np.cos(theta), dev)
+    yr = torch.empty(2 * n_dir, dtype=torch.float64, device=dev)
+    call("gx_slice_yrange", ptr(atoms.xs), ptr(atoms.ys), A, ptr(d_sn), ptr(d_cs), n_dir, ptr(yr), st)
+    idx = torch.empty(2 * n_dir, dtype=torch.int32, device=dev)
+    call("gx_extreme_atoms", ptr(atoms.xs), ptr(atoms.ys), A, ptr(d_sn), ptr(d_cs), ptr(yr), n_dir, ptr(idx), st)
+    sel = torch.unique(idx.to(torch.int64))
+    sel = sel[sel < A]
+    pts = torch.stack([atoms.xs[sel], atoms.ys[sel]], dim=1).cpu().numpy()
+    poly = convex_polygon(pts)
+    if len(poly) < 3 or len(poly) > 64:
+        return atoms.xs, atoms.ys, A
+    nxt = np.roll(poly, -1, axis=0)
+    e = nxt - poly
+    length = np.hypot(e[:, 0], e[:, 1])
+    normal = np.stack([-e[:, 1], e[:, 0]], axis=1) / length[:, None]          # inward for CCW order
+    edges = np.concatenate([normal, -(normal * poly).sum(axis=1, keepdims=True)], axis=1)
+    eps = 1e-7 * (1.0 + float(np.abs(atoms.minmax[:4]).max()))
+    cap = int(min(A, capacity))
+    out_x = torch.empty(cap, dtype=torch.float64, device=dev)
+    out_y = torch.empty(cap, dtype=torch.float64, device=dev)
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    d_edges = _dev(np.ascontiguousarray(edges), dev)
+    call("gx_hull_filter", ptr(atoms.xs), ptr(atoms.ys), A, ptr(d_edges), int(len(poly)), eps, ptr(count),
+         ptr(out_x), ptr(out_y), cap, st)
+    n = int(count.item())
+    if n > cap or n == 0:
+        return atoms.xs, atoms.ys, A
+    return out_x[:n].contiguous(), out_y[:n].contiguous(), n
 
 
 class SliceEngine:
@@ -292,7 +364,8 @@ class SliceEngine:
         t = dict(n=n)
         t["sin"], t["cos"] = _dev(sn, dev), _dev(cs, dev)
         t["yrange"] = torch.empty(2 * n, dtype=torch.float64, device=dev)
-        call("gx_slice_yrange", ptr(a.xs), ptr(a.ys), a.A, ptr(t["sin"]), ptr(t["cos"]), n, ptr(t["yrange"]), st)
+        cx, cy, cn = a.candidates()
+        call("gx_slice_yrange", ptr(cx), ptr(cy), cn, ptr(t["sin"]), ptr(t["cos"]), n, ptr(t["yrange"]), st)
         t["bbox"] = torch.empty(4 * n, dtype=torch.int32, device=dev)
         scratch = torch.empty(n, dtype=torch.int32, device=dev)
         call("gx_slice_bbox", ptr(a.xs), ptr(a.ys), ptr(a.row_start), N, self.r, ptr(t["sin"]), ptr(t["cos"]),
@@ -301,8 +374,7 @@ class SliceEngine:
         d_chord = None
         if self.fill_bkg:
             ch = chord_constants(phis, self.y_bound, self.x_bound)
-            host = np.frombuffer(ch, dtype=np.uint8).copy()
-            t["chord"] = _dev(host, dev)
+            t["chord"] = _dev(ch.view(np.uint8), dev)
             d_chord = t["chord"]
         # blend mask x "inside the atom box" indicator per column / per row
         t["my"] = torch.empty(n * N, dtype=torch.float32, device=dev)
@@ -373,16 +445,20 @@ class SliceEngine:
             raise ValueError("the fused path accumulates rank-1 counts (count3d=False)")
         with torch.cuda.device(self.device):
             B = self.fused_batch_size()
-            work = torch.empty(min(B, len(phis)) * self.N * self.KC * 2, dtype=torch.float32, device=self.device)
-            boxes = []
+            N = self.N
+            work = torch.empty(min(B, len(phis)) * N * self.KC * 2, dtype=torch.float32, device=self.device)
+            # per-rotation tables for the whole run in one set of launches, then one
+            # pair of fused launches per batch on views of them
+            full = self._timed("prepare", self.prepare, phis)
+            per_phi = {"sin": 1, "cos": 1, "yrange": 2, "bbox": 4, "base": 2 * N, "my": N, "mz": N, "col": N}
             for i0 in range(0, len(phis), B):
-                chunk = phis[i0:i0 + B]
-                t = self._timed("prepare", self.prepare, chunk)
-                boxes.append(t["bbox"])
+                n = min(B, len(phis) - i0)
+                t = {k: full[k][i0 * w:(i0 + n) * w] for k, w in per_phi.items()}
+                t["n"] = n
                 self._timed("fused", self.fused, t, work)
-                self.slices_done += len(chunk)
+                self.slices_done += n
             torch.cuda.current_stream().synchronize()
-            self.check_bbox({"bbox": torch.cat(boxes)})
+            self.check_bbox(full)
 
     def run(self, phis, capture=None, staged=None):
         """Accumulate the given phi slices.  capture: optional dict receiving

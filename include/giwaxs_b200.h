@@ -79,6 +79,23 @@ int gx_slice_yrange(const double *d_xs, const double *d_ys, int64_t A,
                     const double *d_sin, const double *d_cos, int n_phi,
                     double *d_yrange, void *stream);
 
+/* Candidate reduction for gx_slice_yrange.  Only atoms on (or within eps of)
+ * the boundary of the convex hull of the (x,y) positions can attain the min or
+ * max of y' for any rotation.
+ *  gx_extreme_atoms: for n <= 64 rotations whose d_yrange is known, the lowest
+ *    atom index attaining the min and the max -> d_index [n][2].
+ *  gx_hull_filter: d_edges [m][3] = (nx, ny, d) with nx*x + ny*y + d the signed
+ *    distance to edge k of a convex polygon whose vertices are atoms (inside
+ *    positive); atoms whose distance to the nearest edge is <= eps are appended
+ *    to d_xs_out/d_ys_out; *d_count receives how many qualified (may exceed
+ *    `capacity`, in which case the caller must fall back to all atoms).      */
+int gx_extreme_atoms(const double *d_xs, const double *d_ys, int64_t A,
+                     const double *d_sin, const double *d_cos, const double *d_yrange, int n,
+                     int32_t *d_index, void *stream);
+int gx_hull_filter(const double *d_xs, const double *d_ys, int64_t A, const double *d_edges, int m,
+                   double eps, int32_t *d_count, double *d_xs_out, double *d_ys_out, int capacity,
+                   void *stream);
+
 /* index bounding box {y_min,y_max,z_min,z_max} of the valid atoms of every
  * rotation; -1 entries when no atom is valid.  d_scratch: n_phi int32.
  *                                                        (vg.py:332-349)   */

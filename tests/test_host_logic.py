@@ -130,9 +130,12 @@ def _chord_from_constants(c, x):
 def test_chord_constants_reproduce_oracle_lengths():
     x = np.arange(400) * 0.3
     phis = np.array([0.0, 0.2, 30.0, 45.0, 77.7, 90.0, 90.2, 120.0, 179.8])
+    import types
     arr = engine.chord_constants(phis, 21.0, 14.0)
+    assert arr.dtype.itemsize == ctypes.sizeof(_lib.Chord)
     for i, phi in enumerate(phis):
-        assert np.array_equal(_chord_from_constants(arr[i], x), ox.chord_lengths(x, 21.0, 14.0, phi)), phi
+        c = types.SimpleNamespace(**{k: arr[i][k] for k in arr.dtype.names})
+        assert np.array_equal(_chord_from_constants(c, x), ox.chord_lengths(x, 21.0, 14.0, phi)), phi
 
 
 def test_gaussian_weights_match_scipy():
