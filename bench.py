@@ -292,7 +292,9 @@ def run_ours(args):
     A = cfg["n_atoms"]
     kr, kc = 567, 636
     alg = {"prepare": 16.0 * A / 256, "project": 28.0 * A + 8.0 * N * N, "fft2": 12.0 * N * N,
-           "bin": 20.0 * kr * kc, "fused_rows": 28.0 * A + 8.0 * N * kc, "fused_cols": 8.0 * N * kc + 20.0 * kr * kc}
+           "bin": 20.0 * kr * kc,
+           # fused = F1 + F2: the whole slice: atoms + grid write + FFT read/write + binning
+           "fused": 28.0 * A + 8.0 * N * N + 12.0 * N * N + 20.0 * kr * kc}
     n_my = len(my_phis)
     top = max(kernel_ms, key=kernel_ms.get) if kernel_ms else None
     roofline = None

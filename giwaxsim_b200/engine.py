@@ -68,6 +68,19 @@ def encode_values(values, max_species=_lib.GX_MAX_SPECIES):
     than `max_species` distinct values."""
     values = np.asarray(values)
     A = values.shape[0]
+    if values.dtype.kind == "U" and values.dtype.itemsize in (4, 8) and A > 0:
+        # element symbols ('<U1' / '<U2'): ASCII code points -> 14-bit key -> lookup table,
+        # three vector passes instead of one string comparison pass per element type
+        cp = np.ascontiguousarray(values).view(np.uint32).reshape(A, -1)
+        if int(cp.max()) < 128:
+            key = cp[:, 0] if cp.shape[1] == 1 else cp[:, 0] + (cp[:, 1] << 7)
+            present = np.flatnonzero(np.bincount(key, minlength=1 << 14))
+            if len(present) > max_species:
+                return None, None
+            lut = np.zeros(1 << 14, dtype=np.uint8)
+            lut[present] = np.arange(len(present), dtype=np.uint8)
+            uniques = [values.dtype.type("".join(chr(c) for c in (k & 127, k >> 7) if c)) for k in present]
+            return lut[key], uniques
     codes = np.full(A, 255, dtype=np.uint8)
     uniques = []
     todo = np.ones(A, dtype=bool)

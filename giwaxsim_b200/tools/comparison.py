@@ -71,7 +71,7 @@ def voxelgridmaker_fitting(coords, elements, r_voxel_size, q_voxel_size, max_q, 
     if world > 1:
         parallel.all_reduce_sum([eng.vsum, eng.count2])
     iq_dev, axis = engine.finalize_voxels(eng.vsum, None, eng.count2, eng.row_hist, q_axis, max_q, dev)
-    iq = iq_dev.cpu().to(torch.float64).numpy()
+    iq = iq_dev.to(torch.float64).cpu().numpy()          # widen on the device, one D2H copy
     _resident["host"], _resident["device"] = iq, iq_dev
     out = (iq, axis.copy(), axis.copy(), axis.copy())
     return out + (eng,) if return_state else out

@@ -267,3 +267,28 @@ def test_random_slab_against_oracle_many_species_and_generic_path():
         eng.run(setup["phis"])
         assert np.array_equal(eng.counts(), vcnt.astype(np.int64))
         assert np.abs(eng.sums() - vsum).max() <= TOL_INT * vsum.max()
+
+
+def test_T8_pm6_default_config_end_to_end(golden):
+    """config_templates/simulate_GIWAXS_config.txt (PM6 slab, N=1048 -> Bluestein, 892 slices,
+    2880 orientations x 500^2) through the two drop-in drivers, against the oracle image and the
+    reference's own shipped golden det_sum.npy (which differs by the unpinned xraydb table)."""
+    g = golden("pm6.npz")
+    names = [str(n) for n in g["element_names"]]
+    elements = np.array(names)[g["element_codes"]]
+    iq, qx, qy, qz = comparison.voxelgridmaker_fitting(g["coords"], elements, float(g["r"]), float(g["q"]),
+                                                       float(g["max_q"]), 12700.0, fill_bkg=True,
+                                                       smooth=int(g["smooth"]))
+    assert iq.shape == tuple(g["iq_shape"])
+    plane = iq[:, :, iq.shape[2] // 2]
+    assert np.abs(plane - g["iq_center_plane"]).max() <= TOL_INT * float(g["iq_max"])
+    det, h, v = comparison.detectormaker_fitting(iq, qx, qy, qz, int(g["P"]), float(g["max_q"]), tuple(g["vals"]),
+                                                 tuple(str(a) for a in g["axs"]), g["psis"], None, g["phis"], None,
+                                                 g["thetas"], None, mirror=True)
+    quad = det[np.ix_(np.where(v >= 0)[0], np.where(h >= 0)[0])]      # simulate_GIWAXS.py:172-177
+    ref = g["det_quadrant_oracle"]
+    assert np.array_equal(h[h >= 0], g["det_h"])
+    assert np.abs(quad - ref).max() <= TOL_INT * ref.max()
+    gold = golden("pm6_det_sum_ref.npy")
+    assert np.abs(quad - gold).max() <= 0.02 * gold.max()
+    assert np.corrcoef(np.log(quad).ravel(), np.log(gold).ravel())[0, 1] > 0.9999
