@@ -28,6 +28,9 @@ STAGED_ONLY = os.environ.get("GIWAXS_B200_STAGED", "0") == "1"
 # GIWAXS_B200_FULL_RANGE=1 computes min/max of y' over all atoms instead of the
 # convex-hull candidates (cross-check of the candidate reduction).
 USE_ALL_ATOMS_FOR_RANGE = os.environ.get("GIWAXS_B200_FULL_RANGE", "0") == "1"
+# GIWAXS_B200_EXACT_DETECTOR=1 runs the all-fp64 detector kernel instead of the
+# fp32-filtered one (both give identical voxel indices).
+EXACT_DETECTOR_ONLY = os.environ.get("GIWAXS_B200_EXACT_DETECTOR", "0") == "1"
 
 _checked_devices = set()
 
@@ -50,6 +53,17 @@ def resolve_device(device=None):
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def to_host_f64(t):
+    """Device tensor -> float64 NumPy array through a pinned buffer (one DMA at PCIe
+    speed instead of a staged pageable copy).  The array owns the pinned block; torch's
+    host caching allocator recycles it once the array is garbage collected."""
+    src = t if t.dtype == torch.float64 else t.to(torch.float64)
+    host = torch.empty(src.shape, dtype=torch.float64, pin_memory=True)
+    host.copy_(src, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()
 
 
 def _dev(a, device, dtype=None):
@@ -632,22 +646,77 @@ class DetectorEngine:
         self.mins = (float(np.min(qx)), float(np.min(qy)), float(np.min(qz)))
         self.dq = float(np.diff(qz)[0])               # detector.py:213
 
-    def accumulate(self, det_x, det_y, det_z, R, w, image=None, probe=-1):
-        """image[P,P] (fp64, device) += sum_o w_o * iq[voxel(R_o p)]."""
+    last_slow_fraction = None
+
+    @staticmethod
+    def _mostly_edge_locked(fast, pmax):
+        """True when, for most orientations, some voxel coordinate is (nearly) constant over the
+        whole detector and within the fp32 bound of an integer, i.e. every pixel would fall back
+        to the exact chain anyway.  Only a dispatch hint: both kernels give identical indices."""
+        rec = fast.reshape(-1, call("gx_fast_record_bytes"))[:, :60].copy().view(np.float32)
+        m, off, slack = rec[:, :9].reshape(-1, 3, 3), rec[:, 9:12], rec[:, 12:15]
+        spread = (np.abs(m) * np.asarray(pmax, dtype=np.float32)[None, None, :]).sum(axis=2)
+        near = np.abs(off - np.round(off)) <= (0.5 - slack) + spread
+        locked = ((spread < 0.25) & near).any(axis=1)
+        return locked.mean() > 0.5
+
+    def accumulate(self, det_x, det_y, det_z, R, w, image=None, probe=-1, exact_only=None, count_slow=False):
+        """image[P,P] (fp64, device) += sum_o w_o * iq[voxel(R_o p)].
+
+        Default: the fp32-filtered kernel (bit-identical indices; exact fp64 chain
+        only for pixels within the rounding bound of a voxel edge).  exact_only=True
+        (or GIWAXS_B200_EXACT_DETECTOR=1) runs the all-fp64 kernel."""
         dev = self.device
+        auto = exact_only is None and not EXACT_DETECTOR_ONLY
+        if exact_only is None:
+            exact_only = EXACT_DETECTOR_ONLY
         with torch.cuda.device(dev):
             shape = det_x.shape
             n_pix = int(np.prod(shape))
-            px, py, pz = (g if isinstance(g, torch.Tensor) else _dev(np.asarray(g, dtype=np.float64), dev)
+            on_device = isinstance(det_x, torch.Tensor)
+            px, py, pz = (g if on_device else _dev(np.asarray(g, dtype=np.float64), dev)
                           for g in (det_x, det_y, det_z))
             if image is None:
                 image = torch.zeros(n_pix, dtype=torch.float64, device=dev)
             index = torch.empty(n_pix, dtype=torch.int64, device=dev) if probe >= 0 else None
-            d_R, d_w = _dev(R, dev), _dev(w, dev)
+            R = np.ascontiguousarray(R, dtype=np.float64)
+            w = np.ascontiguousarray(w, dtype=np.float64)
+            d_R = _dev(R, dev)
             Vy, Vx, Vz = self.shape
-            call("gx_detector_accumulate", ptr(self.iq), Vy, Vx, Vz, self.mins[0], self.mins[1], self.mins[2],
-                 self.dq, ptr(px), ptr(py), ptr(pz), n_pix, ptr(d_R), ptr(d_w), int(len(w)),
-                 ptr(image), int(probe), ptr(index), _stream())
+            if exact_only:
+                d_w = _dev(w, dev)
+                call("gx_detector_accumulate", ptr(self.iq), Vy, Vx, Vz, self.mins[0], self.mins[1], self.mins[2],
+                     self.dq, ptr(px), ptr(py), ptr(pz), n_pix, ptr(d_R), ptr(d_w), int(len(w)),
+                     ptr(image), int(probe), ptr(index), _stream())
+            else:
+                if on_device and len(shape) == 2:
+                    # driver path: the grid is affine in (row, col), so |component| peaks at a corner
+                    c = grid_corners(det_x, det_y, det_z)
+                    corners = np.vstack([c, c[1] + c[2] - c[0]])
+                    pmax = np.abs(corners).max(axis=0) * (1.0 + 1e-9)
+                else:
+                    pmax = np.array([float(np.abs(np.asarray(g)).max()) for g in (det_x, det_y, det_z)])
+                fast = np.zeros(len(w) * call("gx_fast_record_bytes"), dtype=np.uint8)
+                pmax = np.ascontiguousarray(pmax, dtype=np.float64)      # keep alive across the call
+                call("gx_host_fast_orientations", ptr(R), ptr(w), int(len(w)), self.mins[0], self.mins[1],
+                     self.mins[2], self.dq, ptr(pmax), ptr(fast))
+                if auto and self._mostly_edge_locked(fast, pmax):
+                    # e.g. phi = theta = 0: the plane lies in q_z = 0, exactly on a voxel edge, so
+                    # every pixel needs the exact chain for that component and the fp32 filter
+                    # would be pure overhead -> all-fp64 kernel (identity steps skipped)
+                    d_w = _dev(w, dev)
+                    call("gx_detector_accumulate", ptr(self.iq), Vy, Vx, Vz, self.mins[0], self.mins[1],
+                         self.mins[2], self.dq, ptr(px), ptr(py), ptr(pz), n_pix, ptr(d_R), ptr(d_w),
+                         int(len(w)), ptr(image), int(probe), ptr(index), _stream())
+                    torch.cuda.current_stream().synchronize()
+                    return image, index
+                d_fast = _dev(fast, dev)
+                slow = torch.zeros(1, dtype=torch.int64, device=dev) if count_slow else None
+                call("gx_detector_accumulate_fast", ptr(self.iq), Vy, Vx, Vz, self.mins[0], self.mins[1],
+                     self.mins[2], self.dq, ptr(px), ptr(py), ptr(pz), n_pix, ptr(d_fast), ptr(d_R), int(len(w)),
+                     ptr(image), int(probe), ptr(index), ptr(slow), _stream())
+                if count_slow:
+                    self.last_slow_fraction = float(slow.item()) / (n_pix * len(w))
             torch.cuda.current_stream().synchronize()
         return image, index
 

@@ -71,7 +71,8 @@ def voxelgridmaker_fitting(coords, elements, r_voxel_size, q_voxel_size, max_q, 
     if world > 1:
         parallel.all_reduce_sum([eng.vsum, eng.count2])
     iq_dev, axis = engine.finalize_voxels(eng.vsum, None, eng.count2, eng.row_hist, q_axis, max_q, dev)
-    iq = iq_dev.to(torch.float64).cpu().numpy()          # widen on the device, one D2H copy
+    with torch.cuda.device(dev):
+        iq = engine.to_host_f64(iq_dev)                   # widen on the device, one pinned D2H copy
     _resident["host"], _resident["device"] = iq, iq_dev
     out = (iq, axis.copy(), axis.copy(), axis.copy())
     return out + (eng,) if return_state else out
@@ -125,4 +126,5 @@ def detectormaker_fitting(iq, qx, qy, qz, num_pixels, max_q, angle_init_vals, an
     if world > 1:
         parallel.all_reduce_sum([image])
     out = engine.detector_epilogue(image, num_pixels, num_pixels, mirror, dev, finish=True)
-    return out.cpu().numpy(), det_h, det_v
+    with torch.cuda.device(dev):
+        return engine.to_host_f64(out), det_h, det_v

@@ -251,6 +251,25 @@ int gx_detector_accumulate(const float *d_iq, int Vy, int Vx, int Vz,
                            const double *d_R, const double *d_w, int n_orient,
                            double *d_image, int probe, int64_t *d_index_out, void *stream);
 
+/* Same result as gx_detector_accumulate, bit for bit, at a fraction of the
+ * fp64 work: the voxel coordinate of every pixel is first evaluated in fp32
+ * from one collapsed matrix per orientation; only pixels whose fp32 coordinate
+ * lies within a host-computed rigorous error bound of a voxel edge fall back to
+ * the exact fp64 chain.  d_fast: n_orient records from
+ * gx_host_fast_orientations; d_slow_count (optional) counts fall-backs.     */
+int gx_detector_accumulate_fast(const float *d_iq, int Vy, int Vx, int Vz,
+                                double qx_min, double qy_min, double qz_min, double dq,
+                                const double *d_px, const double *d_py, const double *d_pz, int64_t n_pix,
+                                const void *d_fast, const double *d_R, int n_orient,
+                                double *d_image, int probe, int64_t *d_index_out,
+                                unsigned long long *d_slow_count, void *stream);
+/* Host helper: records for the kernel above.  h_R [n][3][9], h_w [n]; h_pmax[3]
+ * = max |x|, |y|, |z| over the detector pixels; h_fast: n records of
+ * gx_fast_record_bytes() bytes each.                                        */
+int gx_fast_record_bytes(void);
+int gx_host_fast_orientations(const double *h_R, const double *h_w, int n, double qx_min, double qy_min,
+                              double qz_min, double dq, const double *h_pmax, void *h_fast);
+
 /* Host helper: the three per-orientation rotation matrices, derived exactly
  * as rotate_psi_phi_theta does from the current corner pixels.
  * h_corners [3][3] = p[0,0], p[0,-1], p[-1,0] of the base detector;

@@ -51,6 +51,62 @@ def test_hull_candidates_give_identical_y_range(kind):
         assert full[k, 0] == yr.min() and full[k, 1] == yr.max()
 
 
+@pytest.mark.parametrize("inits,axs", [((90.0, 90.0, 90.0), ("psi", "phi", "psi")),
+                                        ((0.0, 0.0, 0.0), ("None", "None", "None")),
+                                        ((12.5, 40.0, 3.0), ("theta", "phi", "psi"))])
+def test_filtered_detector_kernel_is_bit_identical_to_exact(inits, axs):
+    """fp32-filtered gather == all-fp64 gather: same voxel index for every pixel of every
+    orientation (so the images are bitwise equal), including grid-aligned orientations
+    where every pixel sits on a voxel edge and pixels far outside the voxel box."""
+    rng = np.random.default_rng(1)
+    V = 101
+    q = np.linspace(-2.0, 2.0, V)                     # dq = 0.04: detector pixels land on voxel edges
+    iq = rng.random((V, V, V)).astype(np.float32)
+    dev = engine.resolve_device()
+    P = 320
+    gx, gy, gz, _, _ = comparison.detector_base_device(P, 2.4, inits, axs, dev)    # extends beyond the box
+    psis = np.array([0.0, 17.3, 45.0, 89.75, 90.0])
+    phis = np.array([0.0, 33.3, 90.0, 179.0])
+    thetas = np.array([0.0, 1.0])
+    ones = lambda a: np.ones_like(a) / len(a)
+    R, w = engine.orientation_tables(engine.grid_corners(gx, gy, gz), psis, ones(psis), phis, ones(phis),
+                                     thetas, ones(thetas))
+    det = engine.DetectorEngine(iq, q, q, q)
+    img_exact, _ = det.accumulate(gx, gy, gz, R, w, exact_only=True)
+    img_fast, _ = det.accumulate(gx, gy, gz, R, w, exact_only=False, count_slow=True)
+    assert torch.equal(img_exact, img_fast)
+    assert 0.0 <= det.last_slow_fraction <= 1.0
+    for o in (0, 7, 19, 39):
+        _, a = det.accumulate(gx, gy, gz, R, w, probe=o, exact_only=True)
+        _, b = det.accumulate(gx, gy, gz, R, w, probe=o, exact_only=False)
+        assert torch.equal(a, b)
+
+
+def test_filtered_detector_kernel_rarely_falls_back_on_generic_orientations():
+    rng = np.random.default_rng(2)
+    V = 403
+    q = np.linspace(-2.01, 2.01, V)
+    iq = rng.random((V, V, V)).astype(np.float32)
+    dev = engine.resolve_device()
+    gx, gy, gz, _, _ = comparison.detector_base_device(512, 2.0, (90.0, 90.0, 90.0), ("psi", "phi", "psi"), dev)
+    psis = np.linspace(3.1, 88.3, 24)
+    ones = np.ones(1)
+    det = engine.DetectorEngine(iq, q, q, q)
+    # tilted planes (phi = 7.3 deg): only pixels within the fp32 bound of a voxel edge fall back
+    R, w = engine.orientation_tables(engine.grid_corners(gx, gy, gz), psis, np.ones(24) / 24, [7.3], ones, [0.4], ones)
+    a, _ = det.accumulate(gx, gy, gz, R, w, exact_only=True)
+    b, _ = det.accumulate(gx, gy, gz, R, w, exact_only=False, count_slow=True)
+    assert torch.equal(a, b)
+    assert det.last_slow_fraction < 0.02, det.last_slow_fraction
+    # phi = theta = 0: the plane lies in q_z = 0, i.e. exactly on a voxel edge, for every pixel
+    # (rounding noise picks the bin) -> every pixel needs the exact z index; still identical
+    R, w = engine.orientation_tables(engine.grid_corners(gx, gy, gz), psis, np.ones(24) / 24, [0.0], ones, [0.0], ones)
+    a, _ = det.accumulate(gx, gy, gz, R, w, exact_only=True)
+    b, _ = det.accumulate(gx, gy, gz, R, w, exact_only=False, count_slow=True)
+    assert torch.equal(a, b)
+    assert det.last_slow_fraction > 0.9
+
+
 def test_linearity_of_detector_accumulation():
     """image(w1) + image(w2) == image(w1 + w2): the gather is linear in the weights."""
     rng = np.random.default_rng(0)
