@@ -310,6 +310,20 @@ def run_ours(args):
                                     "achieved": (28.0 * A + 20.0 * N * N + 20.0 * kr * kc) * len(phis_all)
                                     / (ms_a * 1e-3) / 1e9 / world}}
         roofline["whole_slice"]["frac"] = roofline["whole_slice"]["achieved"] / peak
+        # achieved / traffic are per launch: one fused launch pair covers a batch of rotations
+        per_launch = eng.fused_batch_size() if top == "fused" else eng.batch_size()
+        roofline["slices_per_launch"] = per_launch
+        roofline["algorithmic_bytes_per_launch"] = alg.get(top, 0.0) * per_launch
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(top)
+            if tr:
+                roofline["traffic"] = tr["dram_bytes_per_slice"] * per_launch
+                roofline["traffic_source"] = tr["source"]
+        except Exception:
+            pass
+        roofline["note"] = ("fused = slice_rows_fused + slice_cols_fused; algorithmic bytes are those of the scatter, "
+                            "2-D FFT and binning kernels they replace (SURVEY 8(d)); measured DRAM traffic is ~13x "
+                            "lower because the N x N grid and image never reach HBM")
     det_bytes = 4.0 * P * P
     det_ach = det_bytes * len(w) / world / (ms_b * 1e-3) / 1e9
     line = {"metric": METRIC, "value": len(phis_all) / (ms_a * 1e-3), "unit": UNIT, "n_gpus": world,
