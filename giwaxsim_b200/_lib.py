@@ -55,6 +55,8 @@ _PROTOTYPES = {
     "gx_device_check": (_i, [_i]),
     "gx_coords_minmax": (_i, [_p, _i64, _p, _p]),
     "gx_atoms_sort_rows": (_i, [_p, _i64, _d, _d, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "gx_species_histogram": (_i, [_p, _i, _i64, _p, _p]),
+    "gx_species_codes": (_i, [_p, _i, _i64, _p, _p, _p]),
     "gx_slice_yrange": (_i, [_p, _p, _i64, _p, _p, _i, _p, _p]),
     "gx_extreme_atoms": (_i, [_p, _p, _i64, _p, _p, _p, _i, _p, _p]),
     "gx_hull_filter": (_i, [_p, _p, _i64, _p, _i, _d, _p, _p, _p, _i, _p]),
@@ -79,13 +81,20 @@ _PROTOTYPES = {
                                     _p, _i, _p, _p]),
     "gx_detector_accumulate_fast": (_i, [_p, _i, _i, _i, _d, _d, _d, _d, _p, _p, _p, _i64, _p, _p, _i,
                                          _p, _i, _p, _p, _p]),
+    "gx_grid_affine_fit": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
+    "gx_affine_record_bytes": (_i, []),
+    "gx_affine_plan_doubles": (_i, []),
+    "gx_host_affine_orientations": (_i, [_p, _p, _i, _i, _p, _p, _i, _d, _d, _d, _d, _i, _i, _i, _p, _p]),
+    "gx_detector_accumulate_affine": (_i, [_p, _i, _i, _i, _d, _d, _d, _d, _p, _p, _p, _i, _i, _p, _p, _p, _i,
+                                           _p, _p, _i, _p, _p, _p]),
     "gx_fast_record_bytes": (_i, []),
     "gx_host_fast_orientations": (_i, [_p, _p, _i, _d, _d, _d, _d, _p, _p]),
     "gx_host_orientation_matrices": (_i, [_p, _p, _i, _p]),
     "gx_detector_epilogue": (_i, [_p, _i, _i, _i, _i, _p, _p]),
 }
 
-_UNCHECKED = {"gx_abi_version", "gx_last_error", "gx_fft_plan_bytes", "gx_fast_record_bytes"}
+_UNCHECKED = {"gx_abi_version", "gx_last_error", "gx_fft_plan_bytes", "gx_fast_record_bytes",
+              "gx_affine_record_bytes", "gx_affine_plan_doubles"}
 
 _cdll = None
 
@@ -121,8 +130,8 @@ _LAUNCHES = {
     "gx_slice_vectors": 1, "gx_project_slices": 1, "gx_fft2_abs2_shift": 2, "gx_slice_col_index": 1,
     "gx_axis_col_index": 1, "gx_axis_row_index": 1, "gx_bin_slices": 1, "gx_row_histogram": 1,
     "gx_voxel_finalize": 1, "gx_rotate_points": 1, "gx_detector_accumulate": 1, "gx_detector_epilogue": 1,
-    "gx_detector_accumulate_fast": 1,
-    "gx_slices_fused": 2, "gx_slice_col_range": 1, "gx_extreme_atoms": 1, "gx_hull_filter": 1,
+    "gx_detector_accumulate_fast": 1, "gx_detector_accumulate_affine": 1, "gx_grid_affine_fit": 1,
+    "gx_slices_fused": 2, "gx_species_histogram": 1, "gx_species_codes": 1, "gx_slice_col_range": 1, "gx_extreme_atoms": 1, "gx_hull_filter": 1,
 }
 _launch_count = 0
 

@@ -451,3 +451,67 @@ extern "C" int gx_hull_filter(const double *d_xs, const double *d_ys, int64_t A,
                                                              d_ys_out, capacity);
     return gx_check_launch("gx_hull_filter");
 }
+
+// ------------------------------------------------------ species coding ----
+// Element symbols arrive as NumPy '<U1' / '<U2' arrays, i.e. `width` UCS-4 code
+// points per atom.  key = cp0 + (cp1 << 7) (14 bits for ASCII symbols).  Pass 1
+// histograms the keys (warp-aggregated atomics: a slab has a handful of distinct
+// elements, so all lanes hit the same few counters); the host turns the occupied
+// bins into a key -> species-code table; pass 2 writes the uint8 codes.
+// d_hist: 16385 counters, the last one counts atoms with a non-ASCII code point.
+#define SPECIES_KEYS 16384
+
+__device__ __forceinline__ uint32_t species_key(const uint32_t *cp, int width, int64_t i, bool &bad)
+{
+    const uint32_t c0 = cp[i * width];
+    const uint32_t c1 = width > 1 ? cp[i * width + 1] : 0u;
+    bad = (c0 | c1) >= 128u;
+    return (c0 & 127u) | ((c1 & 127u) << 7);
+}
+
+__global__ void __launch_bounds__(ATOM_THREADS)
+species_hist_kernel(const uint32_t *__restrict__ cp, int width, int64_t A, uint32_t *hist)
+{
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < A; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        const bool live = i < A;
+        bool bad = false;
+        uint32_t key = live ? species_key(cp, width, i, bad) : 0xffffffffu;
+        if (live && bad) key = SPECIES_KEYS;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (live && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(hist + key, (uint32_t)__popc(peers));
+    }
+}
+
+__global__ void __launch_bounds__(ATOM_THREADS)
+species_code_kernel(const uint32_t *__restrict__ cp, int width, int64_t A, const uint8_t *__restrict__ lut,
+                    uint8_t *codes)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A; i += (int64_t)gridDim.x * blockDim.x) {
+        bool bad;
+        codes[i] = lut[species_key(cp, width, i, bad)];
+    }
+}
+
+extern "C" int gx_species_histogram(const uint32_t *d_codepoints, int width, int64_t A, uint32_t *d_hist,
+                                    void *stream)
+{
+    GX_REQUIRE(d_codepoints && d_hist, "NULL pointer");
+    GX_REQUIRE((width == 1 || width == 2) && A > 0, "width must be 1 or 2 code points");
+    GX_CUDA(cudaMemsetAsync(d_hist, 0, (SPECIES_KEYS + 1) * sizeof(uint32_t), gx_stream(stream)));
+    int64_t blocks = (A + ATOM_THREADS - 1) / ATOM_THREADS;
+    if (blocks > GX_SM_COUNT * 8) blocks = GX_SM_COUNT * 8;
+    species_hist_kernel<<<(int)blocks, ATOM_THREADS, 0, gx_stream(stream)>>>(d_codepoints, width, A, d_hist);
+    return gx_check_launch("gx_species_histogram");
+}
+
+extern "C" int gx_species_codes(const uint32_t *d_codepoints, int width, int64_t A, const uint8_t *d_lut,
+                                uint8_t *d_codes, void *stream)
+{
+    GX_REQUIRE(d_codepoints && d_lut && d_codes, "NULL pointer");
+    GX_REQUIRE((width == 1 || width == 2) && A > 0, "width must be 1 or 2 code points");
+    int64_t blocks = (A + ATOM_THREADS - 1) / ATOM_THREADS;
+    if (blocks > GX_SM_COUNT * 8) blocks = GX_SM_COUNT * 8;
+    species_code_kernel<<<(int)blocks, ATOM_THREADS, 0, gx_stream(stream)>>>(d_codepoints, width, A, d_lut, d_codes);
+    return gx_check_launch("gx_species_codes");
+}

@@ -55,15 +55,33 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_staging = {}
+
+
+def _pinned_staging(nbytes):
+    """Persistent page-locked scratch (grown, never shrunk).  Page-locking is slow (~1 GB/s), so
+    results are never handed out in freshly pinned memory; they are DMA'd into this buffer and
+    copied out."""
+    buf = _staging.get("buf")
+    if buf is None or buf.numel() < nbytes:
+        _staging["buf"] = None
+        buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
+        _staging["buf"] = buf
+    return buf
+
+
 def to_host_f64(t):
-    """Device tensor -> float64 NumPy array through a pinned buffer (one DMA at PCIe
-    speed instead of a staged pageable copy).  The array owns the pinned block; torch's
-    host caching allocator recycles it once the array is garbage collected."""
-    src = t if t.dtype == torch.float64 else t.to(torch.float64)
-    host = torch.empty(src.shape, dtype=torch.float64, pin_memory=True)
-    host.copy_(src, non_blocking=True)
+    """Device tensor -> fresh float64 NumPy array: one DMA of the tensor in its own dtype (fp32
+    voxel grids cross PCIe at half the bytes) into the persistent pinned buffer, then a
+    multi-threaded widening copy on the host."""
+    t = t.contiguous()
+    nbytes = t.numel() * t.element_size()
+    stage = _pinned_staging(nbytes)[:nbytes].view(t.dtype).view(t.shape)
+    stage.copy_(t, non_blocking=True)
+    out = torch.empty(t.shape, dtype=torch.float64)
     torch.cuda.current_stream().synchronize()
-    return host.numpy()
+    out.copy_(stage)
+    return out.numpy()
 
 
 def _dev(a, device, dtype=None):
@@ -110,6 +128,35 @@ def encode_values(values, max_species=_lib.GX_MAX_SPECIES):
         uniques.append(v)
         todo &= ~hit
     return codes, uniques
+
+
+def encode_elements_device(elements, device, max_species=_lib.GX_MAX_SPECIES):
+    """Code a NumPy '<U1' / '<U2' element array as uint8 ON THE DEVICE (the raw code points are
+    uploaded; a 10 M-atom array costs three full passes on the host otherwise).
+    Returns (codes uint8 device tensor [A], unique symbols, atoms per symbol) or None when the
+    array is not of that form / has more than `max_species` distinct symbols."""
+    elements = np.asarray(elements)
+    A = elements.shape[0] if elements.ndim == 1 else 0
+    if A == 0 or elements.dtype.kind != "U" or elements.dtype.itemsize not in (4, 8):
+        return None
+    width = elements.dtype.itemsize // 4
+    cp = torch.from_numpy(np.ascontiguousarray(elements).view(np.uint32).view(np.int32)).to(device, non_blocking=True)
+    hist = torch.empty(16385, dtype=torch.int32, device=device)
+    st = _stream()
+    call("gx_species_histogram", ptr(cp), width, A, ptr(hist), st)
+    h = hist.cpu().numpy()
+    if h[16384] != 0:
+        return None
+    present = np.flatnonzero(h[:16384])
+    if len(present) > max_species:
+        return None
+    lut = np.zeros(16384, dtype=np.uint8)
+    lut[present] = np.arange(len(present), dtype=np.uint8)
+    d_lut = _dev(lut, device)
+    codes = torch.empty(A, dtype=torch.uint8, device=device)
+    call("gx_species_codes", ptr(cp), width, A, ptr(d_lut), ptr(codes), st)
+    uniques = [elements.dtype.type("".join(chr(c) for c in (int(k) & 127, int(k) >> 7) if c)) for k in present]
+    return codes, uniques, h[present].astype(np.int64)
 
 
 # ---------------------------------------------------------------------------
@@ -227,7 +274,7 @@ class AtomSet:
         self.species = self.f = self.table = None
         if species is not None:
             self.n_species = len(table)
-            d_species = _dev(species, device)
+            d_species = species if isinstance(species, torch.Tensor) else _dev(species, device)
             self.species = torch.empty(self.A, dtype=torch.uint8, device=device)
             self.table = _dev(np.asarray(table, dtype=np.complex128).astype(np.complex64).view(np.float32), device)
         else:
@@ -631,6 +678,33 @@ def grid_corners(det_x, det_y, det_z):
                      [g[-1, 0] for g in (det_x, det_y, det_z)]], dtype=np.float64)
 
 
+def affine_plan_host(shape, mins, dq, corners, dev3, rows, cols, R, w):
+    """Host half of the fixed-point detector kernel (gx_host_affine_orientations): records and
+    plan for a [rows, cols] grid with exact corners `corners` ([3,3]: p[0,0], p[0,-1], p[-1,0]) whose
+    deviation from their interpolation is at most dev3 per component.  None when unsupported."""
+    n = int(len(w))
+    Vy, Vx, Vz = (int(v) for v in shape)
+    R = np.ascontiguousarray(R, dtype=np.float64)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    rec = np.zeros(n * call("gx_affine_record_bytes"), dtype=np.uint8)
+    plan = np.zeros(call("gx_affine_plan_doubles"), dtype=np.float64)
+    corners = np.ascontiguousarray(corners, dtype=np.float64).reshape(9)
+    dev3 = np.ascontiguousarray(dev3, dtype=np.float64)
+    try:
+        call("gx_host_affine_orientations", ptr(corners), ptr(dev3), int(rows), int(cols), ptr(R), ptr(w), n,
+             float(mins[0]), float(mins[1]), float(mins[2]), float(dq), Vy, Vx, Vz, ptr(rec), ptr(plan))
+    except _lib.GxError as e:
+        if e.code != _lib.GX_ERR_UNSUPPORTED:
+            raise
+        return None
+    return corners, rec, plan
+
+
+AFFINE_RECORD = np.dtype([("o", "<f8", 3), ("u", "<f8", 3), ("v", "<f8", 3), ("U", "<i4", 3), ("V", "<i4", 3),
+                          ("w", "<f4"), ("n_const", "<i4")])
+AFFINE_TILE = (16, 32)          # rows, cols of a CTA tile (GA_TH, GA_TW in gx_detector_affine.cu)
+
+
 class DetectorEngine:
     """Voxel grid resident on the device + accumulation of detector images."""
 
@@ -647,6 +721,8 @@ class DetectorEngine:
         self.dq = float(np.diff(qz)[0])               # detector.py:213
 
     last_slow_fraction = None
+    last_kernel = None
+    last_plan = None
 
     @staticmethod
     def _mostly_edge_locked(fast, pmax):
@@ -660,21 +736,38 @@ class DetectorEngine:
         locked = ((spread < 0.25) & near).any(axis=1)
         return locked.mean() > 0.5
 
-    def accumulate(self, det_x, det_y, det_z, R, w, image=None, probe=-1, exact_only=None, count_slow=False):
+    def affine_plan(self, px, py, pz, R, w):
+        """Fixed-point affine model of a [rows, cols] device grid for the orientations R, w:
+        (corners [3,3], records uint8 [n * record_bytes], plan float64 [8]) or None when the
+        grid is not affine enough / does not fit the fixed-point format."""
+        rows, cols = (int(s) for s in px.shape)
+        corners = np.zeros(9, dtype=np.float64)
+        dev3 = np.zeros(3, dtype=np.float64)
+        scratch = torch.zeros(3, dtype=torch.float64, device=self.device)
+        call("gx_grid_affine_fit", ptr(px), ptr(py), ptr(pz), rows, cols, ptr(scratch), ptr(corners), ptr(dev3),
+             _stream())
+        return self.affine_plan_host(corners, dev3, rows, cols, R, w)
+
+    def affine_plan_host(self, corners, dev3, rows, cols, R, w):
+        return affine_plan_host(self.shape, self.mins, self.dq, corners, dev3, rows, cols, R, w)
+
+    def accumulate(self, det_x, det_y, det_z, R, w, image=None, probe=-1, exact_only=None, count_slow=False,
+                   kernel=None):
         """image[P,P] (fp64, device) += sum_o w_o * iq[voxel(R_o p)].
 
-        Default: the fp32-filtered kernel (bit-identical indices; exact fp64 chain
-        only for pixels within the rounding bound of a voxel edge).  exact_only=True
-        (or GIWAXS_B200_EXACT_DETECTOR=1) runs the all-fp64 kernel."""
+        kernel: None (auto) | "affine" | "filtered" | "exact".  Auto uses the
+        fixed-point affine-grid kernel for 2-D grids that are affine in (row, col)
+        (every grid make_detector + rotations produce), else the fp32-filtered
+        generic kernel, else the all-fp64 one.  All three give bit-identical voxel
+        indices.  exact_only=True / GIWAXS_B200_EXACT_DETECTOR=1 forces "exact"."""
         dev = self.device
-        auto = exact_only is None and not EXACT_DETECTOR_ONLY
-        if exact_only is None:
-            exact_only = EXACT_DETECTOR_ONLY
+        if exact_only or (exact_only is None and EXACT_DETECTOR_ONLY):
+            kernel = "exact"
         with torch.cuda.device(dev):
-            shape = det_x.shape
+            shape = tuple(det_x.shape)
             n_pix = int(np.prod(shape))
             on_device = isinstance(det_x, torch.Tensor)
-            px, py, pz = (g if on_device else _dev(np.asarray(g, dtype=np.float64), dev)
+            px, py, pz = ((g.contiguous() if on_device else _dev(np.asarray(g, dtype=np.float64), dev))
                           for g in (det_x, det_y, det_z))
             if image is None:
                 image = torch.zeros(n_pix, dtype=torch.float64, device=dev)
@@ -683,41 +776,58 @@ class DetectorEngine:
             w = np.ascontiguousarray(w, dtype=np.float64)
             d_R = _dev(R, dev)
             Vy, Vx, Vz = self.shape
-            if exact_only:
-                d_w = _dev(w, dev)
-                call("gx_detector_accumulate", ptr(self.iq), Vy, Vx, Vz, self.mins[0], self.mins[1], self.mins[2],
-                     self.dq, ptr(px), ptr(py), ptr(pz), n_pix, ptr(d_R), ptr(d_w), int(len(w)),
-                     ptr(image), int(probe), ptr(index), _stream())
-            else:
+            slow = torch.zeros(1, dtype=torch.int64, device=dev) if count_slow else None
+            self.last_slow_fraction = None
+
+            if kernel in (None, "affine") and len(shape) == 2 and shape[0] > 1 and shape[1] > 1:
+                plan = self.affine_plan(px, py, pz, R, w)
+                # edge-locked: a coordinate that is constant over the detector, sits on a voxel edge
+                # and could not be proved constant -> every pixel would take the exact path anyway
+                if plan is not None and (kernel == "affine" or plan[2][6] <= 0.5 * len(w)):
+                    corners, rec, pl = plan
+                    d_rec = _dev(rec, dev)
+                    call("gx_detector_accumulate_affine", ptr(self.iq), Vy, Vx, Vz, self.mins[0], self.mins[1],
+                         self.mins[2], self.dq, ptr(px), ptr(py), ptr(pz), shape[0], shape[1], ptr(corners),
+                         ptr(d_rec), ptr(d_R), int(len(w)), ptr(pl), ptr(image), int(probe), ptr(index),
+                         ptr(slow), _stream())
+                    torch.cuda.current_stream().synchronize()
+                    self.last_kernel, self.last_plan = "affine", pl
+                    if count_slow:
+                        self.last_slow_fraction = float(slow.item()) / (n_pix * len(w))
+                    return image, index
+                if kernel == "affine":
+                    raise _lib.GxError(_lib.GX_ERR_UNSUPPORTED, "detector grid is not affine in (row, col)")
+
+            if kernel in (None, "filtered"):
                 if on_device and len(shape) == 2:
                     # driver path: the grid is affine in (row, col), so |component| peaks at a corner
-                    c = grid_corners(det_x, det_y, det_z)
+                    c = grid_corners(px, py, pz)
                     corners = np.vstack([c, c[1] + c[2] - c[0]])
                     pmax = np.abs(corners).max(axis=0) * (1.0 + 1e-9)
                 else:
-                    pmax = np.array([float(np.abs(np.asarray(g)).max()) for g in (det_x, det_y, det_z)])
+                    pmax = np.array([float(g.abs().max()) for g in (px, py, pz)])
                 fast = np.zeros(len(w) * call("gx_fast_record_bytes"), dtype=np.uint8)
                 pmax = np.ascontiguousarray(pmax, dtype=np.float64)      # keep alive across the call
                 call("gx_host_fast_orientations", ptr(R), ptr(w), int(len(w)), self.mins[0], self.mins[1],
                      self.mins[2], self.dq, ptr(pmax), ptr(fast))
-                if auto and self._mostly_edge_locked(fast, pmax):
-                    # e.g. phi = theta = 0: the plane lies in q_z = 0, exactly on a voxel edge, so
-                    # every pixel needs the exact chain for that component and the fp32 filter
-                    # would be pure overhead -> all-fp64 kernel (identity steps skipped)
-                    d_w = _dev(w, dev)
-                    call("gx_detector_accumulate", ptr(self.iq), Vy, Vx, Vz, self.mins[0], self.mins[1],
-                         self.mins[2], self.dq, ptr(px), ptr(py), ptr(pz), n_pix, ptr(d_R), ptr(d_w),
-                         int(len(w)), ptr(image), int(probe), ptr(index), _stream())
+                if kernel == "filtered" or not self._mostly_edge_locked(fast, pmax):
+                    d_fast = _dev(fast, dev)
+                    call("gx_detector_accumulate_fast", ptr(self.iq), Vy, Vx, Vz, self.mins[0], self.mins[1],
+                         self.mins[2], self.dq, ptr(px), ptr(py), ptr(pz), n_pix, ptr(d_fast), ptr(d_R),
+                         int(len(w)), ptr(image), int(probe), ptr(index), ptr(slow), _stream())
                     torch.cuda.current_stream().synchronize()
+                    self.last_kernel = "filtered"
+                    if count_slow:
+                        self.last_slow_fraction = float(slow.item()) / (n_pix * len(w))
                     return image, index
-                d_fast = _dev(fast, dev)
-                slow = torch.zeros(1, dtype=torch.int64, device=dev) if count_slow else None
-                call("gx_detector_accumulate_fast", ptr(self.iq), Vy, Vx, Vz, self.mins[0], self.mins[1],
-                     self.mins[2], self.dq, ptr(px), ptr(py), ptr(pz), n_pix, ptr(d_fast), ptr(d_R), int(len(w)),
-                     ptr(image), int(probe), ptr(index), ptr(slow), _stream())
-                if count_slow:
-                    self.last_slow_fraction = float(slow.item()) / (n_pix * len(w))
+
+            # all-fp64 kernel (identity rotation steps skipped)
+            d_w = _dev(w, dev)
+            call("gx_detector_accumulate", ptr(self.iq), Vy, Vx, Vz, self.mins[0], self.mins[1], self.mins[2],
+                 self.dq, ptr(px), ptr(py), ptr(pz), n_pix, ptr(d_R), ptr(d_w), int(len(w)),
+                 ptr(image), int(probe), ptr(index), _stream())
             torch.cuda.current_stream().synchronize()
+            self.last_kernel = "exact"
         return image, index
 
 

@@ -21,6 +21,12 @@ from .utilities import ATOMIC_NUMBER, get_element_f1_f2_dict
 _resident = {"host": None, "device": None}
 
 
+def f_table(uniq, energy):
+    """complex f = Z + f' + i f'' per unique element (comparison.py:735-739)."""
+    f1f2 = get_element_f1_f2_dict(energy, [str(e) for e in uniq])
+    return [complex(f1f2[str(e)]) + ATOMIC_NUMBER[str(e)] for e in uniq]
+
+
 def species_table(elements, energy):
     """(codes uint8 [A] or None, unique elements, complex f per unique element):
     f = Z + f' + i f'' (comparison.py:735-739)."""
@@ -28,9 +34,7 @@ def species_table(elements, energy):
     codes, uniq = engine.encode_values(elements)
     if codes is None:
         uniq = list(np.unique(elements))
-    f1f2 = get_element_f1_f2_dict(energy, [str(e) for e in uniq])
-    table = [complex(f1f2[str(e)]) + ATOMIC_NUMBER[str(e)] for e in uniq]
-    return codes, uniq, table
+    return codes, uniq, f_table(uniq, energy)
 
 
 def voxelgridmaker_fitting(coords, elements, r_voxel_size, q_voxel_size, max_q, energy, num_cpus=None,
@@ -49,11 +53,18 @@ def voxelgridmaker_fitting(coords, elements, r_voxel_size, q_voxel_size, max_q, 
     if max_q_diag > 2 * np.pi / r_voxel_size:
         raise Exception('Max_q is non-physical for given voxel size')
     grid_size = int(np.ceil(2 * np.pi / (q_voxel_size * r_voxel_size)))
-    codes, uniq, table = species_table(elements, energy)
+    with torch.cuda.device(dev):
+        enc = engine.encode_elements_device(elements, dev)
+    if enc is not None:
+        codes, uniq, counts = enc                    # coded on the device, counted there too
+        table = f_table(uniq, energy)
+    else:
+        codes, uniq, table = species_table(elements, energy)
+        counts = np.bincount(codes, minlength=len(table)) if codes is not None else None
     with torch.cuda.device(dev):
         if codes is not None:
             atoms = engine.AtomSet(coords, r_voxel_size, grid_size, dev, species=codes, table=table)
-            sum_f = np.sum(np.bincount(codes, minlength=len(table)) * np.asarray(table))
+            sum_f = np.sum(counts * np.asarray(table))
         else:
             lut = dict(zip([str(e) for e in uniq], table))
             f_values = np.array([lut[str(e)] for e in elements], dtype=complex)

@@ -73,6 +73,17 @@ int gx_atoms_sort_rows(const double *d_coords, int64_t A, double z_min, double r
                        uint8_t *d_species_out, gx_float2 *d_f_out,
                        int32_t *d_row_start, int32_t *d_cursor, void *stream);
 
+/* Species coding on the device (comparison.py:735-739 looks f up per atom from
+ * the element symbol).  d_codepoints: the NumPy '<U1' / '<U2' element array
+ * viewed as uint32 [A][width].  gx_species_histogram fills d_hist[16385]:
+ * bin k < 16384 counts atoms with key cp0 + (cp1 << 7), the last bin counts
+ * atoms with a non-ASCII code point.  gx_species_codes writes
+ * d_codes[i] = d_lut[key_i] (d_lut: 16384 uint8, built by the host from the
+ * occupied bins).                                                          */
+int gx_species_histogram(const uint32_t *d_codepoints, int width, int64_t A, uint32_t *d_hist, void *stream);
+int gx_species_codes(const uint32_t *d_codepoints, int width, int64_t A, const uint8_t *d_lut,
+                     uint8_t *d_codes, void *stream);
+
 /* min and max over all atoms of y' = fma(y, cos, x*sin) for n_phi rotations.
  * d_yrange [n_phi][2].                   (utilities.py:303-317, vg.py:323) */
 int gx_slice_yrange(const double *d_xs, const double *d_ys, int64_t A,
@@ -269,6 +280,41 @@ int gx_detector_accumulate_fast(const float *d_iq, int Vy, int Vx, int Vz,
 int gx_fast_record_bytes(void);
 int gx_host_fast_orientations(const double *h_R, const double *h_w, int n, double qx_min, double qy_min,
                               double qz_min, double dq, const double *h_pmax, void *h_fast);
+
+/* Production detector kernel: same result as gx_detector_accumulate, bit for
+ * bit in the voxel indices, for a pixel grid that is affine in (row, col)
+ * (make_detector + rotations, detector.py:5-162).  Voxel coordinates are
+ * evaluated in 32-bit fixed point from a per-orientation affine model that
+ * interpolates the reference's exact corner values; pixels within a rigorous
+ * error bound of a voxel edge fall back to the exact fp64 chain.
+ *   1. gx_grid_affine_fit: corners p[0,0], p[0,-1], p[-1,0] (h_corners9) and
+ *      max deviation of the grid from their interpolation per component
+ *      (h_dev3); d_scratch3 = 3 doubles of device scratch.  Synchronises.
+ *   2. gx_host_affine_orientations: n records of gx_affine_record_bytes()
+ *      and a plan of gx_affine_plan_doubles() doubles {frac bits, half-width
+ *      of the edge band in fixed-point units, coordinate offset, in-box
+ *      radius^2, error bound in voxels, #components the host proved constant,
+ *      #edge-locked orientations (a nearly constant coordinate on a voxel
+ *      edge that could not be modelled: every pixel takes the exact path),
+ *      #components modelled as a single rounding step}; GX_ERR_UNSUPPORTED
+ *      if the grid is not affine enough -> use gx_detector_accumulate.
+ *   3. gx_detector_accumulate_affine: the gather; d_records = device copy of
+ *      the records.  d_image fp64, += semantics (atomic when the orientation
+ *      range is split).                     (detector.py:194-244, 289-298)  */
+int gx_grid_affine_fit(const double *d_px, const double *d_py, const double *d_pz, int rows, int cols,
+                       double *d_scratch3, double *h_corners9, double *h_dev3, void *stream);
+int gx_affine_record_bytes(void);
+int gx_affine_plan_doubles(void);
+int gx_host_affine_orientations(const double *h_corners9, const double *h_dev3, int rows, int cols,
+                                const double *h_R, const double *h_w, int n, double qx_min, double qy_min,
+                                double qz_min, double dq, int Vy, int Vx, int Vz, void *h_records,
+                                double *h_plan);
+int gx_detector_accumulate_affine(const float *d_iq, int Vy, int Vx, int Vz, double qx_min, double qy_min,
+                                  double qz_min, double dq, const double *d_px, const double *d_py,
+                                  const double *d_pz, int rows, int cols, const double *h_corners9,
+                                  const void *d_records, const double *d_R, int n_orient,
+                                  const double *h_plan, double *d_image, int probe, int64_t *d_index_out,
+                                  unsigned long long *d_slow_count, void *stream);
 
 /* Host helper: the three per-orientation rotation matrices, derived exactly
  * as rotate_psi_phi_theta does from the current corner pixels.

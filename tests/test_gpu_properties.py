@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from giwaxsim_b200 import engine, synth
+from giwaxsim_b200 import _lib, engine, synth
 from giwaxsim_b200._lib import call, ptr
 from giwaxsim_b200.tools import comparison
 from oracle import giwaxs_oracle as ox
@@ -54,10 +54,10 @@ def test_hull_candidates_give_identical_y_range(kind):
 @pytest.mark.parametrize("inits,axs", [((90.0, 90.0, 90.0), ("psi", "phi", "psi")),
                                         ((0.0, 0.0, 0.0), ("None", "None", "None")),
                                         ((12.5, 40.0, 3.0), ("theta", "phi", "psi"))])
-def test_filtered_detector_kernel_is_bit_identical_to_exact(inits, axs):
-    """fp32-filtered gather == all-fp64 gather: same voxel index for every pixel of every
-    orientation (so the images are bitwise equal), including grid-aligned orientations
-    where every pixel sits on a voxel edge and pixels far outside the voxel box."""
+def test_fast_detector_kernels_are_bit_identical_to_exact(inits, axs):
+    """fixed-point affine gather == fp32-filtered gather == all-fp64 gather: same voxel index for
+    every pixel of every orientation, including grid-aligned orientations where every pixel sits
+    on a voxel edge and pixels far outside the voxel box (clamped)."""
     rng = np.random.default_rng(1)
     V = 101
     q = np.linspace(-2.0, 2.0, V)                     # dq = 0.04: detector pixels land on voxel edges
@@ -72,17 +72,72 @@ def test_filtered_detector_kernel_is_bit_identical_to_exact(inits, axs):
     R, w = engine.orientation_tables(engine.grid_corners(gx, gy, gz), psis, ones(psis), phis, ones(phis),
                                      thetas, ones(thetas))
     det = engine.DetectorEngine(iq, q, q, q)
-    img_exact, _ = det.accumulate(gx, gy, gz, R, w, exact_only=True)
-    img_fast, _ = det.accumulate(gx, gy, gz, R, w, exact_only=False, count_slow=True)
+    img_exact, _ = det.accumulate(gx, gy, gz, R, w, kernel="exact")
+    img_fast, _ = det.accumulate(gx, gy, gz, R, w, kernel="filtered", count_slow=True)
     assert torch.equal(img_exact, img_fast)
     assert 0.0 <= det.last_slow_fraction <= 1.0
-    for o in (0, 7, 19, 39):
-        _, a = det.accumulate(gx, gy, gz, R, w, probe=o, exact_only=True)
-        _, b = det.accumulate(gx, gy, gz, R, w, probe=o, exact_only=False)
-        assert torch.equal(a, b)
+    img_aff, _ = det.accumulate(gx, gy, gz, R, w, kernel="affine", count_slow=True)
+    assert det.last_kernel == "affine"
+    # fp32 partial sums over <= 64 orientations, then fp64: not bitwise, but close
+    assert float((img_aff - img_exact).abs().max()) <= 2e-6 * float(img_exact.abs().max())
+    for o in range(len(w)):
+        _, a = det.accumulate(gx, gy, gz, R, w, probe=o, kernel="exact")
+        _, c = det.accumulate(gx, gy, gz, R, w, probe=o, kernel="affine")
+        assert torch.equal(a, c), o
+        if o in (0, 7, 19, 39):
+            _, b = det.accumulate(gx, gy, gz, R, w, probe=o, kernel="filtered")
+            assert torch.equal(a, b)
+    # default dispatch picks the affine kernel for make_detector grids
+    det.accumulate(gx, gy, gz, R, w)
+    assert det.last_kernel == "affine"
 
 
-def test_filtered_detector_kernel_rarely_falls_back_on_generic_orientations():
+def test_affine_detector_kernel_partial_tiles_rectangular_and_split():
+    """rows != cols, sizes that are not multiples of the 32 x 16 tile, and the orientation-range
+    split with atomic accumulation used for small images."""
+    rng = np.random.default_rng(5)
+    V = 203
+    q = np.linspace(-2.02, 2.02, V)
+    iq = rng.random((V, V, V)).astype(np.float32)
+    dev = engine.resolve_device()
+    gx, gy, gz, _, _ = comparison.detector_base_device(150, 2.0, (90.0, 90.0, 90.0), ("psi", "phi", "psi"), dev)
+    gx, gy, gz = (g[:77, 3:140].contiguous() for g in (gx, gy, gz))
+    psis = np.linspace(0.0, 89.0, 40)
+    phis = np.array([0.0, 3.0, 90.0, 135.0, 177.0])
+    ones = lambda a: np.ones(len(a)) / len(a)
+    R, w = engine.orientation_tables(engine.grid_corners(gx, gy, gz), psis, ones(psis), phis, ones(phis), [0.0],
+                                     np.ones(1))
+    det = engine.DetectorEngine(iq, q, q, q)
+    a, _ = det.accumulate(gx, gy, gz, R, w, kernel="exact")
+    b, _ = det.accumulate(gx, gy, gz, R, w, kernel="affine", count_slow=True)
+    assert float((a - b).abs().max()) <= 2e-6 * float(a.abs().max())
+    assert det.last_slow_fraction < 0.01
+    for o in (0, 1, 57, 123, 199):
+        _, ia = det.accumulate(gx, gy, gz, R, w, probe=o, kernel="exact")
+        _, ib = det.accumulate(gx, gy, gz, R, w, probe=o, kernel="affine")
+        assert torch.equal(ia, ib), o
+
+
+def test_non_affine_grid_falls_back_to_generic_kernels():
+    rng = np.random.default_rng(6)
+    V = 64
+    q = np.linspace(-2.0, 2.0, V)
+    iq = rng.random((V, V, V)).astype(np.float32)
+    dev = engine.resolve_device()
+    gx, gy, gz, _, _ = comparison.detector_base_device(64, 2.0, (0.0, 0.0, 0.0), ("None", "None", "None"), dev)
+    gx = gx + 0.05 * torch.sin(gy * 3.0)                 # a curved detector: not affine in (row, col)
+    R, w = engine.orientation_tables(engine.grid_corners(gx, gy, gz), [10.0, 20.0], np.ones(2) / 2, [5.0],
+                                     np.ones(1), [0.0], np.ones(1))
+    det = engine.DetectorEngine(iq, q, q, q)
+    a, _ = det.accumulate(gx, gy, gz, R, w, kernel="exact")
+    b, _ = det.accumulate(gx, gy, gz, R, w)
+    assert det.last_kernel in ("filtered", "exact")
+    assert torch.equal(a, b)
+    with pytest.raises(_lib.GxError):
+        det.accumulate(gx, gy, gz, R, w, kernel="affine")
+
+
+def test_fast_detector_kernels_rarely_fall_back():
     rng = np.random.default_rng(2)
     V = 403
     q = np.linspace(-2.01, 2.01, V)
@@ -92,19 +147,50 @@ def test_filtered_detector_kernel_rarely_falls_back_on_generic_orientations():
     psis = np.linspace(3.1, 88.3, 24)
     ones = np.ones(1)
     det = engine.DetectorEngine(iq, q, q, q)
-    # tilted planes (phi = 7.3 deg): only pixels within the fp32 bound of a voxel edge fall back
+    # tilted planes (phi = 7.3 deg): only pixels within the error bound of a voxel edge fall back
     R, w = engine.orientation_tables(engine.grid_corners(gx, gy, gz), psis, np.ones(24) / 24, [7.3], ones, [0.4], ones)
-    a, _ = det.accumulate(gx, gy, gz, R, w, exact_only=True)
-    b, _ = det.accumulate(gx, gy, gz, R, w, exact_only=False, count_slow=True)
+    a, _ = det.accumulate(gx, gy, gz, R, w, kernel="exact")
+    b, _ = det.accumulate(gx, gy, gz, R, w, kernel="filtered", count_slow=True)
     assert torch.equal(a, b)
     assert det.last_slow_fraction < 0.02, det.last_slow_fraction
+    c, _ = det.accumulate(gx, gy, gz, R, w, kernel="affine", count_slow=True)
+    assert float((a - c).abs().max()) <= 2e-6 * float(a.abs().max())
+    assert det.last_slow_fraction < 1e-3, det.last_slow_fraction
     # phi = theta = 0: the plane lies in q_z = 0, i.e. exactly on a voxel edge, for every pixel
-    # (rounding noise picks the bin) -> every pixel needs the exact z index; still identical
+    # (rounding noise picks the bin) -> the fp32 filter sends every pixel to the exact chain; the
+    # affine kernel models the coordinate as constant / a single rounding step on the host
     R, w = engine.orientation_tables(engine.grid_corners(gx, gy, gz), psis, np.ones(24) / 24, [0.0], ones, [0.0], ones)
-    a, _ = det.accumulate(gx, gy, gz, R, w, exact_only=True)
-    b, _ = det.accumulate(gx, gy, gz, R, w, exact_only=False, count_slow=True)
+    a, _ = det.accumulate(gx, gy, gz, R, w, kernel="exact")
+    b, _ = det.accumulate(gx, gy, gz, R, w, kernel="filtered", count_slow=True)
     assert torch.equal(a, b)
     assert det.last_slow_fraction > 0.9
+    c, _ = det.accumulate(gx, gy, gz, R, w, kernel="affine", count_slow=True)
+    assert float((a - c).abs().max()) <= 2e-6 * float(a.abs().max())
+    assert det.last_slow_fraction < 1e-3, det.last_slow_fraction
+    for o in (0, 11, 23):
+        _, ia = det.accumulate(gx, gy, gz, R, w, probe=o, kernel="exact")
+        _, ic = det.accumulate(gx, gy, gz, R, w, probe=o, kernel="affine")
+        assert torch.equal(ia, ic)
+
+
+def test_affine_detector_kernel_rounding_step_model():
+    """Dyadic voxel axis: q = 0 is exactly a voxel edge AND a binade boundary of p - qmin, so the
+    1e-16 rounding noise of the in-plane coordinate decides the voxel pixel by pixel."""
+    rng = np.random.default_rng(3)
+    q = -2.0 + np.arange(513) * 2.0 ** -7
+    iq = rng.random((513, 513, 513)).astype(np.float32)
+    dev = engine.resolve_device()
+    gx, gy, gz, _, _ = comparison.detector_base_device(400, 2.0, (90.0, 90.0, 90.0), ("psi", "phi", "psi"), dev)
+    psis = np.linspace(0, 89.75, 16)
+    R, w = engine.orientation_tables(engine.grid_corners(gx, gy, gz), psis, np.ones(16) / 16, [0.0], np.ones(1),
+                                     [0.0], np.ones(1))
+    det = engine.DetectorEngine(iq, q, q, q)
+    for o in range(16):
+        _, ia = det.accumulate(gx, gy, gz, R, w, probe=o, kernel="exact")
+        _, ic = det.accumulate(gx, gy, gz, R, w, probe=o, kernel="affine", count_slow=True)
+        assert torch.equal(ia, ic), o
+    assert det.last_plan[7] >= 8          # the step model was used
+    assert det.last_slow_fraction < 0.05
 
 
 def test_linearity_of_detector_accumulation():
@@ -123,7 +209,8 @@ def test_linearity_of_detector_accumulation():
     a, _ = det.accumulate(gx, gy, gz, R, w1)
     b, _ = det.accumulate(gx, gy, gz, R, w2)
     c, _ = det.accumulate(gx, gy, gz, R, w1 + w2)
-    assert torch.allclose(a + b, c, rtol=1e-12, atol=0)
+    # fp32 partial sums inside the kernel (<= 64 orientations each), fp64 across them
+    assert torch.allclose(a + b, c, rtol=2e-6, atol=0)
 
 
 def test_counts_are_sum_over_slices_and_fused_equals_staged():
@@ -153,3 +240,32 @@ def test_counts_are_sum_over_slices_and_fused_equals_staged():
     assert np.abs(s_st - s_all).max() <= 1e-5 * s_all.max()
     # every kept sample is counted exactly once: total count = sum over slices of kept rows x kept cols
     assert c_all.sum() > 0
+
+
+@pytest.mark.parametrize("dtype", ["<U1", "<U2"])
+def test_device_species_coding_matches_host_coding(dtype):
+    rng = np.random.default_rng(4)
+    symbols = np.array(["C", "H", "S", "O", "F"] if dtype == "<U1" else ["C", "H", "Si", "O", "Cl", "Br"], dtype=dtype)
+    el = symbols[rng.integers(0, len(symbols), 100_003)]
+    dev = engine.resolve_device()
+    codes, uniq, counts = engine.encode_elements_device(el, dev)
+    h_codes, h_uniq = engine.encode_values(el)
+    assert [str(u) for u in uniq] == [str(u) for u in h_uniq]
+    assert np.array_equal(codes.cpu().numpy(), h_codes)
+    assert np.array_equal(counts, np.bincount(h_codes, minlength=len(h_uniq)))
+    # not element-symbol shaped input -> None (the caller uses the host coder)
+    assert engine.encode_elements_device(np.arange(5).astype(complex), dev) is None
+    assert engine.encode_elements_device(np.array(["C", "é"]), dev) is None
+    many = np.array(["%c%c" % (65 + i // 26, 97 + i % 26) for i in range(40)])
+    assert engine.encode_elements_device(many, dev) is None
+
+
+def test_to_host_f64_roundtrip():
+    dev = engine.resolve_device()
+    for dt in (torch.float32, torch.float64):
+        t = torch.randn(37, 41, 5, device=dev, dtype=dt)
+        out = engine.to_host_f64(t)
+        assert out.dtype == np.float64 and out.shape == (37, 41, 5)
+        assert np.array_equal(out, t.cpu().double().numpy())
+        out2 = engine.to_host_f64(t * 2)                 # the staging buffer is reused, results are not aliased
+        assert np.array_equal(out, t.cpu().double().numpy()) and np.array_equal(out2, 2 * out)
