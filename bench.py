@@ -82,11 +82,14 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Launch nvidia-smi early (it needs ~0.1 s to produce its first row); rows are time-stamped
+        and only those inside [mark_begin, mark_end] are reported."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -94,18 +97,30 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        good = [(t, r) for t, r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in good if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e300)]
+        window = "timed region"
+        if not rows:
+            # a timed region shorter than the sampling period: report the rows of warm-up + timed region
+            rows, window = [r for t, r in good], "warm-up + timed region (timed region shorter than one sample)"
+        sm = [float(r[1]) for r in rows]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) >= 8 and r[4 + k] == "Active" for r in self.rows)]
+        reasons = [n for k, n in enumerate(names) if any(r[4 + k] == "Active" for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": reasons}
+                "samples": len(sm), "reasons": reasons, "window": window}
 
 
 # --------------------------------------------------------------------------- CPU arm
@@ -185,8 +200,9 @@ def run_ours(args):
     N, q_num, q_axis, _ = engine.stage_a_geometry(atoms.bounds, r, q, max_q)
     sum_f = np.sum(np.bincount(codes, minlength=len(table)) * np.asarray(table))
     avg_f = (sum_f / np.prod(atoms.bounds)) * r ** 3
+    window = engine.crop_range(q_axis, max_q)          # as voxelgridmaker_fitting: accumulate the kept voxels only
     eng = engine.SliceEngine(None, r, q_axis, N, avg_f, atoms.bounds[0], atoms.bounds[1], cfg["fill_bkg"],
-                             cfg["smooth"], device=dev, atoms=atoms)
+                             cfg["smooth"], device=dev, atoms=atoms, window=window)
     my_phis = parallel.shard(phis_all, rank, world)
     P = cfg["num_pixels"]
     gx, gy, gz, det_h, det_v = comparison.detector_base_device(P, max_q, cfg["angle_init_vals"],
@@ -205,7 +221,8 @@ def run_ours(args):
         eng.run(my_phis)
         if world > 1:
             parallel.all_reduce_sum([eng.vsum, eng.count2])
-        state["iq"], state["axis"] = engine.finalize_voxels(eng.vsum, None, eng.count2, eng.row_hist, q_axis, max_q, dev)
+        state["iq"], state["axis"] = engine.finalize_voxels(eng.vsum, None, eng.count2, eng.row_hist, q_axis, max_q,
+                                                            dev, window=window)
 
     def stage_b():
         image.zero_()
@@ -216,16 +233,17 @@ def run_ours(args):
             parallel.all_reduce_sum([image])
         state["det"] = engine.detector_epilogue(image, P, P, True, dev, finish=True)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         stage_a()
         stage_b()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     eng.timers = {}
     _lib.reset_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
     barrier()
+    sampler.mark_begin()
     ev[0].record()
     for s in range(args.steps):
         stage_a()
@@ -233,6 +251,7 @@ def run_ours(args):
         stage_b()
         ev[2 * s + 2].record()
     barrier()
+    sampler.mark_end()
     launches = _lib.launch_count()
     clocks = sampler.stop()
     ms_a = sum(ev[2 * s].elapsed_time(ev[2 * s + 1]) for s in range(args.steps)) / args.steps

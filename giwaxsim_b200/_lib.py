@@ -75,6 +75,7 @@ _PROTOTYPES = {
     "gx_row_histogram": (_i, [_p, _i, _i, _p, _p]),
     "gx_voxel_finalize": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _d, _p, _p]),
     "gx_slice_col_range": (_i, [_p, _i, _i, _p, _p]),
+    "gx_window_indices": (_i, [_p, _i64, _i, _i, _i, _i, _p]),
     "gx_slices_fused": (_i, [_p, _p]),
     "gx_rotate_points": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "gx_detector_accumulate": (_i, [_p, _i, _i, _i, _d, _d, _d, _d, _p, _p, _p, _i64, _p, _p, _i,
@@ -131,7 +132,7 @@ _LAUNCHES = {
     "gx_axis_col_index": 1, "gx_axis_row_index": 1, "gx_bin_slices": 1, "gx_row_histogram": 1,
     "gx_voxel_finalize": 1, "gx_rotate_points": 1, "gx_detector_accumulate": 1, "gx_detector_epilogue": 1,
     "gx_detector_accumulate_fast": 1, "gx_detector_accumulate_affine": 1, "gx_grid_affine_fit": 1,
-    "gx_slices_fused": 2, "gx_species_histogram": 1, "gx_species_codes": 1, "gx_slice_col_range": 1, "gx_extreme_atoms": 1, "gx_hull_filter": 1,
+    "gx_slices_fused": 2, "gx_species_histogram": 1, "gx_species_codes": 1, "gx_window_indices": 1, "gx_slice_col_range": 1, "gx_extreme_atoms": 1, "gx_hull_filter": 1,
 }
 _launch_count = 0
 

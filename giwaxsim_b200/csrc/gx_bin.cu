@@ -191,3 +191,37 @@ extern "C" int gx_voxel_finalize(const float *d_sum, const uint32_t *d_count3, c
                                                                      lo, V, d_axis, aff, d_iq);
     return gx_check_launch("gx_voxel_finalize");
 }
+
+// ---------------------------------------------------------- crop window ----
+// downselect_voxelgrid (voxelgrids.py:16-48) keeps the voxels lo <= i < hi on
+// every axis and the crop commutes with the accumulation, so the production
+// driver accumulates only that window: bin indices outside it become -1 (the
+// column / row is then neither transformed nor binned) and the others are
+// re-based to a [V]^3 grid, V = hi - lo.  packed != 0: entries are iy*q_num+ix.
+__global__ void __launch_bounds__(256)
+window_indices_kernel(int32_t *idx, int64_t n, int q_num, int lo, int hi, int packed)
+{
+    const int V = hi - lo;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int v = idx[i];
+        if (v < 0) continue;
+        int out;
+        if (packed) {
+            const int iy = v / q_num, ix = v - iy * q_num;
+            out = (iy >= lo && iy < hi && ix >= lo && ix < hi) ? (iy - lo) * V + (ix - lo) : -1;
+        } else {
+            out = (v >= lo && v < hi) ? v - lo : -1;
+        }
+        idx[i] = out;
+    }
+}
+
+extern "C" int gx_window_indices(int32_t *d_index, int64_t n, int q_num, int lo, int hi, int packed, void *stream)
+{
+    GX_REQUIRE(d_index && n > 0, "bad arguments");
+    GX_REQUIRE(q_num > 0 && lo >= 0 && hi > lo && hi <= q_num, "bad window");
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > GX_SM_COUNT * 16) blocks = GX_SM_COUNT * 16;
+    window_indices_kernel<<<(int)blocks, 256, 0, gx_stream(stream)>>>(d_index, n, q_num, lo, hi, packed);
+    return gx_check_launch("gx_window_indices");
+}

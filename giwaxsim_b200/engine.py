@@ -80,7 +80,18 @@ def to_host_f64(t):
     stage.copy_(t, non_blocking=True)
     out = torch.empty(t.shape, dtype=torch.float64)
     torch.cuda.current_stream().synchronize()
-    out.copy_(stage)
+    # torchrun pins OMP_NUM_THREADS=1; the widening copy of a large grid is worth a few host
+    # threads per rank (never more than the cores this rank can fairly claim)
+    before = torch.get_num_threads()
+    want = max(1, min(16, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+    if nbytes >= (8 << 20) and want > before:
+        torch.set_num_threads(want)
+        try:
+            out.copy_(stage)
+        finally:
+            torch.set_num_threads(before)
+    else:
+        out.copy_(stage)
     return out.numpy()
 
 
@@ -361,7 +372,10 @@ class SliceEngine:
 
     def __init__(self, coords, r_voxel_size, q_axis, grid_size, avg_voxel_f, x_bound, y_bound,
                  fill_bkg, smooth, species=None, table=None, f_values=None, device=None,
-                 count3d=False, accumulators=None, atoms=None):
+                 count3d=False, accumulators=None, atoms=None, window=None):
+        """window=(lo, hi): accumulate only the voxels lo <= i < hi of every axis (the crop of
+        downselect_voxelgrid commutes with the sum) into [hi-lo]^3 grids; columns and rows that
+        fall outside are neither transformed nor binned."""
         self.device = resolve_device(device)
         with torch.cuda.device(self.device):
             self.N = int(grid_size)
@@ -391,14 +405,20 @@ class SliceEngine:
             self.d_q_fft = _dev(self.q_fft, dev)
             call("gx_axis_row_index", ptr(self.d_q_fft), self.N, self.qmin, self.qmax, self.dq,
                  self.q_num, ptr(self.row_index), st)
+            self.window = None if window is None else (int(window[0]), int(window[1]))
+            self.q_out = self.q_num            # side of the accumulator grids
+            if self.window is not None:
+                lo, hi = self.window
+                call("gx_window_indices", ptr(self.row_index), self.N, self.q_num, lo, hi, 0, st)
+                self.q_out = hi - lo
             if accumulators is not None:
                 self.vsum, self.count3, self.count2 = accumulators
             else:
-                self.vsum = torch.zeros(self.q_num ** 3, dtype=torch.float32, device=dev)
-                self.count3 = torch.zeros(self.q_num ** 3, dtype=torch.int32, device=dev) if count3d else None
-                self.count2 = None if count3d else torch.zeros(self.q_num ** 2, dtype=torch.int32, device=dev)
-            self.row_hist = torch.zeros(self.q_num, dtype=torch.int32, device=dev)
-            call("gx_row_histogram", ptr(self.row_index), self.N, self.q_num, ptr(self.row_hist), st)
+                self.vsum = torch.zeros(self.q_out ** 3, dtype=torch.float32, device=dev)
+                self.count3 = torch.zeros(self.q_out ** 3, dtype=torch.int32, device=dev) if count3d else None
+                self.count2 = None if count3d else torch.zeros(self.q_out ** 2, dtype=torch.int32, device=dev)
+            self.row_hist = torch.zeros(self.q_out, dtype=torch.int32, device=dev)
+            call("gx_row_histogram", ptr(self.row_index), self.N, self.q_out, ptr(self.row_hist), st)
             if self.sigma > 0:
                 w, self.gauss_radius = gaussian_weights(self.sigma)
                 self.gauss = _dev(w, dev)
@@ -412,6 +432,9 @@ class SliceEngine:
             self.row_lo, self.row_hi = (int(kept[0]), int(kept[-1]) + 1) if len(kept) else (0, 0)
             step = 2.0 * self.q_fft_max / (self.N - 1)
             reach = max(abs(self.qmin), abs(self.qmax))
+            if self.window is not None:
+                # columns are kept when both q components fall in [axis[lo], axis[hi-1] + dq)
+                reach = max(abs(self.q_axis[self.window[0]]), abs(self.q_axis[self.window[1] - 1] + self.dq))
             self.KC = int(min(self.N, (int(2.0 * np.sqrt(2.0) * reach / step) + 4 + 7) // 8 * 8))
 
     # -- per-batch host scalars -------------------------------------------
@@ -463,6 +486,8 @@ class SliceEngine:
         t["ends"] = [_dev(a, dev) for a in (xl, xr, yl, yr)]
         call("gx_slice_col_index", ptr(t["ends"][0]), ptr(t["ends"][1]), ptr(t["ends"][2]), ptr(t["ends"][3]),
              n, N, self.qmin, self.qmax, self.dq, self.q_num, ptr(t["col"]), st)
+        if self.window is not None:
+            call("gx_window_indices", ptr(t["col"]), n * N, self.q_num, self.window[0], self.window[1], 1, st)
         return t
 
     def project(self, t, grid):
@@ -478,7 +503,7 @@ class SliceEngine:
 
     def bin(self, t, iq2d):
         call("gx_bin_slices", ptr(iq2d), t["n"], self.N, self.N, ptr(t["col"]), self.N, ptr(self.row_index),
-             self.q_num, ptr(self.vsum), ptr(self.count3), ptr(self.count2), _stream())
+             self.q_out, ptr(self.vsum), ptr(self.count3), ptr(self.count2), _stream())
 
     def check_bbox(self, t):
         bb = t["bbox"].cpu().numpy().reshape(-1, 4)
@@ -507,7 +532,7 @@ class SliceEngine:
             setattr(args, name, None if tensor is None else tensor.data_ptr())
         args.r = self.r
         args.pedestal_re, args.pedestal_im = self.pedestal.real, self.pedestal.imag
-        args.n_species, args.n_phi, args.N, args.KC, args.q_num = a.n_species, n, self.N, self.KC, self.q_num
+        args.n_species, args.n_phi, args.N, args.KC, args.q_num = a.n_species, n, self.N, self.KC, self.q_out
         args.row_lo, args.row_hi = self.row_lo, self.row_hi
         args.fill_bkg, args.smooth_sigma = int(self.fill_bkg), self.sigma
         call("gx_slices_fused", ctypes.byref(args), _stream())
@@ -607,8 +632,8 @@ class SliceEngine:
             return y.cpu().numpy(), z.cpu().numpy(), t["bbox"].cpu().numpy()
 
     def counts(self):
-        """Per-voxel sample counts as an int64 host array [q,q,q]."""
-        q = self.q_num
+        """Per-voxel sample counts as an int64 host array [q,q,q] (q = window size if windowed)."""
+        q = self.q_out
         if self.count3 is not None:
             return self.count3.cpu().numpy().astype(np.int64).reshape(q, q, q)
         # rank-1 form: every slice shares the row table, so
@@ -618,7 +643,7 @@ class SliceEngine:
         return h[:, :, None] * m[None, None, :]
 
     def sums(self):
-        q = self.q_num
+        q = self.q_out
         return self.vsum.cpu().numpy().reshape(q, q, q)
 
 
@@ -633,17 +658,25 @@ def crop_range(axis, max_val):
     return int(idx[0]), int(idx[-1]) + 1
 
 
-def finalize_voxels(vsum, count3, count2, row_hist, q_axis, max_q, device):
-    """sum/count, crop, carbon f0 weighting -> (iq fp32 device [V,V,V], axis)."""
+def finalize_voxels(vsum, count3, count2, row_hist, q_axis, max_q, device, window=None):
+    """sum/count, crop, carbon f0 weighting -> (iq fp32 device [V,V,V], axis).
+    window: the accumulators already cover only that index window (SliceEngine(window=...))."""
     q_num = int(q_axis.shape[0])
     lo, hi = crop_range(q_axis, max_q)
     V = hi - lo
     with torch.cuda.device(device):
         iq = torch.empty(V * V * V, dtype=torch.float32, device=device)
         aff = np.asarray(CARBON_AFF, dtype=np.float64)
-        d_axis = _dev(q_axis, device)
-        call("gx_voxel_finalize", ptr(vsum), ptr(count3), ptr(count2), ptr(row_hist), q_num, lo, hi,
-             ptr(d_axis), ptr(aff), CARBON_Z, ptr(iq), _stream())
+        if window is not None:
+            if tuple(window) != (lo, hi):
+                raise ValueError("accumulator window %s is not the crop range %s" % (tuple(window), (lo, hi)))
+            d_axis = _dev(q_axis[lo:hi], device)
+            call("gx_voxel_finalize", ptr(vsum), ptr(count3), ptr(count2), ptr(row_hist), V, 0, V,
+                 ptr(d_axis), ptr(aff), CARBON_Z, ptr(iq), _stream())
+        else:
+            d_axis = _dev(q_axis, device)
+            call("gx_voxel_finalize", ptr(vsum), ptr(count3), ptr(count2), ptr(row_hist), q_num, lo, hi,
+                 ptr(d_axis), ptr(aff), CARBON_Z, ptr(iq), _stream())
         torch.cuda.current_stream().synchronize()
     return iq.view(V, V, V), q_axis[lo:hi].copy()
 
@@ -700,6 +733,7 @@ def affine_plan_host(shape, mins, dq, corners, dev3, rows, cols, R, w):
     return corners, rec, plan
 
 
+_affine_fit_cache = {}
 AFFINE_RECORD = np.dtype([("o", "<f8", 3), ("u", "<f8", 3), ("v", "<f8", 3), ("U", "<i4", 3), ("V", "<i4", 3),
                           ("w", "<f4"), ("n_const", "<i4")])
 AFFINE_TILE = (16, 32)          # rows, cols of a CTA tile (GA_TH, GA_TW in gx_detector_affine.cu)
@@ -741,12 +775,20 @@ class DetectorEngine:
         (corners [3,3], records uint8 [n * record_bytes], plan float64 [8]) or None when the
         grid is not affine enough / does not fit the fixed-point format."""
         rows, cols = (int(s) for s in px.shape)
-        corners = np.zeros(9, dtype=np.float64)
-        dev3 = np.zeros(3, dtype=np.float64)
-        scratch = torch.zeros(3, dtype=torch.float64, device=self.device)
-        call("gx_grid_affine_fit", ptr(px), ptr(py), ptr(pz), rows, cols, ptr(scratch), ptr(corners), ptr(dev3),
-             _stream())
-        return self.affine_plan_host(corners, dev3, rows, cols, R, w)
+        # the fit (one pass over the grid + a device->host read) is cached on the identity and
+        # version of the three tensors: drivers reuse one base grid for every call
+        key = tuple((g.data_ptr(), g._version) for g in (px, py, pz)) + (rows, cols, str(self.device))
+        hit = _affine_fit_cache.get(key)
+        if hit is None:
+            corners = np.zeros(9, dtype=np.float64)
+            dev3 = np.zeros(3, dtype=np.float64)
+            scratch = torch.zeros(3, dtype=torch.float64, device=self.device)
+            call("gx_grid_affine_fit", ptr(px), ptr(py), ptr(pz), rows, cols, ptr(scratch), ptr(corners),
+                 ptr(dev3), _stream())
+            while len(_affine_fit_cache) >= 4:
+                _affine_fit_cache.pop(next(iter(_affine_fit_cache)))
+            hit = _affine_fit_cache[key] = (corners, dev3, (px, py, pz))    # tensors kept alive: pointers stay valid
+        return self.affine_plan_host(hit[0], hit[1], rows, cols, R, w)
 
     def affine_plan_host(self, corners, dev3, rows, cols, R, w):
         return affine_plan_host(self.shape, self.mins, self.dq, corners, dev3, rows, cols, R, w)
@@ -790,7 +832,6 @@ class DetectorEngine:
                          self.mins[2], self.dq, ptr(px), ptr(py), ptr(pz), shape[0], shape[1], ptr(corners),
                          ptr(d_rec), ptr(d_R), int(len(w)), ptr(pl), ptr(image), int(probe), ptr(index),
                          ptr(slow), _stream())
-                    torch.cuda.current_stream().synchronize()
                     self.last_kernel, self.last_plan = "affine", pl
                     if count_slow:
                         self.last_slow_fraction = float(slow.item()) / (n_pix * len(w))

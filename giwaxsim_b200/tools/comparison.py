@@ -75,13 +75,16 @@ def voxelgridmaker_fitting(coords, elements, r_voxel_size, q_voxel_size, max_q, 
     if phis is None:
         phis = ref_phis
     avg_voxel_f = (sum_f / (x_bound * y_bound * z_bound)) * r_voxel_size ** 3     # comparison.py:742-744
+    # only the voxels downselect_voxelgrid keeps are accumulated (the crop commutes with the sum)
+    window = engine.crop_range(q_axis, max_q)
     eng = engine.SliceEngine(None, r_voxel_size, q_axis, grid_size, avg_voxel_f, x_bound, y_bound,
-                             fill_bkg, smooth, device=dev, atoms=atoms)
+                             fill_bkg, smooth, device=dev, atoms=atoms, window=window)
     rank, world = parallel.rank_world()
     eng.run(parallel.shard(np.asarray(phis, dtype=np.float64), rank, world))
     if world > 1:
         parallel.all_reduce_sum([eng.vsum, eng.count2])
-    iq_dev, axis = engine.finalize_voxels(eng.vsum, None, eng.count2, eng.row_hist, q_axis, max_q, dev)
+    iq_dev, axis = engine.finalize_voxels(eng.vsum, None, eng.count2, eng.row_hist, q_axis, max_q, dev,
+                                          window=window)
     with torch.cuda.device(dev):
         iq = engine.to_host_f64(iq_dev)                   # widen on the device, one pinned D2H copy
     _resident["host"], _resident["device"] = iq, iq_dev
@@ -89,9 +92,27 @@ def voxelgridmaker_fitting(coords, elements, r_voxel_size, q_voxel_size, max_q, 
     return out + (eng,) if return_state else out
 
 
+_base_cache = {}
+
+
 def detector_base_device(num_pixels, max_q, angle_init_vals, angle_init_axs, dev):
     """make_detector + the optional init rotations (comparison.py:798-818) with
-    the three coordinate grids kept on the device."""
+    the three coordinate grids kept on the device.  The (read-only) grids of the
+    last few detector geometries are kept, so repeated calls (fits, scans over
+    weights) neither rebuild nor re-analyse them."""
+    key = (int(num_pixels), float(max_q), tuple(float(v) for v in angle_init_vals),
+           tuple(str(a) for a in angle_init_axs), str(dev))
+    hit = _base_cache.get(key)
+    if hit is not None:
+        return hit
+    out = _detector_base_device(num_pixels, max_q, angle_init_vals, angle_init_axs, dev)
+    while len(_base_cache) >= 2:
+        _base_cache.pop(next(iter(_base_cache)))
+    _base_cache[key] = out
+    return out
+
+
+def _detector_base_device(num_pixels, max_q, angle_init_vals, angle_init_axs, dev):
     h = np.linspace(-max_q, max_q, num_pixels)
     v = np.linspace(-max_q, max_q, num_pixels)
     with torch.cuda.device(dev):
@@ -138,4 +159,4 @@ def detectormaker_fitting(iq, qx, qy, qz, num_pixels, max_q, angle_init_vals, an
         parallel.all_reduce_sum([image])
     out = engine.detector_epilogue(image, num_pixels, num_pixels, mirror, dev, finish=True)
     with torch.cuda.device(dev):
-        return engine.to_host_f64(out), det_h, det_v
+        return engine.to_host_f64(out), det_h.copy(), det_v.copy()

@@ -244,6 +244,13 @@ typedef struct gx_fused_args {
 } gx_fused_args;
 int gx_slices_fused(const gx_fused_args *h_args, void *stream);
 
+/* Restrict bin indices to the crop window lo <= i < hi of downselect_voxelgrid
+ * (voxelgrids.py:16-48; the crop commutes with the accumulation): entries
+ * outside become -1, the others are re-based to a [hi-lo]^3 grid.  packed != 0:
+ * entries are iy*q_num+ix (gx_slice_col_index), else plain iz
+ * (gx_axis_row_index).  In place.                                           */
+int gx_window_indices(int32_t *d_index, int64_t n, int q_num, int lo, int hi, int packed, void *stream);
+
 /* --------------------------------------------------------- detector (K4) */
 /* p <- R p for n points, R row-major 3x3, fma chain k=0,1,2.
  *                                                  (detector.py:71,113,155) */

@@ -20,14 +20,14 @@ TOL_INT = 1e-4       # intensities, relative to the reference maximum
 CASES = ["graphite262", "silicon256", "clipped128"]
 
 
-def _engine_for(g, count3d=False):
+def _engine_for(g, count3d=False, window=None):
     """SliceEngine on the fixture's slab with the reference-derived scalars."""
     coords = g["coords"]
     codes, uniq = engine.encode_values(g["f_values"])
     b = g["bounds"]
     return engine.SliceEngine(coords, float(g["r"]), g["q_axis"], int(g["grid_size"]), complex(g["avg_voxel_f"]),
                               b[0], b[1], bool(g["fill_bkg"]), int(g["smooth"]), species=codes, table=uniq,
-                              count3d=count3d)
+                              count3d=count3d, window=window)
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -80,6 +80,24 @@ def test_T5_accumulators(golden, name, count3d):
     assert np.array_equal(eng.counts(), g["vcnt"].astype(np.int64))          # bit-exact
     err = np.abs(eng.sums().astype(np.float64) - g["vsum"]).max() / float(g["vsum_max"])
     assert err <= TOL_INT, err
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("count3d", [False, True])
+def test_T5_accumulators_crop_window(golden, name, count3d):
+    """The production driver accumulates only the voxels downselect_voxelgrid keeps: counts and
+    sums of that window equal the reference's full accumulators cropped to it."""
+    g = golden(name + ".npz")
+    lo, hi = engine.crop_range(g["q_axis"], float(g["max_q"]))
+    assert hi - lo == len(g["q_crop"]) and hi - lo < len(g["q_axis"])
+    eng = _engine_for(g, count3d=count3d, window=(lo, hi))
+    eng.run(g["phis"])
+    ref_cnt = g["vcnt"].astype(np.int64)[lo:hi, lo:hi, lo:hi]
+    ref_sum = g["vsum"][lo:hi, lo:hi, lo:hi]
+    assert np.array_equal(eng.counts(), ref_cnt)                               # bit-exact
+    err = np.abs(eng.sums().astype(np.float64) - ref_sum).max() / float(g["vsum_max"])
+    assert err <= TOL_INT, err
+    assert eng.KC <= _engine_for(g).KC
 
 
 @pytest.mark.parametrize("name", CASES)
