@@ -143,12 +143,18 @@ def cpu_stage_rates(cfg, coords, elements, n_slices, n_orient, threads):
     return len(phis) / ta, len(psis) / tb, len(phis), len(psis)
 
 
+def cpu_threads():
+    """Host threads of the CPU arm: all cores, capped at 32 (the reference's own pool is
+    min(32, cores + 4) workers, comparison.py:759; one N = 4096 slice needs ~1.5 GB of scratch)."""
+    return max(1, min(32, os.cpu_count() or 1))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg, coords, elements = workload(args)
-    threads = os.cpu_count()
+    threads = cpu_threads()
     n = args.cpu_slices or threads
     rates = []
     for _ in range(max(1, args.warmup > 0) + args.steps):     # one warm-up pass is enough on the CPU
@@ -359,7 +365,7 @@ def run_ours(args):
     if e2e is not None:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu:
-        threads = os.cpu_count()
+        threads = cpu_threads()
         n = args.cpu_slices or threads
         sa, sb, na, nb = cpu_stage_rates(cfg, coords, elements, n, n, threads)
         line["cpu_baseline"] = {"value": sa, "unit": UNIT, "cores": threads, "kind": "port",

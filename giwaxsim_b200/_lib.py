@@ -36,9 +36,9 @@ class FusedArgs(ctypes.Structure):
     """gx_fused_args (include/giwaxs_b200.h)."""
     _fields_ = [(n, ctypes.c_void_p) for n in
                 ("d_xs", "d_ys", "d_species", "d_f", "d_row_start", "d_table", "d_sin", "d_cos", "d_yrange",
-                 "d_bbox", "d_base", "d_my", "d_mz", "d_plan", "d_col", "d_colrange", "d_row_index",
+                 "d_bbox", "d_dmy", "d_mz", "d_plan", "d_col", "d_colrange", "d_row_index",
                  "d_work", "d_sum", "d_count2")] + \
-               [(n, ctypes.c_double) for n in ("r", "pedestal_re", "pedestal_im")] + \
+               [(n, ctypes.c_double) for n in ("r", "pedestal_re", "pedestal_im", "avg_f_re", "avg_f_im")] + \
                [(n, ctypes.c_int32) for n in ("n_species", "n_phi", "N", "KC", "q_num", "row_lo", "row_hi",
                                               "fill_bkg", "smooth_sigma", "pad")]
 
@@ -62,7 +62,7 @@ _PROTOTYPES = {
     "gx_hull_filter": (_i, [_p, _p, _i64, _p, _i, _d, _p, _p, _p, _i, _p]),
     "gx_slice_bbox": (_i, [_p, _p, _p, _i, _d, _p, _p, _p, _i, _p, _p, _p]),
     "gx_atom_pixel_indices": (_i, [_p, _p, _p, _p, _i64, _i, _d, _d, _d, _d, _p, _p, _p]),
-    "gx_slice_vectors": (_i, [_p, _p, _i, _i, _d, _d, _d, _d, _d, _d, _i, _i, _p, _i, _p, _p, _p, _p]),
+    "gx_slice_vectors": (_i, [_p, _p, _i, _i, _d, _d, _d, _d, _d, _d, _i, _i, _p, _i, _p, _p, _p, _p, _p]),
     "gx_project_slices": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _d,
                                _d, _d, _i, _i, _p, _p]),
     "gx_fft_plan_bytes": (_i64, [_i]),

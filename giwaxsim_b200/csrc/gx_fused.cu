@@ -29,6 +29,8 @@
 
 struct FusedArgs {
     ProjArgs proj;
+    const float2 *dmy;         // [n_phi][N] (num_missing - max_voxels, my): base = dmy.x * avg_f
+    float af_re, af_im;
     GxFftLayout lay;
     const float2 *plan;
     const int32_t *col;        // [n_phi][N] packed iy*q_num+ix or -1
@@ -75,15 +77,20 @@ slice_rows_fused(FusedArgs fa)
     const ProjArgs &a = fa.proj;
     const int p = blockIdx.x, z = blockIdx.y;
     const int N = a.N, tid = threadIdx.x;
+    // every per-rotation / per-row scalar is requested before the first branch, so the CTA
+    // pays one L2 round trip for all of them instead of one per dependent use
+    const int z_min = __ldg(a.bbox + 4 * p + 2), z_max = __ldg(a.bbox + 4 * p + 3);
+    const int jlo = __ldg(fa.colrange + 2 * p), jhi = __ldg(fa.colrange + 2 * p + 1);
+    const double s = __ldg(a.sn + p), c = __ldg(a.cs + p), shift = __ldg(a.yrange + 2 * p);
+    const int beg = __ldg(a.row_start + z), end = __ldg(a.row_start + z + 1);
+    const float mzv = __ldg(a.mz + (size_t)p * N + z);
     int za, zb;
-    active_band(a, p, za, zb);
+    if (a.fill_bkg) { za = z_min; zb = z_max - 1; }
+    else if (a.sigma > 0) { za = 0; zb = N - 1; }
+    else { za = z_min; zb = z_max; }
     if (z < za || z > zb) return;
-    const int jlo = fa.colrange[2 * p], jhi = fa.colrange[2 * p + 1];
     if (jhi <= jlo) return;
 
-    const double s = a.sn[p], c = a.cs[p], shift = a.yrange[2 * p];
-    const int beg = a.row_start[z], end = a.row_start[z + 1];
-    const float mzv = a.mz[(size_t)p * N + z];
     const int NP = (N + 3) & ~3;                           // counter plane stride (words)
     float2 px[NB0][R0];
 #pragma unroll
@@ -97,6 +104,7 @@ slice_rows_fused(FusedArgs fa)
         uint4 *words4 = reinterpret_cast<uint4 *>(smem_raw);
         for (int y = tid; y < npair * (NP / 4); y += NT) words4[y] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
+        // 16-bit counters: rows with more than 65535 atoms are counted in chunks
         for (int c0 = beg; c0 < end; c0 += 65535) {
             const int c1 = min(c0 + 65535, end);
             scatter_species(a, c0, c1, s, c, shift, words, NP);
@@ -112,18 +120,22 @@ slice_rows_fused(FusedArgs fa)
                     for (int n = 0; n < R0; ++n) {
                         const int y = t + S0 * n;
                         if (t < S0 && y < N) {
+                            // branch-free: most warps see a non-empty pixel anyway.  Counts go to
+                            // fp32 through the 2^23 mantissa trick (LOP/PRMT + FADD, no I2F)
                             const uint32_t cnt = plane[y];
-                            if (cnt) {
-                                const float n0 = (float)(cnt & 0xffffu), n1 = (float)(cnt >> 16);
-                                px[i][n].x += n0 * f0.x + n1 * f1.x;
-                                px[i][n].y += n0 * f0.y + n1 * f1.y;
-                                if (more) plane[y] = 0u;
-                            }
+                            const float n0 = __uint_as_float(0x4B000000u | (cnt & 0xffffu)) - 8388608.f;
+                            const float n1 = __uint_as_float(__byte_perm(cnt, 0x4B000000u, 0x7632)) - 8388608.f;
+                            px[i][n].x = fmaf(n1, f1.x, fmaf(n0, f0.x, px[i][n].x));
+                            px[i][n].y = fmaf(n1, f1.y, fmaf(n0, f0.y, px[i][n].y));
                         }
                     }
                 }
             }
             __syncthreads();   // every counter read is done before the next chunk / before buf is written
+            if (more) {
+                for (int y = tid; y < npair * (NP / 4); y += NT) words4[y] = make_uint4(0u, 0u, 0u, 0u);
+                __syncthreads();
+            }
         }
     } else {
         // generic per-atom f: accumulate straight into the (padded) row buffer
@@ -150,19 +162,27 @@ slice_rows_fused(FusedArgs fa)
         __syncthreads();
     }
 
-    // complete the pixels (pedestal-free) in registers and run the first pass on them
-    const size_t vo = (size_t)p * N;
+    // complete the pixels (pedestal-free) in registers and run the first pass on them:
+    // (atoms + d * avg_f) * mz * my with (d, my) packed in one 8-byte load per pixel
+    const float2 *dmy = fa.dmy + (size_t)p * N;
     const float2 *tw0 = fa.plan + fa.lay.tw_off[0];
 #pragma unroll
     for (int i = 0; i < NB0; ++i) {
         const int t = tid + i * NT;
         if (t < S0) {
+            float2 dm[R0];
+#pragma unroll
+            for (int n = 0; n < R0; ++n) {
+                const int y = t + S0 * n;
+                dm[n] = (y < N) ? __ldg(dmy + y) : make_float2(0.f, 0.f);
+            }
 #pragma unroll
             for (int n = 0; n < R0; ++n) {
                 const int y = t + S0 * n;
                 float2 v = make_float2(0.f, 0.f);
                 if (y < N) {
-                    v = finish_pixel(px[i][n], a.base[vo + y], mzv * a.my[vo + y]);
+                    const float m = mzv * dm[n].y;
+                    v = make_float2(fmaf(dm[n].x, fa.af_re, px[i][n].x) * m, fmaf(dm[n].x, fa.af_im, px[i][n].y) * m);
                     if (BLUE) v = gx_cmul(v, fa.plan[fa.lay.chirp_off + y]);
                 }
                 px[i][n] = v;
@@ -313,12 +333,12 @@ extern "C" int gx_slices_fused(const gx_fused_args *h, void *stream)
 {
     GX_REQUIRE(h != NULL, "NULL argument block");
     GX_REQUIRE(h->d_xs && h->d_ys && h->d_row_start && h->d_sin && h->d_cos && h->d_yrange && h->d_bbox &&
-               h->d_base && h->d_plan && h->d_col && h->d_colrange && h->d_row_index && h->d_work &&
+               h->d_dmy && h->d_plan && h->d_col && h->d_colrange && h->d_row_index && h->d_work &&
                h->d_sum && h->d_count2, "NULL pointer");
     GX_REQUIRE(h->n_species >= 0 && h->n_species <= GX_MAX_SPECIES, "n_species out of range");
     GX_REQUIRE(h->n_species == 0 ? h->d_f != NULL : (h->d_species != NULL && h->d_table != NULL),
                "species/f inputs missing");
-    GX_REQUIRE(h->d_my && h->d_mz, "mask vectors missing");
+    GX_REQUIRE(h->d_mz, "mask vector missing");
     GX_REQUIRE(h->n_phi > 0 && h->n_phi <= 65535 && h->N >= 16 && h->KC > 0 && h->q_num > 0, "bad sizes");
     GX_REQUIRE(h->row_lo >= 0 && h->row_hi <= h->N && h->row_lo <= h->row_hi, "bad kept-row range");
     FusedArgs fa;
@@ -326,7 +346,9 @@ extern "C" int gx_slices_fused(const gx_fused_args *h, void *stream)
     a.xs = h->d_xs; a.ys = h->d_ys; a.species = h->d_species; a.f = reinterpret_cast<const float2 *>(h->d_f);
     a.row_start = h->d_row_start; a.table = reinterpret_cast<const float2 *>(h->d_table);
     a.n_species = h->n_species; a.sn = h->d_sin; a.cs = h->d_cos; a.yrange = h->d_yrange; a.bbox = h->d_bbox;
-    a.base = reinterpret_cast<const float2 *>(h->d_base); a.my = h->d_my; a.mz = h->d_mz;
+    a.base = NULL; a.my = NULL; a.mz = h->d_mz;
+    fa.dmy = reinterpret_cast<const float2 *>(h->d_dmy);
+    fa.af_re = (float)h->avg_f_re; fa.af_im = (float)h->avg_f_im;
     a.N = h->N; a.r = h->r; a.ped_re = (float)h->pedestal_re; a.ped_im = (float)h->pedestal_im;
     a.fill_bkg = h->fill_bkg; a.sigma = h->smooth_sigma;
     fa.lay = gx_fft_layout(h->N);

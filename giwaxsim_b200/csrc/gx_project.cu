@@ -58,13 +58,15 @@ __global__ void __launch_bounds__(256)
 slice_vectors_kernel(const gx_chord *__restrict__ chord, const int32_t *__restrict__ bbox, int N, double r,
                      double max_voxels, double af_re, double af_im, double ped_re, double ped_im,
                      int fill_bkg, int sigma, const double *__restrict__ gauss, int radius,
-                     float2 *base, float *my, float *mz)
+                     float2 *base, float *my, float *mz, float2 *dmy)
 {
     const int p = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const size_t o = (size_t)p * N + i;
     const int y_min = bbox[4 * p + 0], y_max = bbox[4 * p + 1], z_min = bbox[4 * p + 2], z_max = bbox[4 * p + 3];
+    // base relative to the pedestal P = avg_f * max_voxels, in units of avg_f: base = d_rel * avg_f
+    float d_rel;
     if (fill_bkg) {
         const gx_chord k = chord[p];
         const double inv_r = 1.0 / r;
@@ -72,10 +74,12 @@ slice_vectors_kernel(const gx_chord *__restrict__ chord, const int32_t *__restri
         double len = chord_length(k, x);
         double q = gx_floordiv(len, r, inv_r);
         double nm = (double)(long long)__dsub_rn(max_voxels, q);   // astype(int) truncates
+        d_rel = (float)__dsub_rn(nm, max_voxels);                  // small integer: exact in fp32
         base[o] = make_float2((float)__dsub_rn(__dmul_rn(nm, af_re), ped_re),
                               (float)__dsub_rn(__dmul_rn(nm, af_im), ped_im));
     } else {
         base[o] = make_float2((float)-ped_re, (float)-ped_im);
+        d_rel = (ped_re != 0.0 || ped_im != 0.0) ? (float)-max_voxels : 0.f;
     }
     float vy = 1.f, vz = 1.f;
     if (sigma > 0) {
@@ -93,13 +97,14 @@ slice_vectors_kernel(const gx_chord *__restrict__ chord, const int32_t *__restri
     }
     my[o] = vy;
     mz[o] = vz;
+    if (dmy) dmy[o] = make_float2(d_rel, vy);
 }
 
 extern "C" int gx_slice_vectors(const gx_chord *d_chord, const int32_t *d_bbox, int n_phi, int N, double r,
                                 double max_voxels, double avg_f_re, double avg_f_im,
                                 double pedestal_re, double pedestal_im,
                                 int fill_bkg, int smooth_sigma, const double *d_gauss, int gauss_radius,
-                                gx_float2 *d_base, float *d_my, float *d_mz, void *stream)
+                                gx_float2 *d_base, float *d_my, float *d_mz, gx_float2 *d_dmy, void *stream)
 {
     GX_REQUIRE(d_bbox && d_base && d_my && d_mz, "NULL pointer");
     GX_REQUIRE(!fill_bkg || d_chord, "fill_bkg needs chord constants");
@@ -107,7 +112,8 @@ extern "C" int gx_slice_vectors(const gx_chord *d_chord, const int32_t *d_bbox, 
     GX_REQUIRE(n_phi > 0 && N >= 16, "bad sizes");
     slice_vectors_kernel<<<dim3((N + 255) / 256, n_phi), 256, 0, gx_stream(stream)>>>(
         d_chord, d_bbox, N, r, max_voxels, avg_f_re, avg_f_im, pedestal_re, pedestal_im, fill_bkg,
-        smooth_sigma, d_gauss, gauss_radius, reinterpret_cast<float2 *>(d_base), d_my, d_mz);
+        smooth_sigma, d_gauss, gauss_radius, reinterpret_cast<float2 *>(d_base), d_my, d_mz,
+        reinterpret_cast<float2 *>(d_dmy));
     return gx_check_launch("gx_slice_vectors");
 }
 

@@ -476,10 +476,11 @@ class SliceEngine:
         # blend mask x "inside the atom box" indicator per column / per row
         t["my"] = torch.empty(n * N, dtype=torch.float32, device=dev)
         t["mz"] = torch.empty(n * N, dtype=torch.float32, device=dev)
+        t["dmy"] = torch.empty(2 * n * N, dtype=torch.float32, device=dev)
         call("gx_slice_vectors", ptr(d_chord), ptr(t["bbox"]), n, N, self.r, float(self.max_voxels),
              self.avg_voxel_f.real, self.avg_voxel_f.imag, self.pedestal.real, self.pedestal.imag,
              int(self.fill_bkg), self.sigma, ptr(self.gauss), self.gauss_radius,
-             ptr(t["base"]), ptr(t.get("my")), ptr(t.get("mz")), st)
+             ptr(t["base"]), ptr(t.get("my")), ptr(t.get("mz")), ptr(t["dmy"]), st)
         t["col"] = torch.empty(n * N, dtype=torch.int32, device=dev)
         # keep the four end-point arrays referenced until the launch: temporaries
         # would be recycled by the caching allocator and alias each other
@@ -525,13 +526,14 @@ class SliceEngine:
         for name, tensor in (("d_xs", a.xs), ("d_ys", a.ys), ("d_species", a.species), ("d_f", a.f),
                              ("d_row_start", a.row_start), ("d_table", a.table), ("d_sin", t["sin"]),
                              ("d_cos", t["cos"]), ("d_yrange", t["yrange"]), ("d_bbox", t["bbox"]),
-                             ("d_base", t["base"]), ("d_my", t.get("my")), ("d_mz", t.get("mz")),
+                             ("d_dmy", t["dmy"]), ("d_mz", t.get("mz")),
                              ("d_plan", self.plan.table), ("d_col", t["col"]), ("d_colrange", t["colrange"]),
                              ("d_row_index", self.row_index), ("d_work", work), ("d_sum", self.vsum),
                              ("d_count2", self.count2)):
             setattr(args, name, None if tensor is None else tensor.data_ptr())
         args.r = self.r
         args.pedestal_re, args.pedestal_im = self.pedestal.real, self.pedestal.imag
+        args.avg_f_re, args.avg_f_im = self.avg_voxel_f.real, self.avg_voxel_f.imag
         args.n_species, args.n_phi, args.N, args.KC, args.q_num = a.n_species, n, self.N, self.KC, self.q_out
         args.row_lo, args.row_hi = self.row_lo, self.row_hi
         args.fill_bkg, args.smooth_sigma = int(self.fill_bkg), self.sigma
@@ -549,7 +551,7 @@ class SliceEngine:
             # per-rotation tables for the whole run in one set of launches, then one
             # pair of fused launches per batch on views of them
             full = self._timed("prepare", self.prepare, phis)
-            per_phi = {"sin": 1, "cos": 1, "yrange": 2, "bbox": 4, "base": 2 * N, "my": N, "mz": N, "col": N}
+            per_phi = {"sin": 1, "cos": 1, "yrange": 2, "bbox": 4, "base": 2 * N, "my": N, "mz": N, "dmy": 2 * N, "col": N}
             for i0 in range(0, len(phis), B):
                 n = min(B, len(phis) - i0)
                 t = {k: full[k][i0 * w:(i0 + n) * w] for k, w in per_phi.items()}
@@ -822,22 +824,44 @@ class DetectorEngine:
             self.last_slow_fraction = None
 
             if kernel in (None, "affine") and len(shape) == 2 and shape[0] > 1 and shape[1] > 1:
-                plan = self.affine_plan(px, py, pz, R, w)
-                # edge-locked: a coordinate that is constant over the detector, sits on a voxel edge
-                # and could not be proved constant -> every pixel would take the exact path anyway
-                if plan is not None and (kernel == "affine" or plan[2][6] <= 0.5 * len(w)):
+                # The host model of a chunk of orientations is built while the GPU works on the
+                # previous chunk (launches are asynchronous): a short first chunk gets the device
+                # busy at once, later chunks are sized so that their host time stays hidden.
+                n = len(w)
+                bounds = [0, min(n, 48)]
+                while bounds[-1] < n:
+                    bounds.append(min(n, bounds[-1] + 1024))
+                launched = False
+                for b0, b1 in zip(bounds[:-1], bounds[1:]):
+                    Rc, wc = R[b0:b1], w[b0:b1]
+                    plan = self.affine_plan(px, py, pz, Rc, wc)
+                    # edge-locked: a coordinate that is constant over the detector, sits on a voxel edge
+                    # and could not be modelled -> every pixel would take the exact path anyway
+                    ok = plan is not None and (kernel == "affine" or plan[2][6] <= 0.5 * (b1 - b0))
+                    if not ok:
+                        if kernel == "affine":
+                            raise _lib.GxError(_lib.GX_ERR_UNSUPPORTED, "detector grid is not affine in (row, col)")
+                        if not launched:
+                            break                          # generic kernels below take the whole set
+                        d_w = _dev(wc, dev)                # this chunk only: all-fp64 kernel
+                        pr = probe - b0 if b0 <= probe < b1 else -1
+                        call("gx_detector_accumulate", ptr(self.iq), Vy, Vx, Vz, self.mins[0], self.mins[1],
+                             self.mins[2], self.dq, ptr(px), ptr(py), ptr(pz), n_pix, ptr(d_R[b0:b1]), ptr(d_w),
+                             b1 - b0, ptr(image), int(pr), ptr(index) if pr >= 0 else None, _stream())
+                        continue
                     corners, rec, pl = plan
                     d_rec = _dev(rec, dev)
+                    pr = probe - b0 if b0 <= probe < b1 else -1
                     call("gx_detector_accumulate_affine", ptr(self.iq), Vy, Vx, Vz, self.mins[0], self.mins[1],
                          self.mins[2], self.dq, ptr(px), ptr(py), ptr(pz), shape[0], shape[1], ptr(corners),
-                         ptr(d_rec), ptr(d_R), int(len(w)), ptr(pl), ptr(image), int(probe), ptr(index),
-                         ptr(slow), _stream())
+                         ptr(d_rec), ptr(d_R[b0:b1]), b1 - b0, ptr(pl), ptr(image), int(pr),
+                         ptr(index) if pr >= 0 else None, ptr(slow), _stream())
+                    launched = True
                     self.last_kernel, self.last_plan = "affine", pl
+                if launched:
                     if count_slow:
                         self.last_slow_fraction = float(slow.item()) / (n_pix * len(w))
                     return image, index
-                if kernel == "affine":
-                    raise _lib.GxError(_lib.GX_ERR_UNSUPPORTED, "detector grid is not affine in (row, col)")
 
             if kernel in (None, "filtered"):
                 if on_device and len(shape) == 2:

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define GX_ABI_VERSION 1
+#define GX_ABI_VERSION 2
 
 #define GX_OK 0
 #define GX_ERR_INVALID (-1)     /* bad argument                              */
@@ -137,13 +137,16 @@ typedef struct gx_chord {
  *   d_base [n_phi][N] complex64 = num_missing[y]*avg_f - pedestal
  *                                 (or -pedestal when !fill_bkg)
  *   d_my, d_mz [n_phi][N] fp32  = Gaussian-smoothed box masks (smooth>0)
+ *   d_dmy [n_phi][N] float2     = (num_missing - max_voxels, my): the packed
+ *                                 form the fused row kernel reads (base =
+ *                                 dmy.x * avg_f); optional (NULL to skip)
  * h_gauss: host array of 2*radius+1 fp64 weights (scipy _gaussian_kernel1d).
  *                                                   (vg.py:344-379)        */
 int gx_slice_vectors(const gx_chord *d_chord, const int32_t *d_bbox, int n_phi, int N, double r,
                      double max_voxels, double avg_f_re, double avg_f_im,
                      double pedestal_re, double pedestal_im,
                      int fill_bkg, int smooth_sigma, const double *d_gauss, int gauss_radius,
-                     gx_float2 *d_base, float *d_my, float *d_mz, void *stream);
+                     gx_float2 *d_base, float *d_my, float *d_mz, gx_float2 *d_dmy, void *stream);
 
 /* ------------------------------------------------------ projection (K1)  */
 /* Scatter + background + edge blend for n_phi rotations; one CTA per
@@ -232,14 +235,14 @@ typedef struct gx_fused_args {
     const gx_float2 *d_table;
     const double *d_sin, *d_cos, *d_yrange;
     const int32_t *d_bbox;
-    const gx_float2 *d_base;
-    const float *d_my, *d_mz;
+    const gx_float2 *d_dmy;     /* gx_slice_vectors: (num_missing - max_voxels, my) */
+    const float *d_mz;
     const void *d_plan;
     const int32_t *d_col, *d_colrange, *d_row_index;
     gx_float2 *d_work;
     float *d_sum;
     uint32_t *d_count2;
-    double r, pedestal_re, pedestal_im;
+    double r, pedestal_re, pedestal_im, avg_f_re, avg_f_im;
     int32_t n_species, n_phi, N, KC, q_num, row_lo, row_hi, fill_bkg, smooth_sigma, pad;
 } gx_fused_args;
 int gx_slices_fused(const gx_fused_args *h_args, void *stream);
