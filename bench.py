@@ -340,17 +340,22 @@ def run_ours(args):
         roofline["slices_per_launch"] = per_launch
         roofline["algorithmic_bytes_per_launch"] = alg.get(top, 0.0) * per_launch
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(top)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(top)
             if tr:
                 roofline["traffic"] = tr["dram_bytes_per_slice"] * per_launch
                 roofline["traffic_source"] = tr["source"]
         except Exception:
             pass
         roofline["note"] = ("fused = slice_rows_fused + slice_cols_fused; algorithmic bytes are those of the scatter, "
-                            "2-D FFT and binning kernels they replace (SURVEY 8(d)); measured DRAM traffic is ~13x "
+                            "2-D FFT and binning kernels they replace (SURVEY 8(d)); measured DRAM traffic is ~19x "
                             "lower because the N x N grid and image never reach HBM")
     det_bytes = 4.0 * P * P
     det_ach = det_bytes * len(w) / world / (ms_b * 1e-3) / 1e9
+    det_traffic = None
+    try:
+        det_traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["detector_affine"]
+    except Exception:
+        pass
     line = {"metric": METRIC, "value": len(phis_all) / (ms_a * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_a + ms_b,
             "ms_per_step_stage_a": ms_a, "ms_per_step_stage_b": ms_b,
@@ -359,8 +364,12 @@ def run_ours(args):
             "detector": {"metric": "detector orientations/sec", "value": len(w) / (ms_b * 1e-3),
                          "unit": "orientations/s",
                          "roofline": {"bound": "hbm", "achieved": det_ach, "peak": peak, "unit": "GB/s",
-                                      "frac": det_ach / peak, "traffic": None,
-                                      "algorithmic_bytes_per_orientation": det_bytes}},
+                                      "frac": det_ach / peak,
+                                      "traffic": (det_traffic["dram_bytes_per_orientation"] * len(w_my)
+                                                  if det_traffic else None),
+                                      "algorithmic_bytes_per_orientation": det_bytes,
+                                      "note": "whole stage-B step (host model, gather kernel, mirror epilogue) per "
+                                              "rank; the gather kernel alone: profiles/r02_summary.md"}},
             "roofline": roofline, "clocks": clocks, "gpu_launches": launches}
     if e2e is not None:
         line["e2e"] = e2e
