@@ -151,7 +151,8 @@ def encode_elements_device(elements, device, max_species=_lib.GX_MAX_SPECIES):
     if A == 0 or elements.dtype.kind != "U" or elements.dtype.itemsize not in (4, 8):
         return None
     width = elements.dtype.itemsize // 4
-    cp = torch.from_numpy(np.ascontiguousarray(elements).view(np.uint32).view(np.int32)).to(device, non_blocking=True)
+    from . import parallel
+    cp = parallel.upload_replicated(np.ascontiguousarray(elements).view(np.uint32).view(np.int32), device)
     hist = torch.empty(16385, dtype=torch.int32, device=device)
     st = _stream()
     call("gx_species_histogram", ptr(cp), width, A, ptr(hist), st)
@@ -275,7 +276,8 @@ class AtomSet:
         self.N = int(grid_size)
         self.r = float(r_voxel_size)
         st = _stream()
-        d_coords = _dev(coords, device)
+        from . import parallel
+        d_coords = parallel.upload_replicated(coords, device)
         mm = torch.empty(6, dtype=torch.float64, device=device)
         call("gx_coords_minmax", ptr(d_coords), self.A, ptr(mm), st)
         self.minmax = mm.cpu().numpy()

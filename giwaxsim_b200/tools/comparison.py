@@ -9,6 +9,9 @@ and detector orientations (stage B) are sharded across ranks and the partial
 grids / images are combined with an all-reduce (NCCL over NVLink on GPUs), so
 every rank returns the full result.
 """
+import os
+import time
+
 import numpy as np
 import torch
 
@@ -19,6 +22,25 @@ from .utilities import ATOMIC_NUMBER, get_element_f1_f2_dict
 # device copy of the last voxel grid returned by voxelgridmaker_fitting, so a
 # following detectormaker_fitting(iq, ...) on the same array skips the upload
 _resident = {"host": None, "device": None}
+_TRACE = os.environ.get("GIWAXS_B200_TRACE", "0") == "1"
+
+
+class _Trace:
+    """GIWAXS_B200_TRACE=1: wall time of each phase of the two drivers (synchronising), rank 0 prints."""
+
+    def __init__(self, name):
+        self.name, self.t, self.laps = name, time.perf_counter(), []
+
+    def lap(self, what):
+        if _TRACE:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            self.laps.append("%s %.1f ms" % (what, 1e3 * (now - self.t)))
+            self.t = now
+
+    def done(self):
+        if _TRACE and parallel.rank_world()[0] == 0:
+            print("[trace] %s: %s" % (self.name, ", ".join(self.laps)), flush=True)
 
 
 def f_table(uniq, energy):
@@ -47,6 +69,7 @@ def voxelgridmaker_fitting(coords, elements, r_voxel_size, q_voxel_size, max_q, 
     the engine (parity probes).
     """
     dev = engine.resolve_device()
+    tr = _Trace("voxelgridmaker_fitting")
     coords = np.asarray(coords, dtype=np.float64)
     # grid size first (needed to sort atoms by pixel row); bounds come back from the device
     max_q_diag = np.sqrt(2) * max_q
@@ -55,6 +78,7 @@ def voxelgridmaker_fitting(coords, elements, r_voxel_size, q_voxel_size, max_q, 
     grid_size = int(np.ceil(2 * np.pi / (q_voxel_size * r_voxel_size)))
     with torch.cuda.device(dev):
         enc = engine.encode_elements_device(elements, dev)
+    tr.lap("species")
     if enc is not None:
         codes, uniq, counts = enc                    # coded on the device, counted there too
         table = f_table(uniq, energy)
@@ -70,6 +94,7 @@ def voxelgridmaker_fitting(coords, elements, r_voxel_size, q_voxel_size, max_q, 
             f_values = np.array([lut[str(e)] for e in elements], dtype=complex)
             atoms = engine.AtomSet(coords, r_voxel_size, grid_size, dev, f_values=f_values)
             sum_f = np.sum(f_values)
+    tr.lap("atoms upload+sort")
     x_bound, y_bound, z_bound = atoms.bounds
     grid_size, q_num, q_axis, ref_phis = engine.stage_a_geometry(atoms.bounds, r_voxel_size, q_voxel_size, max_q)
     if phis is None:
@@ -80,13 +105,19 @@ def voxelgridmaker_fitting(coords, elements, r_voxel_size, q_voxel_size, max_q, 
     eng = engine.SliceEngine(None, r_voxel_size, q_axis, grid_size, avg_voxel_f, x_bound, y_bound,
                              fill_bkg, smooth, device=dev, atoms=atoms, window=window)
     rank, world = parallel.rank_world()
+    tr.lap("engine")
     eng.run(parallel.shard(np.asarray(phis, dtype=np.float64), rank, world))
+    tr.lap("slices")
     if world > 1:
         parallel.all_reduce_sum([eng.vsum, eng.count2])
+    tr.lap("all-reduce")
     iq_dev, axis = engine.finalize_voxels(eng.vsum, None, eng.count2, eng.row_hist, q_axis, max_q, dev,
                                           window=window)
+    tr.lap("finalise")
     with torch.cuda.device(dev):
-        iq = engine.to_host_f64(iq_dev)                   # widen on the device, one pinned D2H copy
+        iq = engine.to_host_f64(iq_dev)                   # one DMA in fp32, widened on the host
+    tr.lap("result to host")
+    tr.done()
     _resident["host"], _resident["device"] = iq, iq_dev
     out = (iq, axis.copy(), axis.copy(), axis.copy())
     return out + (eng,) if return_state else out

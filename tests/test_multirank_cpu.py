@@ -35,6 +35,16 @@ def _worker(rank, world, port, coords, f, r, q, max_q, ret):
         t_sum = torch.from_numpy(vsum)
         t_cnt = torch.from_numpy(vcnt.astype(np.int32))
         parallel.all_reduce_sum([t_sum, None, t_cnt])
+        # replicated host array -> "device" copy, each rank contributing only its slice
+        old = parallel.SHARDED_UPLOAD_MIN_BYTES
+        parallel.SHARDED_UPLOAD_MIN_BYTES = 64
+        try:
+            for arr in (coords, np.arange(1001, dtype=np.int32), np.array(["C", "Si", "O"] * 37)):
+                src = arr if arr.dtype.kind != "U" else np.ascontiguousarray(arr).view(np.uint32).view(np.int32)
+                got = parallel.upload_replicated(src, torch.device("cpu"))
+                assert got.shape == src.shape and np.array_equal(got.numpy(), src)
+        finally:
+            parallel.SHARDED_UPLOAD_MIN_BYTES = old
         if rank == 0:
             ret["sum"], ret["cnt"], ret["n"] = t_sum.numpy().copy(), t_cnt.numpy().copy(), len(mine)
     finally:
