@@ -148,13 +148,24 @@ extern "C" int gx_bin_slices(const float *d_iq2d, int batch, int rows, int cols,
 // -------------------------------------------------------------- finalise ----
 struct Aff { double a[9]; double Z; };
 
+// exp(-b k (qx^2+qy^2+qz^2)) = e_b(qx) e_b(qy) e_b(qz): the four Gaussians of the Cromer-Mann sum are
+// tabulated per axis value (4 x V fp64 exps in shared memory) instead of evaluated per voxel
+// (4 x V^3 fp64 exps made this kernel compute-bound at 0.6 TB/s); products differ from the
+// reference's single exp by a few fp64 ulps, far below the fp32 result.
 __global__ void __launch_bounds__(256)
 voxel_finalize_kernel(const float *__restrict__ sum, const uint32_t *__restrict__ count3,
                       const uint32_t *__restrict__ count2, const uint32_t *__restrict__ m,
                       int q_num, int lo, int V, const double *__restrict__ axis, Aff aff, float *iq)
 {
-    const size_t n = (size_t)V * V * V;
+    extern __shared__ double s_e[];                 // [4][V]
     const double k = 1.0 / (16.0 * 3.14159265358979323846 * 3.14159265358979323846);
+    for (int t = threadIdx.x; t < 4 * V; t += blockDim.x) {
+        const int term = t / V, i = t - term * V;
+        const double q = axis[i + lo];
+        s_e[t] = exp(-aff.a[2 * term + 1] * (q * q) * k);
+    }
+    __syncthreads();
+    const size_t n = (size_t)V * V * V;
     for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (size_t)gridDim.x * blockDim.x) {
         const int iz = (int)(o % V), ix = (int)((o / V) % V), iy = (int)(o / ((size_t)V * V));
         const size_t yx = (size_t)(iy + lo) * q_num + (ix + lo);
@@ -162,10 +173,10 @@ voxel_finalize_kernel(const float *__restrict__ sum, const uint32_t *__restrict_
         const double cnt = count3 ? (double)count3[v] : (double)count2[yx] * (double)m[iz + lo];
         float out = 0.f;
         if (cnt != 0.0) {
-            const double qx = axis[ix + lo], qy = axis[iy + lo], qz = axis[iz + lo];
-            const double q2 = (qx * qx + qy * qy + qz * qz) * k;
-            double f = aff.a[0] * exp(-aff.a[1] * q2) + aff.a[2] * exp(-aff.a[3] * q2) +
-                       aff.a[4] * exp(-aff.a[5] * q2) + aff.a[6] * exp(-aff.a[7] * q2) + aff.a[8];
+            double f = aff.a[8];
+#pragma unroll
+            for (int term = 0; term < 4; ++term)
+                f += aff.a[2 * term] * (s_e[term * V + ix] * s_e[term * V + iy] * s_e[term * V + iz]);
             f /= aff.Z;
             out = (float)(((double)sum[v] / cnt) * f * f);
         }
@@ -187,8 +198,15 @@ extern "C" int gx_voxel_finalize(const float *d_sum, const uint32_t *d_count3, c
     const size_t n = (size_t)V * V * V;
     size_t blocks = (n + 255) / 256;
     if (blocks > (size_t)GX_SM_COUNT * 16) blocks = (size_t)GX_SM_COUNT * 16;
-    voxel_finalize_kernel<<<(int)blocks, 256, 0, gx_stream(stream)>>>(d_sum, d_count3, d_count2, d_m, q_num,
-                                                                     lo, V, d_axis, aff, d_iq);
+    const size_t smem = (size_t)4 * V * sizeof(double);
+    if (smem > 200 * 1024) {
+        gx_set_error("gx_voxel_finalize: cropped grid side %d too large", V);
+        return GX_ERR_UNSUPPORTED;
+    }
+    GX_CUDA(cudaFuncSetAttribute(voxel_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (blocks > (size_t)GX_SM_COUNT * 8) blocks = (size_t)GX_SM_COUNT * 8;
+    voxel_finalize_kernel<<<(int)blocks, 256, smem, gx_stream(stream)>>>(d_sum, d_count3, d_count2, d_m, q_num,
+                                                                        lo, V, d_axis, aff, d_iq);
     return gx_check_launch("gx_voxel_finalize");
 }
 

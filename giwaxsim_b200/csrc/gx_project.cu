@@ -42,9 +42,27 @@ __device__ __forceinline__ void py_slice(int a, int b, int n, int &lo, int &hi)
     lo = a; hi = max(a, b);
 }
 
-__device__ __forceinline__ float smoothed_box(int i, int lo, int hi, int n, const double *w, int radius)
+// gaussian_filter1d(mask, mode='wrap')[i] for mask = 1 on [lo,hi): the taps k in [-radius, radius]
+// with (i + k) mod n in [lo, hi).  cw[m] = w[0] + ... + w[m-1] (prefix sums, cw[0] = 0), so each of the
+// (at most three) images of the box under the wrap contributes one difference of prefix sums.
+__device__ __forceinline__ double box_taps(const double *cw, int radius, int a, int b)
 {
-    // gaussian_filter1d(mask, mode='wrap')[i] for mask = 1 on [lo,hi)
+    // taps k with a <= k < b, clipped to [-radius, radius]
+    a = max(a, -radius);
+    b = min(b, radius + 1);
+    return b > a ? cw[b + radius] - cw[a + radius] : 0.0;
+}
+
+__device__ __forceinline__ float smoothed_box(int i, int lo, int hi, int n, const double *w, const double *cw,
+                                              int radius)
+{
+    if (hi <= lo) return 0.f;
+    if (cw != NULL && 2 * radius + 1 <= n) {
+        double acc = box_taps(cw, radius, lo - i, hi - i);
+        acc += box_taps(cw, radius, lo - n - i, hi - n - i);
+        acc += box_taps(cw, radius, lo + n - i, hi + n - i);
+        return (float)acc;
+    }
     double acc = 0.0;
     for (int k = -radius; k <= radius; ++k) {
         int j = (i + k) % n;
@@ -60,6 +78,18 @@ slice_vectors_kernel(const gx_chord *__restrict__ chord, const int32_t *__restri
                      int fill_bkg, int sigma, const double *__restrict__ gauss, int radius,
                      float2 *base, float *my, float *mz, float2 *dmy)
 {
+    // prefix sums of the Gaussian taps (<= 2 * 4 * sigma + 2 entries), once per CTA
+    extern __shared__ double s_cw[];
+    const double *cw = NULL;
+    if (sigma > 0 && 2 * radius + 2 <= 4096) {
+        if (threadIdx.x == 0) {
+            double c = 0.0;
+            s_cw[0] = 0.0;
+            for (int t = 0; t <= 2 * radius; ++t) { c += gauss[t]; s_cw[t + 1] = c; }
+        }
+        __syncthreads();
+        cw = s_cw;
+    }
     const int p = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -85,9 +115,9 @@ slice_vectors_kernel(const gx_chord *__restrict__ chord, const int32_t *__restri
     if (sigma > 0) {
         int lo, hi;
         py_slice(y_min + sigma, y_max - sigma, N, lo, hi);
-        vy = smoothed_box(i, lo, hi, N, gauss, radius);
+        vy = smoothed_box(i, lo, hi, N, gauss, cw, radius);
         py_slice(z_min + sigma, z_max - sigma, N, lo, hi);
-        vz = smoothed_box(i, lo, hi, N, gauss, radius);
+        vz = smoothed_box(i, lo, hi, N, gauss, cw, radius);
     }
     if (fill_bkg) {
         // voxelgrids.py:358-361: rows < z_min or >= z_max and columns <= y_min or
@@ -110,7 +140,8 @@ extern "C" int gx_slice_vectors(const gx_chord *d_chord, const int32_t *d_bbox, 
     GX_REQUIRE(!fill_bkg || d_chord, "fill_bkg needs chord constants");
     GX_REQUIRE(smooth_sigma <= 0 || d_gauss, "smooth needs Gaussian weights");
     GX_REQUIRE(n_phi > 0 && N >= 16, "bad sizes");
-    slice_vectors_kernel<<<dim3((N + 255) / 256, n_phi), 256, 0, gx_stream(stream)>>>(
+    const size_t smem = smooth_sigma > 0 ? (size_t)(2 * gauss_radius + 2) * sizeof(double) : 0;
+    slice_vectors_kernel<<<dim3((N + 255) / 256, n_phi), 256, smem <= 32768 ? smem : 0, gx_stream(stream)>>>(
         d_chord, d_bbox, N, r, max_voxels, avg_f_re, avg_f_im, pedestal_re, pedestal_im, fill_bkg,
         smooth_sigma, d_gauss, gauss_radius, reinterpret_cast<float2 *>(d_base), d_my, d_mz,
         reinterpret_cast<float2 *>(d_dmy));
