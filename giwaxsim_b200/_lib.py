@@ -43,6 +43,13 @@ class FusedArgs(ctypes.Structure):
                                               "fill_bkg", "smooth_sigma", "pad")]
 
 
+class SlabArgs(ctypes.Structure):
+    """gx_slab_args (include/giwaxs_b200.h)."""
+    _fields_ = [("d_cell_xyz", ctypes.c_void_p), ("d_cell_species", ctypes.c_void_p), ("n_cell", ctypes.c_int64),
+                ("nx", ctypes.c_int32), ("ny", ctypes.c_int32), ("nz", ctypes.c_int32), ("pad", ctypes.c_int32)] + \
+               [(n, ctypes.c_double) for n in ("ax", "bx", "by", "cx", "cy", "cz")]
+
+
 _p = ctypes.c_void_p
 _i = ctypes.c_int
 _i64 = ctypes.c_int64
@@ -77,6 +84,10 @@ _PROTOTYPES = {
     "gx_slice_col_range": (_i, [_p, _i, _i, _p, _p]),
     "gx_window_indices": (_i, [_p, _i64, _i, _i, _i, _i, _p]),
     "gx_slices_fused": (_i, [_p, _p]),
+    "gx_slab_tiles": (_i64, [_p]),
+    "gx_slab_minmax": (_i, [_p, _p, _p]),
+    "gx_slab_count": (_i, [_p, _p, _p, _p, _p, _p, _p, _p]),
+    "gx_slab_write": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gx_rotate_points": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "gx_detector_accumulate": (_i, [_p, _i, _i, _i, _d, _d, _d, _d, _p, _p, _p, _i64, _p, _p, _i,
                                     _p, _i, _p, _p]),
@@ -95,7 +106,7 @@ _PROTOTYPES = {
 }
 
 _UNCHECKED = {"gx_abi_version", "gx_last_error", "gx_fft_plan_bytes", "gx_fast_record_bytes",
-              "gx_affine_record_bytes", "gx_affine_plan_doubles"}
+              "gx_affine_record_bytes", "gx_affine_plan_doubles", "gx_slab_tiles"}
 
 _cdll = None
 
@@ -132,7 +143,7 @@ _LAUNCHES = {
     "gx_axis_col_index": 1, "gx_axis_row_index": 1, "gx_bin_slices": 1, "gx_row_histogram": 1,
     "gx_voxel_finalize": 1, "gx_rotate_points": 1, "gx_detector_accumulate": 1, "gx_detector_epilogue": 1,
     "gx_detector_accumulate_fast": 1, "gx_detector_accumulate_affine": 1, "gx_grid_affine_fit": 1,
-    "gx_slices_fused": 2, "gx_species_histogram": 1, "gx_species_codes": 1, "gx_window_indices": 1, "gx_slice_col_range": 1, "gx_extreme_atoms": 1, "gx_hull_filter": 1,
+    "gx_slices_fused": 2, "gx_species_histogram": 1, "gx_species_codes": 1, "gx_window_indices": 1, "gx_slab_minmax": 3, "gx_slab_count": 3, "gx_slab_write": 1, "gx_slice_col_range": 1, "gx_extreme_atoms": 1, "gx_hull_filter": 1,
 }
 _launch_count = 0
 

@@ -172,6 +172,57 @@ def encode_elements_device(elements, device, max_species=_lib.GX_MAX_SPECIES):
 
 
 # ---------------------------------------------------------------------------
+# slab builder (next row N3)
+# ---------------------------------------------------------------------------
+def build_slab(cell_coords, cell_codes, sizes, vectors, device):
+    """Tile the unit cell and cut the centred slab on the device (comparison.py:605-671).
+    cell_coords [n,3] float64 host, cell_codes [n] uint8 host or None, sizes = (x, y, z) slab
+    edge lengths, vectors = (a, b, c) cell vectors.  Returns (coords [M,3] float64 device tensor,
+    codes [M] uint8 device tensor or None), atoms in the reference's order, coordinates
+    bit-identical to the reference's."""
+    a_vec, b_vec, c_vec = (np.asarray(v, dtype=np.float64) for v in vectors)
+    x_size, y_size, z_size = sizes
+    num = (int(np.ceil(2 * x_size / a_vec[0])), int(np.ceil(2 * y_size / b_vec[1])),
+           int(np.ceil(2 * z_size / c_vec[2])))                                   # comparison.py:608-610
+    if min(num) < 0:
+        raise ValueError("slab sizes and cell vectors must be positive")
+    cell = np.ascontiguousarray(cell_coords, dtype=np.float64)
+    st = _stream()
+    d_cell = _dev(cell, device)
+    d_codes = _dev(np.ascontiguousarray(cell_codes, dtype=np.uint8), device) if cell_codes is not None else None
+    args = _lib.SlabArgs()
+    args.d_cell_xyz, args.d_cell_species = d_cell.data_ptr(), (d_codes.data_ptr() if d_codes is not None else None)
+    args.n_cell = int(cell.shape[0])
+    args.nx, args.ny, args.nz = num[0] + 1, num[1] + 1, num[2] + 1
+    args.ax, args.bx, args.by = float(a_vec[0]), float(b_vec[0]), float(b_vec[1])
+    args.cx, args.cy, args.cz = float(c_vec[0]), float(c_vec[1]), float(c_vec[2])
+    ref = ctypes.byref(args)
+    mm = torch.empty(6, dtype=torch.float64, device=device)
+    call("gx_slab_minmax", ref, ptr(mm), st)
+    mm = mm.cpu().numpy()
+    mins = np.ascontiguousarray(mm[0::2])
+    ext = mm[1::2] - mm[0::2]                                                     # comparison.py:639-641
+    assert ext[0] > x_size, "x_max must be greater than x_size"
+    assert ext[1] > y_size, "y_max must be greater than y_size"
+    assert ext[2] > z_size, "z_max must be greater than z_size"
+    lo = np.ascontiguousarray((ext - np.array([x_size, y_size, z_size], dtype=np.float64)) / 2)
+    hi = np.ascontiguousarray(ext - lo)
+    tiles = int(_lib.cdll().gx_slab_tiles(ref))
+    offsets = torch.empty(tiles, dtype=torch.int64, device=device)
+    total = torch.empty(1, dtype=torch.int64, device=device)
+    kept_min = torch.empty(3, dtype=torch.float64, device=device)
+    call("gx_slab_count", ref, ptr(mins), ptr(lo), ptr(hi), ptr(offsets), ptr(total), ptr(kept_min), st)
+    M = int(total.item())
+    if M == 0:
+        raise ValueError("zero-size array to reduction operation minimum which has no identity")
+    kmin = np.ascontiguousarray(kept_min.cpu().numpy())
+    out = torch.empty((M, 3), dtype=torch.float64, device=device)
+    out_codes = torch.empty(M, dtype=torch.uint8, device=device) if d_codes is not None else None
+    call("gx_slab_write", ref, ptr(mins), ptr(lo), ptr(hi), ptr(kmin), ptr(offsets), ptr(out), ptr(out_codes), st)
+    return out, out_codes
+
+
+# ---------------------------------------------------------------------------
 # stage A
 # ---------------------------------------------------------------------------
 class FftPlan:
@@ -268,7 +319,10 @@ class AtomSet:
     """Device-resident slab: atoms sorted by z pixel row (phi-invariant)."""
 
     def __init__(self, coords, r_voxel_size, grid_size, device, species=None, table=None, f_values=None):
-        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        """coords: host [A,3] array, or a float64 device tensor (a slab built by build_slab)."""
+        on_device = isinstance(coords, torch.Tensor)
+        if not on_device:
+            coords = np.ascontiguousarray(coords, dtype=np.float64)
         if coords.ndim != 2 or coords.shape[1] != 3 or coords.shape[0] == 0:
             raise ValueError("coords must be a non-empty [A,3] array")
         self.device = device
@@ -277,7 +331,7 @@ class AtomSet:
         self.r = float(r_voxel_size)
         st = _stream()
         from . import parallel
-        d_coords = parallel.upload_replicated(coords, device)
+        d_coords = coords.contiguous() if on_device else parallel.upload_replicated(coords, device)
         mm = torch.empty(6, dtype=torch.float64, device=device)
         call("gx_coords_minmax", ptr(d_coords), self.A, ptr(mm), st)
         self.minmax = mm.cpu().numpy()

@@ -17,7 +17,7 @@ import torch
 
 from .. import engine, parallel
 from .detector import rotate_about_horizontal, rotate_about_normal, rotate_about_vertical
-from .utilities import ATOMIC_NUMBER, get_element_f1_f2_dict
+from .utilities import ATOMIC_NUMBER, calc_real_space_abc, get_element_f1_f2_dict, load_pdb, load_xyz
 
 # device copy of the last voxel grid returned by voxelgridmaker_fitting, so a
 # following detectormaker_fitting(iq, ...) on the same array skips the upload
@@ -59,6 +59,59 @@ def species_table(elements, energy):
     return codes, uniq, f_table(uniq, energy)
 
 
+# device copy of the last slab returned by slabmaker_fitting: a following
+# voxelgridmaker_fitting(coords, elements, ...) on the same arrays skips upload and species coding
+_slab = {"coords": None, "elements": None, "probe": None, "d_coords": None, "d_codes": None, "uniq": None,
+         "counts": None}
+
+
+def _slab_probe(coords):
+    """A few entries of the array: detects in-place edits between the two calls."""
+    flat = coords.reshape(-1)
+    idx = np.linspace(0, flat.size - 1, num=min(flat.size, 16)).astype(np.int64)
+    return flat[idx].copy()
+
+
+def slabmaker_fitting(input_filepath, x_size, y_size, z_size, a, b, c, alpha, beta, gamma):
+    """Tile the unit cell of an .xyz / .pdb file and cut a centred x_size x y_size x z_size
+    slab (comparison.py:595-671).  Returns (coords [M,3] float64, elements [M]) with the
+    reference's atom order and bit-identical coordinates; the slab also stays on the device
+    for the voxelgridmaker_fitting call that follows."""
+    low = input_filepath.lower()
+    if low.endswith('.xyz'):
+        cell, cell_el = load_xyz(input_filepath)
+    elif low.endswith('.pdb'):
+        cell, cell_el = load_pdb(input_filepath)
+    else:
+        raise Exception('Files must be a .pdb or .xyz file')
+    dev = engine.resolve_device()
+    vectors = calc_real_space_abc(a, b, c, alpha, beta, gamma)
+    uniq, codes = np.unique(cell_el, return_inverse=True)
+    if len(uniq) > 255:
+        raise ValueError("more than 255 distinct element symbols")
+    with torch.cuda.device(dev):
+        d_coords, d_codes = engine.build_slab(cell, codes.astype(np.uint8), (x_size, y_size, z_size), vectors, dev)
+        coords = engine.to_host_f64(d_coords)
+        h_codes = d_codes.cpu().numpy()
+    elements = uniq[h_codes]
+    counts = np.bincount(h_codes, minlength=len(uniq)).astype(np.int64)
+    _slab.update(coords=coords, elements=elements, probe=_slab_probe(coords), d_coords=d_coords, d_codes=d_codes,
+                 uniq=[u for u in uniq], counts=counts)
+    return coords, elements
+
+
+def _resident_slab(coords, elements, dev):
+    """(d_coords, d_codes, uniq, counts) when (coords, elements) are the arrays slabmaker_fitting
+    just returned, untouched and on this device; else None."""
+    if coords is not _slab["coords"] or elements is not _slab["elements"] or _slab["d_coords"] is None:
+        return None
+    if _slab["d_coords"].device != dev or not np.array_equal(_slab_probe(coords), _slab["probe"]):
+        return None
+    if len(_slab["uniq"]) > engine._lib.GX_MAX_SPECIES:
+        return None
+    return _slab["d_coords"], _slab["d_codes"], _slab["uniq"], _slab["counts"]
+
+
 def voxelgridmaker_fitting(coords, elements, r_voxel_size, q_voxel_size, max_q, energy, num_cpus=None,
                            fill_bkg=False, smooth=0, phis=None, return_state=False):
     """3-D I(q) voxel grid of a slab by the projection-slice method.
@@ -70,14 +123,18 @@ def voxelgridmaker_fitting(coords, elements, r_voxel_size, q_voxel_size, max_q, 
     """
     dev = engine.resolve_device()
     tr = _Trace("voxelgridmaker_fitting")
+    resident = _resident_slab(coords, elements, dev)
     coords = np.asarray(coords, dtype=np.float64)
     # grid size first (needed to sort atoms by pixel row); bounds come back from the device
     max_q_diag = np.sqrt(2) * max_q
     if max_q_diag > 2 * np.pi / r_voxel_size:
         raise Exception('Max_q is non-physical for given voxel size')
     grid_size = int(np.ceil(2 * np.pi / (q_voxel_size * r_voxel_size)))
-    with torch.cuda.device(dev):
-        enc = engine.encode_elements_device(elements, dev)
+    if resident is not None:
+        coords, enc = resident[0], resident[1:]           # device slab from slabmaker_fitting
+    else:
+        with torch.cuda.device(dev):
+            enc = engine.encode_elements_device(elements, dev)
     tr.lap("species")
     if enc is not None:
         codes, uniq, counts = enc                    # coded on the device, counted there too

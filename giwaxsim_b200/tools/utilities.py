@@ -138,3 +138,57 @@ def lookup_shared_array(name):
         return _registry[name]
     except KeyError:
         raise FileNotFoundError("no device shared array named %r" % (name,)) from None
+
+
+# ---------------------------------------------------------------------------
+# structure files and cell vectors (inputs of slabmaker_fitting)
+# ---------------------------------------------------------------------------
+def _symbol(token):
+    """Element symbol of an .xyz first column: digits removed (utilities.py:52-55 use)."""
+    return "".join(ch for ch in token if not ch.isdigit())
+
+
+def load_xyz(xyz_path):
+    """(coords [n,3] float64, elements [n]) of an XYZ file: two header lines, then
+    `symbol x y z ...` per atom; malformed lines are skipped (utilities.py:97-132)."""
+    coords, symbols = [], []
+    with open(xyz_path, "r") as fh:
+        body = fh.readlines()[2:]
+    for line in body:
+        parts = line.split()
+        if len(parts) < 4:
+            continue
+        try:
+            xyz = [float(parts[1]), float(parts[2]), float(parts[3])]
+        except ValueError:
+            continue
+        symbols.append(_symbol(parts[0]))
+        coords.append(xyz)
+    return np.array(coords), np.array(symbols)
+
+
+def load_pdb(pdb_path):
+    """(coords, elements) of the ATOM / HETATM records of a PDB file: fixed columns
+    31-54 for x, y, z and 77-78 for the element (utilities.py:134-161)."""
+    coords, symbols = [], []
+    with open(pdb_path, "r") as fh:
+        for line in fh:
+            if line.startswith(("ATOM", "HETATM")):
+                symbols.append(line[76:78].strip())
+                coords.append([float(line[30:38]), float(line[38:46]), float(line[46:54])])
+    return np.array(coords), np.array(symbols)
+
+
+def calc_real_space_abc(a_mag, b_mag, c_mag, alpha_deg, beta_deg, gamma_deg):
+    """Cell vectors a (along x), b (in the xy plane), c from lengths and angles
+    (utilities.py:276-301); the same NumPy expressions, so the components are
+    bit-identical to the reference's."""
+    alpha, beta, gamma = np.deg2rad(alpha_deg), np.deg2rad(beta_deg), np.deg2rad(gamma_deg)
+    V = a_mag * b_mag * c_mag * np.sqrt(1 - np.cos(alpha) ** 2 - np.cos(beta) ** 2 - np.cos(gamma) ** 2
+                                        + 2 * np.cos(alpha) * np.cos(beta) * np.cos(gamma))
+    a = np.array([a_mag, 0, 0])
+    b = np.array([b_mag * np.cos(gamma), b_mag * np.sin(gamma), 0])
+    c = np.array([c_mag * np.cos(beta),
+                  c_mag * (np.cos(alpha) - np.cos(beta) * np.cos(gamma)) / (np.sin(gamma)),
+                  V / (a_mag * b_mag * np.sin(gamma))])
+    return a, b, c

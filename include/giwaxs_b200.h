@@ -254,6 +254,34 @@ int gx_slices_fused(const gx_fused_args *h_args, void *stream);
  * (gx_axis_row_index).  In place.                                           */
 int gx_window_indices(int32_t *d_index, int64_t n, int q_num, int lo, int hi, int packed, void *stream);
 
+/* ------------------------------------------------- slab builder (next row N3) */
+/* slabmaker_fitting on the device (comparison.py:605-671): replicas of the unit
+ * cell  x = ((x0 + ax*i) + bx*j) + cx*k,  y = (y0 + by*j) + cy*k,  z = z0 + cz*k
+ * for i < nx, j < ny, k < nz (nx = num_x + 1, ...), every product and sum rounded
+ * in fp64 like NumPy; atom order k, j, i, atom.  The replicated array is never
+ * stored; the three passes recompute it.
+ *  gx_slab_minmax : d_out6 = {xmin,xmax,ymin,ymax,zmin,zmax} over all replicas
+ *  gx_slab_count  : with p = x - min (h_min3) keep h_lo3 <= p <= h_hi3 on all
+ *                   axes; d_tile_count [gx_slab_tiles()] receives the EXCLUSIVE
+ *                   prefix of the kept atoms per tile of 1024 replica atoms,
+ *                   *d_total their number, d_kept_min3 the minimum p of the kept
+ *  gx_slab_write  : kept atoms in reference order: d_xyz_out [M][3] = p -
+ *                   h_kept_min3, d_species_out [M] = species of the source atom  */
+typedef struct gx_slab_args {
+    const double *d_cell_xyz;      /* [n_cell][3] unit-cell coordinates      */
+    const uint8_t *d_cell_species; /* [n_cell] or NULL                        */
+    int64_t n_cell;
+    int32_t nx, ny, nz, pad;
+    double ax, bx, by, cx, cy, cz;
+} gx_slab_args;
+int64_t gx_slab_tiles(const gx_slab_args *h_args);
+int gx_slab_minmax(const gx_slab_args *h_args, double *d_out6, void *stream);
+int gx_slab_count(const gx_slab_args *h_args, const double *h_min3, const double *h_lo3, const double *h_hi3,
+                  int64_t *d_tile_count, int64_t *d_total, double *d_kept_min3, void *stream);
+int gx_slab_write(const gx_slab_args *h_args, const double *h_min3, const double *h_lo3, const double *h_hi3,
+                  const double *h_kept_min3, const int64_t *d_tile_offset, double *d_xyz_out,
+                  uint8_t *d_species_out, void *stream);
+
 /* --------------------------------------------------------- detector (K4) */
 /* p <- R p for n points, R row-major 3x3, fma chain k=0,1,2.
  *                                                  (detector.py:71,113,155) */

@@ -310,3 +310,67 @@ def test_T8_pm6_default_config_end_to_end(golden):
     gold = golden("pm6_det_sum_ref.npy")
     assert np.abs(quad - gold).max() <= 0.02 * gold.max()
     assert np.corrcoef(np.log(quad).ravel(), np.log(gold).ravel())[0, 1] > 0.9999
+
+
+def _write_cell_files(tmp_path):
+    """A small triclinic-capable unit cell as .xyz and .pdb (same atoms)."""
+    rng = np.random.default_rng(8)
+    n = 37
+    xyz = np.round(rng.random((n, 3)) * [6.1, 7.3, 5.2], 3)
+    el = rng.choice(np.array(["C", "H", "S", "O", "Si"]), size=n)
+    px, pp = str(tmp_path / "cell.xyz"), str(tmp_path / "cell.pdb")
+    with open(px, "w") as fh:
+        fh.write("%d\ncomment line\n" % n)
+        for e, p in zip(el, xyz):
+            fh.write("%s1 %.3f %.3f %.3f\n" % (e, p[0], p[1], p[2]))
+        fh.write("bad line\n")
+    with open(pp, "w") as fh:
+        fh.write("CRYST1    6.100    7.300    5.200  90.00  90.00  90.00 P 1           1\n")
+        for i, (e, p) in enumerate(zip(el, xyz)):
+            fh.write("ATOM  %5d  %-3s MOL A   1    %8.3f%8.3f%8.3f  1.00  0.00          %2s\n"
+                     % (i + 1, e, p[0], p[1], p[2], e))
+        fh.write("END\n")
+    return px, pp
+
+
+@pytest.mark.parametrize("cell", [(6.1, 7.3, 5.2, 90.0, 90.0, 90.0), (6.1, 7.3, 5.2, 82.0, 96.0, 107.0)])
+@pytest.mark.parametrize("kind", ["xyz", "pdb"])
+def test_slabmaker_fitting_bit_exact_and_resident_handoff(tmp_path, cell, kind):
+    """Next row N3: the device slab builder returns the reference's array (order and every
+    bit of every coordinate), and the slab it leaves on the device gives the same voxel grid
+    as re-uploading the returned arrays."""
+    px, pp = _write_cell_files(tmp_path)
+    path = px if kind == "xyz" else pp
+    size = (33.0, 41.0, 28.0)
+    c0, e0 = ox.read_structure(path)
+    o_coords, o_el = ox.slabmaker(c0, e0, *size, *cell)
+    coords, el = comparison.slabmaker_fitting(path, *size, *cell)
+    assert coords.dtype == np.float64 and coords.shape == o_coords.shape
+    assert np.array_equal(coords, o_coords) and np.array_equal(el, o_el)
+    previous = utilities._f1f2_provider
+    utilities.set_f1f2_provider(lambda e, en=None: (0.01 * len(e), 0.002))
+    try:
+        r, q, max_q = 0.3, 0.1, 1.5
+        a = comparison.voxelgridmaker_fitting(coords, el, r, q, max_q, 12700.0, fill_bkg=True, smooth=2)
+        b = comparison.voxelgridmaker_fitting(coords.copy(), el.copy(), r, q, max_q, 12700.0, fill_bkg=True, smooth=2)
+        assert np.abs(a[0] - b[0]).max() <= 1e-6 * b[0].max() and np.array_equal(a[0] == 0, b[0] == 0)
+        f = ox.f_values_for(el, table=lambda e, en=None: (0.01 * len(e), 0.002))
+        o_iq = ox.voxelgridmaker(o_coords, f, r, q, max_q, True, 2)[0]
+        assert np.abs(a[0] - o_iq).max() <= TOL_INT * o_iq.max()
+        # an in-place edit of the returned array must not be served from the stale device copy
+        coords2, el2 = comparison.slabmaker_fitting(path, *size, *cell)
+        coords2 *= 1.01
+        c = comparison.voxelgridmaker_fitting(coords2, el2, r, q, max_q, 12700.0, fill_bkg=True, smooth=2)
+        d = comparison.voxelgridmaker_fitting(coords2.copy(), el2.copy(), r, q, max_q, 12700.0, fill_bkg=True, smooth=2)
+        assert c[0].shape == d[0].shape and np.abs(c[0] - d[0]).max() <= 1e-6 * d[0].max()
+    finally:
+        utilities.set_f1f2_provider(previous)
+
+
+def test_slabmaker_fitting_errors(tmp_path):
+    px, _ = _write_cell_files(tmp_path)
+    with pytest.raises(Exception, match="must be a .pdb or .xyz"):
+        comparison.slabmaker_fitting(str(tmp_path / "cell.cif"), 10, 10, 10, 6.1, 7.3, 5.2, 90, 90, 90)
+    # a slab size of zero keeps only the exact mid-plane: nothing survives -> the reference's np.min error
+    with pytest.raises(ValueError, match="zero-size array"):
+        comparison.slabmaker_fitting(px, 1e-9, 1e-9, 1e-9, 6.1, 7.3, 5.2, 90, 90, 90)

@@ -154,3 +154,21 @@ def test_fft_pass_address_identity(fft_emul):
     """gx_phys(base + S*n) == gx_phys(base) + gx_phys(S*n) for every butterfly of every
     pass of every schedule (the kernels rely on it for immediate-offset addressing)."""
     assert fft_emul.emul_offsets_ok() == 1
+
+
+def test_structure_loaders_and_cell_vectors_match_oracle(tmp_path):
+    from giwaxsim_b200.tools import utilities
+    xyz = tmp_path / "m.xyz"
+    xyz.write_text("3\ncomment\nC1 0.0 1.5 2.25\nSi12 -1.0 2.0 3.0 extra\nbroken line\nH 1e-3 2 x\nO 4 5 6\n")
+    pdb = tmp_path / "m.pdb"
+    pdb.write_text("HEADER\n"
+                   "ATOM      1  C1  MOL A   1      11.104   6.134  -6.504  1.00  0.00           C\n"
+                   "HETATM    2 CL   MOL A   1       1.000  -2.000   3.500  1.00  0.00          CL\n"
+                   "TER\nEND\n")
+    for path, fn in ((str(xyz), utilities.load_xyz), (str(pdb), utilities.load_pdb)):
+        c, e = fn(path)
+        oc, oe = ox.read_structure(path)
+        assert np.array_equal(c, oc) and np.array_equal(e, oe) and len(e) > 0
+    for cell in [(4.0, 5.0, 6.0, 90.0, 90.0, 90.0), (2.456, 4.254, 6.696, 90.0, 90.0, 120.0), (7.0, 8.0, 9.0, 75.0, 85.0, 95.0)]:
+        for u, v in zip(utilities.calc_real_space_abc(*cell), ox.cell_vectors(*cell)):
+            assert np.array_equal(u, v)

@@ -60,3 +60,21 @@ def test_stage_b_bit_exact(P, vals, axs, mirror):
     a = ref_shim.detectormaker_serial(iq, q, q, q, P, 2.0, vals, axs, psis, w[0], phis, w[1], thetas, w[2], mirror=mirror)
     b = ox.detectormaker(iq, q, q, q, P, 2.0, vals, axs, psis, w[0], phis, w[1], thetas, w[2], mirror=mirror)
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("name,size,cell", [
+    ("PM6_sample.pdb", (60.0, 50.0, 45.0), (44.456, 45.726, 40.097, 90.0, 90.0, 90.0)),
+    ("graphite_medium.xyz", (20.0, 30.0, 25.0), (14.0, 21.0, 15.0, 90.0, 90.0, 90.0)),
+    ("graphite_medium.xyz", (18.0, 22.0, 16.0), (14.0, 21.0, 15.0, 80.0, 95.0, 110.0)),     # triclinic cell
+])
+def test_slabmaker_bit_exact(name, size, cell):
+    import os
+    ref = ref_shim.load()
+    path = os.path.join(ref_shim.REFERENCE_ROOT, "test_input_files", name)
+    r_coords, r_el = ref.comparison.slabmaker_fitting(path, *size, *cell)
+    c0, e0 = ox.read_structure(path)
+    loader = ref.utilities.load_pdb if name.endswith(".pdb") else ref.utilities.load_xyz
+    rc0, re0 = loader(path)
+    assert np.array_equal(c0, rc0) and np.array_equal(e0, re0)
+    o_coords, o_el = ox.slabmaker(c0, e0, *size, *cell)
+    assert np.array_equal(o_coords, r_coords) and np.array_equal(o_el, r_el)
