@@ -1,0 +1,109 @@
+"""BASELINE configs[4] sizes (N = 4096 real-space grid, q_num = 569, 2048^2 detector) through
+size-independent properties: at these sizes the CPU oracle needs seconds per slice, so the
+checks are internal identities of the path plus the oracle on a single slice / a few pixels."""
+import numpy as np
+import pytest
+import torch
+
+from giwaxsim_b200 import engine, synth
+from giwaxsim_b200.tools import comparison
+from oracle import giwaxs_oracle as ox
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def slab5():
+    cfg = synth.config5()
+    coords, el = synth.random_slab(1_500_000, cfg["box"], seed=11)       # config-5 box, 15 % of its atoms
+    dev = engine.resolve_device()
+    codes, uniq, counts = engine.encode_elements_device(el, dev)
+    table = comparison.f_table(uniq, cfg["energy"])
+    r, q, max_q = cfg["r_voxel_size"], cfg["q_voxel_size"], cfg["max_q"]
+    atoms = engine.AtomSet(coords, r, cfg["grid_size"], dev, species=codes, table=table)
+    N, q_num, q_axis, phis = engine.stage_a_geometry(atoms.bounds, r, q, max_q)
+    assert (N, q_num) == (4096, 569)
+    avg = np.sum(counts * np.asarray(table)) / np.prod(atoms.bounds) * r ** 3
+    return dict(cfg=cfg, coords=coords, el=el, atoms=atoms, table=table, uniq=uniq, q_axis=q_axis, phis=phis,
+                avg=avg, r=r, q=q, max_q=max_q, N=N)
+
+
+def _engine(s, window=None, count3d=False):
+    a = s["atoms"]
+    return engine.SliceEngine(None, s["r"], s["q_axis"], s["N"], s["avg"], a.bounds[0], a.bounds[1], True, 25,
+                              atoms=a, window=window, count3d=count3d)
+
+
+def test_full_size_fused_equals_staged_and_window_equals_crop(slab5):
+    s = slab5
+    sel = s["phis"][[0, 1, 400, 891, 1337, 1782]]
+    lo, hi = engine.crop_range(s["q_axis"], s["max_q"])
+    full = _engine(s)
+    full.run(sel)                                   # fused, full q_num^3 accumulators
+    win = _engine(s, window=(lo, hi))
+    win.run(sel)                                    # fused, crop window only
+    staged = _engine(s)
+    staged.run(sel, staged=True)                    # project -> fft2 -> bin kernels
+    c_full, s_full = full.counts(), full.sums().astype(np.float64)
+    assert np.array_equal(win.counts(), c_full[lo:hi, lo:hi, lo:hi])                  # bit-exact
+    top = s_full.max()
+    assert np.abs(win.sums() - s_full[lo:hi, lo:hi, lo:hi]).max() <= 2e-6 * top
+    assert np.array_equal(staged.counts(), c_full)
+    assert np.abs(staged.sums() - s_full).max() <= 1e-5 * top
+    # every kept (row, col) sample of every slice is counted exactly once
+    kept_rows = int((full.row_index >= 0).sum())
+    t = full.prepare(sel)
+    kept_cols = int((t["col"] >= 0).sum())
+    assert int(c_full.sum()) == kept_rows * kept_cols
+
+
+def test_full_size_single_slice_against_oracle(slab5):
+    """One N = 4096 slice of the 1.5 M-atom slab: atom pixel indices and voxel counts bit-exact,
+    accumulated intensities within 1e-4 of the maximum."""
+    s = slab5
+    phi = float(s["phis"][777])
+    e = _engine(s)
+    y_idx, z_idx, bbox = e.atom_indices(phi)
+    oy, oz, _valid = ox.atom_pixel_indices(s["coords"], phi, s["N"], s["r"])[:3]
+    assert np.array_equal(y_idx, oy) and np.array_equal(z_idx, oz)
+    e.run(np.array([phi]))
+    f = ox.f_values_for(s["el"], table=synth.fixed_f1f2)
+    setup = ox.stage_a_setup(s["coords"], f, s["r"], s["q"], s["max_q"])
+    q3 = (setup["q_num"],) * 3
+    vsum, vcnt = np.zeros(q3), np.zeros(q3)
+    ox.run_slice(vsum, vcnt, s["coords"], setup, s["r"], phi, True, 25)
+    assert np.array_equal(e.counts(), vcnt.astype(np.int64))
+    assert np.abs(e.sums() - vsum).max() <= 1e-4 * vsum.max()
+
+
+def test_full_size_detector_kernels_agree(slab5):
+    """2048^2 detector, bench geometry: the fixed-point kernel's voxel index equals the all-fp64
+    kernel's for every pixel of the probed orientations, and the oracle's on a sample of pixels."""
+    cfg = slab5["cfg"]
+    rng = np.random.default_rng(3)
+    V = 403
+    q = np.linspace(-2.01, 2.01, V)
+    iq = rng.random((V, V, V)).astype(np.float32)
+    dev = engine.resolve_device()
+    P = 2048
+    gx, gy, gz, _, _ = comparison.detector_base_device(P, 2.0, cfg["angle_init_vals"], cfg["angle_init_axs"], dev)
+    psis = np.linspace(0, 89.75, 360)
+    for phis, thetas in (([0.0], [0.0]), ([11.0], [0.7])):
+        R, w = engine.orientation_tables(engine.grid_corners(gx, gy, gz), psis, np.ones(360) / 360, phis, np.ones(1),
+                                         thetas, np.ones(1))
+        det = engine.DetectorEngine(iq, q, q, q)
+        a, _ = det.accumulate(gx, gy, gz, R, w, kernel="exact")
+        b, _ = det.accumulate(gx, gy, gz, R, w, kernel="affine", count_slow=True)
+        assert float((a - b).abs().max()) <= 2e-6 * float(a.abs().max())
+        assert det.last_slow_fraction < 1e-3
+        for o in (0, 1, 47, 48, 179, 359):                  # both sides of the 48-orientation first chunk
+            _, ia = det.accumulate(gx, gy, gz, R, w, probe=o, kernel="exact")
+            _, ib = det.accumulate(gx, gy, gz, R, w, probe=o, kernel="affine")
+            assert torch.equal(ia, ib), o
+    # oracle on a strided sample of pixels of one tilted orientation
+    hx, hy, hz, _, _ = ox.detector_base(P, 2.0, cfg["angle_init_vals"], cfg["angle_init_axs"])
+    g = ox.rotate_psi_phi_theta(hx, hy, hz, psis[179], 11.0, 0.7)
+    ix, iy, iz = ox.detector_voxel_indices((V, V, V), q, q, q, *g)
+    flat = ((iy * V + ix) * V + iz).reshape(P, P)
+    _, ib = det.accumulate(gx, gy, gz, R, w, probe=179, kernel="affine")
+    assert np.array_equal(ib.cpu().numpy().reshape(P, P)[::7, ::5], flat[::7, ::5])
