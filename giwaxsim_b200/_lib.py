@@ -40,7 +40,8 @@ class FusedArgs(ctypes.Structure):
                  "d_work", "d_sum", "d_count2")] + \
                [(n, ctypes.c_double) for n in ("r", "pedestal_re", "pedestal_im", "avg_f_re", "avg_f_im")] + \
                [(n, ctypes.c_int32) for n in ("n_species", "n_phi", "N", "KC", "q_num", "row_lo", "row_hi",
-                                              "fill_bkg", "smooth_sigma", "pad")]
+                                              "fill_bkg", "smooth_sigma", "pad")] + \
+               [("table", ctypes.c_float * (2 * GX_MAX_SPECIES))]
 
 
 class SlabArgs(ctypes.Structure):

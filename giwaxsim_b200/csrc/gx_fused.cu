@@ -31,6 +31,8 @@ struct FusedArgs {
     ProjArgs proj;
     const float2 *dmy;         // [n_phi][N] (num_missing - max_voxels, my): base = dmy.x * avg_f
     float af_re, af_im;
+    float2 ftab[GX_MAX_SPECIES];   // species f-values in the parameter (constant) bank: FFMA operands
+                                   // straight from c[][] cost neither registers nor shared-memory loads
     GxFftLayout lay;
     const float2 *plan;
     const int32_t *col;        // [n_phi][N] packed iy*q_num+ix or -1
@@ -56,12 +58,69 @@ __device__ __forceinline__ void active_band(const ProjArgs &a, int p, int &za, i
 }
 
 // ------------------------------------------------------------------ F1 ----
+// Single-chunk rows (<= 65535 atoms, i.e. always except for huge crystalline rows): the pixels of
+// this thread's first butterfly are produced in one go from the species counters,
+//     v = (sum_w n0 f0 + n1 f1 + d * avg_f) * mz * my,
+// pixel-outer / plane-inner so that every counter load is independent of every other (the
+// plane-outer accumulation into px serialised on the LDS latency and spilled px under the
+// 64-register cap).  px arrives holding the prefetched (d, my) of each pixel and leaves holding v.
+// NPAIR > 0: number of counter planes known at compile time (f-values in registers);
+// NPAIR == 0: any number of planes, f-values re-read from shared memory.
+template <int NPAIR, int NB0, int R0, int S0, int NT>
+__device__ __forceinline__ void flush_finish(float2 (&px)[NB0][R0], const uint32_t *words, int NP,
+                                             const float2 *s_table, const float2 (&f)[GX_MAX_SPECIES], int npair,
+                                             int tid, int N, float af_re, float af_im, float mzv)
+{
+#pragma unroll
+    for (int i = 0; i < NB0; ++i) {
+        const int t = tid + i * NT;
+        if (t >= S0) {
+#pragma unroll
+            for (int n = 0; n < R0; ++n) px[i][n] = make_float2(0.f, 0.f);
+            continue;
+        }
+        // no branch per pixel (a pixel beyond N reads a clamped address and is zeroed by a select):
+        // the R0 x NPAIR counter loads are then free to be issued back to back
+#pragma unroll
+        for (int n = 0; n < R0; ++n) {
+            const int y = t + S0 * n;
+            const int yy = min(y, N - 1);
+            float sx = 0.f, sy = 0.f;
+            if (NPAIR > 0) {
+#pragma unroll
+                for (int w = 0; w < NPAIR; ++w) {
+                    // counts -> fp32 through the 2^23 mantissa trick (LOP/PRMT + FADD, no I2F)
+                    const uint32_t cnt = words[w * NP + yy];
+                    const float n0 = __uint_as_float(0x4B000000u | (cnt & 0xffffu)) - 8388608.f;
+                    const float n1 = __uint_as_float(__byte_perm(cnt, 0x4B000000u, 0x7632)) - 8388608.f;
+                    sx = fmaf(n1, f[2 * w + 1].x, fmaf(n0, f[2 * w].x, sx));
+                    sy = fmaf(n1, f[2 * w + 1].y, fmaf(n0, f[2 * w].y, sy));
+                }
+            } else {
+                for (int w = 0; w < npair; ++w) {
+                    const uint32_t cnt = words[w * NP + yy];
+                    const float2 f0 = s_table[2 * w], f1 = s_table[2 * w + 1];
+                    const float n0 = __uint_as_float(0x4B000000u | (cnt & 0xffffu)) - 8388608.f;
+                    const float n1 = __uint_as_float(__byte_perm(cnt, 0x4B000000u, 0x7632)) - 8388608.f;
+                    sx = fmaf(n1, f1.x, fmaf(n0, f0.x, sx));
+                    sy = fmaf(n1, f1.y, fmaf(n0, f0.y, sy));
+                }
+            }
+            const float2 dm = px[i][n];
+            const float m = (y < N) ? mzv * dm.y : 0.f;
+            px[i][n] = make_float2(fmaf(dm.x, af_re, sx) * m, fmaf(dm.x, af_im, sy) * m);
+        }
+    }
+}
+
 // Pixel ownership follows the first FFT pass: butterfly t of pass 0 combines the
 // pixels t + S0*n (n < R0), so the thread that runs butterfly t also gathers the
 // species counts of exactly those pixels, completes them in registers and feeds
 // them straight into its radix-R0 butterfly: the finished row is never written
 // to shared memory in natural order and never read back by pass 0.
-template <int L, bool SPECIES, bool BLUE>
+// NPAIR: number of species-counter planes fixed at compile time (1..3; the flush is then fully
+// unrolled with the f-values as constant-bank operands), 0 = any number (generic loop).
+template <int L, bool SPECIES, bool BLUE, int NPAIR>
 __global__ void __launch_bounds__(PROJ_THREADS, (L >= 13) ? 2 : GX_F1_MINBLOCKS)
 slice_rows_fused(FusedArgs fa)
 {
@@ -92,11 +151,9 @@ slice_rows_fused(FusedArgs fa)
     if (jhi <= jlo) return;
 
     const int NP = (N + 3) & ~3;                           // counter plane stride (words)
+    const float2 *dmy = fa.dmy + (size_t)p * N;
     float2 px[NB0][R0];
-#pragma unroll
-    for (int i = 0; i < NB0; ++i)
-#pragma unroll
-        for (int n = 0; n < R0; ++n) px[i][n] = make_float2(0.f, 0.f);
+    bool finished = false;                                 // px already holds the completed pixels
 
     if (SPECIES) {
         if (tid < GX_MAX_SPECIES) s_table[tid] = tid < a.n_species ? a.table[tid] : make_float2(0.f, 0.f);
@@ -104,37 +161,57 @@ slice_rows_fused(FusedArgs fa)
         uint4 *words4 = reinterpret_cast<uint4 *>(smem_raw);
         for (int y = tid; y < npair * (NP / 4); y += NT) words4[y] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
-        // 16-bit counters: rows with more than 65535 atoms are counted in chunks
-        for (int c0 = beg; c0 < end; c0 += 65535) {
-            const int c1 = min(c0 + 65535, end);
-            scatter_species(a, c0, c1, s, c, shift, words, NP);
+        if (end - beg <= 65535) {
+            // 16-bit counters cannot wrap: one scatter, one flush
+            scatter_species(a, beg, end, s, c, shift, words, NP);
+            // (d, my) of this thread's pixels, requested before the barrier so that the L2 round
+            // trip overlaps the wait for the slowest warp
+#pragma unroll
+            for (int i = 0; i < NB0; ++i)
+#pragma unroll
+                for (int n = 0; n < R0; ++n) {
+                    const int t = tid + i * NT, y = t + S0 * n;
+                    px[i][n] = __ldg(dmy + min(y, N - 1));            // clamped: pixels beyond N are zeroed later
+                }
             __syncthreads();
-            const bool more = c1 < end;
-            for (int w = 0; w < npair; ++w) {
-                const float2 f0 = s_table[2 * w], f1 = s_table[2 * w + 1];
-                uint32_t *plane = words + w * NP;
+            flush_finish<NPAIR, NB0, R0, S0, NT>(px, words, NP, s_table, fa.ftab, npair, tid, N, fa.af_re, fa.af_im, mzv);
+            __syncthreads();   // every counter read is done before buf is written
+            finished = true;
+        } else {
 #pragma unroll
-                for (int i = 0; i < NB0; ++i) {
-                    const int t = tid + i * NT;
+            for (int i = 0; i < NB0; ++i)
 #pragma unroll
-                    for (int n = 0; n < R0; ++n) {
-                        const int y = t + S0 * n;
-                        if (t < S0 && y < N) {
-                            // branch-free: most warps see a non-empty pixel anyway.  Counts go to
-                            // fp32 through the 2^23 mantissa trick (LOP/PRMT + FADD, no I2F)
-                            const uint32_t cnt = plane[y];
-                            const float n0 = __uint_as_float(0x4B000000u | (cnt & 0xffffu)) - 8388608.f;
-                            const float n1 = __uint_as_float(__byte_perm(cnt, 0x4B000000u, 0x7632)) - 8388608.f;
-                            px[i][n].x = fmaf(n1, f1.x, fmaf(n0, f0.x, px[i][n].x));
-                            px[i][n].y = fmaf(n1, f1.y, fmaf(n0, f0.y, px[i][n].y));
+                for (int n = 0; n < R0; ++n) px[i][n] = make_float2(0.f, 0.f);
+            // rows with more than 65535 atoms are counted in chunks
+            for (int c0 = beg; c0 < end; c0 += 65535) {
+                const int c1 = min(c0 + 65535, end);
+                scatter_species(a, c0, c1, s, c, shift, words, NP);
+                __syncthreads();
+                const bool more = c1 < end;
+                for (int w = 0; w < npair; ++w) {
+                    const float2 f0 = s_table[2 * w], f1 = s_table[2 * w + 1];
+                    uint32_t *plane = words + w * NP;
+#pragma unroll
+                    for (int i = 0; i < NB0; ++i) {
+                        const int t = tid + i * NT;
+#pragma unroll
+                        for (int n = 0; n < R0; ++n) {
+                            const int y = t + S0 * n;
+                            if (t < S0 && y < N) {
+                                const uint32_t cnt = plane[y];
+                                const float n0 = __uint_as_float(0x4B000000u | (cnt & 0xffffu)) - 8388608.f;
+                                const float n1 = __uint_as_float(__byte_perm(cnt, 0x4B000000u, 0x7632)) - 8388608.f;
+                                px[i][n].x = fmaf(n1, f1.x, fmaf(n0, f0.x, px[i][n].x));
+                                px[i][n].y = fmaf(n1, f1.y, fmaf(n0, f0.y, px[i][n].y));
+                            }
                         }
                     }
                 }
-            }
-            __syncthreads();   // every counter read is done before the next chunk / before buf is written
-            if (more) {
-                for (int y = tid; y < npair * (NP / 4); y += NT) words4[y] = make_uint4(0u, 0u, 0u, 0u);
-                __syncthreads();
+                __syncthreads();   // every counter read is done before the next chunk / before buf is written
+                if (more) {
+                    for (int y = tid; y < npair * (NP / 4); y += NT) words4[y] = make_uint4(0u, 0u, 0u, 0u);
+                    __syncthreads();
+                }
             }
         }
     } else {
@@ -164,28 +241,35 @@ slice_rows_fused(FusedArgs fa)
 
     // complete the pixels (pedestal-free) in registers and run the first pass on them:
     // (atoms + d * avg_f) * mz * my with (d, my) packed in one 8-byte load per pixel
-    const float2 *dmy = fa.dmy + (size_t)p * N;
     const float2 *tw0 = fa.plan + fa.lay.tw_off[0];
 #pragma unroll
     for (int i = 0; i < NB0; ++i) {
         const int t = tid + i * NT;
         if (t < S0) {
-            float2 dm[R0];
+            if (!finished) {
+                float2 dm[R0];
 #pragma unroll
-            for (int n = 0; n < R0; ++n) {
-                const int y = t + S0 * n;
-                dm[n] = (y < N) ? __ldg(dmy + y) : make_float2(0.f, 0.f);
-            }
-#pragma unroll
-            for (int n = 0; n < R0; ++n) {
-                const int y = t + S0 * n;
-                float2 v = make_float2(0.f, 0.f);
-                if (y < N) {
-                    const float m = mzv * dm[n].y;
-                    v = make_float2(fmaf(dm[n].x, fa.af_re, px[i][n].x) * m, fmaf(dm[n].x, fa.af_im, px[i][n].y) * m);
-                    if (BLUE) v = gx_cmul(v, fa.plan[fa.lay.chirp_off + y]);
+                for (int n = 0; n < R0; ++n) {
+                    const int y = t + S0 * n;
+                    dm[n] = (y < N) ? __ldg(dmy + y) : make_float2(0.f, 0.f);
                 }
-                px[i][n] = v;
+#pragma unroll
+                for (int n = 0; n < R0; ++n) {
+                    const int y = t + S0 * n;
+                    float2 v = make_float2(0.f, 0.f);
+                    if (y < N) {
+                        const float m = mzv * dm[n].y;
+                        v = make_float2(fmaf(dm[n].x, fa.af_re, px[i][n].x) * m, fmaf(dm[n].x, fa.af_im, px[i][n].y) * m);
+                    }
+                    px[i][n] = v;
+                }
+            }
+            if (BLUE) {
+#pragma unroll
+                for (int n = 0; n < R0; ++n) {
+                    const int y = t + S0 * n;
+                    if (y < N) px[i][n] = gx_cmul(px[i][n], fa.plan[fa.lay.chirp_off + y]);
+                }
             }
             gx_fft_pass0_from_regs<L>(px[i], buf, tw0, t);
         }
@@ -304,16 +388,27 @@ static int launch_fused(const FusedArgs &fa, bool species, cudaStream_t st)
         return GX_ERR_UNSUPPORTED;
     }
     const dim3 grid1(fa.n_phi, N);
-#define GX_LAUNCH_ROWS(SP, BL)                                                                              \
+#define GX_LAUNCH_ROWS(SP, BL, NPR)                                                                         \
     do {                                                                                                    \
-        GX_CUDA(cudaFuncSetAttribute(slice_rows_fused<L, SP, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        GX_CUDA(cudaFuncSetAttribute(slice_rows_fused<L, SP, BL, NPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)smem1));                                                          \
-        slice_rows_fused<L, SP, BL><<<grid1, PROJ_THREADS, smem1, st>>>(fa);                               \
+        slice_rows_fused<L, SP, BL, NPR><<<grid1, PROJ_THREADS, smem1, st>>>(fa);                          \
     } while (0)
-    if (species && blue) GX_LAUNCH_ROWS(true, true);
-    else if (species) GX_LAUNCH_ROWS(true, false);
-    else if (blue) GX_LAUNCH_ROWS(false, true);
-    else GX_LAUNCH_ROWS(false, false);
+    // compile-time plane counts only for the large transforms (L >= 10), where F1 dominates the run
+    const int npair = (fa.proj.n_species + 1) / 2;
+    const int npr = (species && L >= 10 && npair >= 1 && npair <= 3) ? npair : 0;
+    if (species && blue) {
+        if (L >= 10 && npr == 1) GX_LAUNCH_ROWS(true, true, (L >= 10 ? 1 : 0));
+        else if (L >= 10 && npr == 2) GX_LAUNCH_ROWS(true, true, (L >= 10 ? 2 : 0));
+        else if (L >= 10 && npr == 3) GX_LAUNCH_ROWS(true, true, (L >= 10 ? 3 : 0));
+        else GX_LAUNCH_ROWS(true, true, 0);
+    } else if (species) {
+        if (L >= 10 && npr == 1) GX_LAUNCH_ROWS(true, false, (L >= 10 ? 1 : 0));
+        else if (L >= 10 && npr == 2) GX_LAUNCH_ROWS(true, false, (L >= 10 ? 2 : 0));
+        else if (L >= 10 && npr == 3) GX_LAUNCH_ROWS(true, false, (L >= 10 ? 3 : 0));
+        else GX_LAUNCH_ROWS(true, false, 0);
+    } else if (blue) GX_LAUNCH_ROWS(false, true, 0);
+    else GX_LAUNCH_ROWS(false, false, 0);
 #undef GX_LAUNCH_ROWS
     if (int e = gx_check_launch("slice_rows_fused")) return e;
     int nt = TC * M / 16;
@@ -349,6 +444,8 @@ extern "C" int gx_slices_fused(const gx_fused_args *h, void *stream)
     a.base = NULL; a.my = NULL; a.mz = h->d_mz;
     fa.dmy = reinterpret_cast<const float2 *>(h->d_dmy);
     fa.af_re = (float)h->avg_f_re; fa.af_im = (float)h->avg_f_im;
+    for (int k = 0; k < GX_MAX_SPECIES; ++k)
+        fa.ftab[k] = k < h->n_species ? make_float2(h->table[k].x, h->table[k].y) : make_float2(0.f, 0.f);
     a.N = h->N; a.r = h->r; a.ped_re = (float)h->pedestal_re; a.ped_im = (float)h->pedestal_im;
     a.fill_bkg = h->fill_bkg; a.sigma = h->smooth_sigma;
     fa.lay = gx_fft_layout(h->N);

@@ -343,7 +343,8 @@ class AtomSet:
             self.n_species = len(table)
             d_species = species if isinstance(species, torch.Tensor) else _dev(species, device)
             self.species = torch.empty(self.A, dtype=torch.uint8, device=device)
-            self.table = _dev(np.asarray(table, dtype=np.complex128).astype(np.complex64).view(np.float32), device)
+            self.table_host = np.asarray(table, dtype=np.complex128).astype(np.complex64).view(np.float32).copy()
+            self.table = _dev(self.table_host, device)
         else:
             d_f = _dev(np.asarray(f_values, dtype=np.complex128).astype(np.complex64).view(np.float32), device)
             self.f = torch.empty(2 * self.A, dtype=torch.float32, device=device)
@@ -590,6 +591,9 @@ class SliceEngine:
         args.r = self.r
         args.pedestal_re, args.pedestal_im = self.pedestal.real, self.pedestal.imag
         args.avg_f_re, args.avg_f_im = self.avg_voxel_f.real, self.avg_voxel_f.imag
+        if a.n_species:
+            for k, v in enumerate(a.table_host):
+                args.table[k] = float(v)
         args.n_species, args.n_phi, args.N, args.KC, args.q_num = a.n_species, n, self.N, self.KC, self.q_out
         args.row_lo, args.row_hi = self.row_lo, self.row_hi
         args.fill_bkg, args.smooth_sigma = int(self.fill_bkg), self.sigma

@@ -244,6 +244,7 @@ typedef struct gx_fused_args {
     uint32_t *d_count2;
     double r, pedestal_re, pedestal_im, avg_f_re, avg_f_im;
     int32_t n_species, n_phi, N, KC, q_num, row_lo, row_hi, fill_bkg, smooth_sigma, pad;
+    gx_float2 table[GX_MAX_SPECIES];   /* host copy of d_table (kernel-parameter operands) */
 } gx_fused_args;
 int gx_slices_fused(const gx_fused_args *h_args, void *stream);
 
