@@ -23,6 +23,9 @@
 #include "gx_project.cuh"
 #include "gx_fft_engine.cuh"
 
+#ifndef GX_F2_TC12
+#define GX_F2_TC12 4        // columns per F2 CTA at N = 4096 (2 -> 3 CTAs/SM was measured: 1 % slower)
+#endif
 #ifndef GX_F1_MINBLOCKS
 #define GX_F1_MINBLOCKS 4   // CTAs/SM the row kernel is compiled for (3 would leave ~84 KB of L1: measured no faster)
 #endif
@@ -156,13 +159,15 @@ slice_rows_fused(FusedArgs fa)
     bool finished = false;                                 // px already holds the completed pixels
 
     if (SPECIES) {
+        const bool single = end - beg <= 65535;            // 16-bit counters cannot wrap: one scatter, one flush
         if (tid < GX_MAX_SPECIES) s_table[tid] = tid < a.n_species ? a.table[tid] : make_float2(0.f, 0.f);
         const int npair = (a.n_species + 1) >> 1;
         uint4 *words4 = reinterpret_cast<uint4 *>(smem_raw);
         for (int y = tid; y < npair * (NP / 4); y += NT) words4[y] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
-        if (end - beg <= 65535) {
-            // 16-bit counters cannot wrap: one scatter, one flush
+        if (single) {
+            // (hand-pipelining the atom loads across the zeroing barrier and across batches was
+            // measured: no gain, the kernel is bound by instruction issue, not by load latency)
             scatter_species(a, beg, end, s, c, shift, words, NP);
             // (d, my) of this thread's pixels, requested before the barrier so that the L2 round
             // trip overlaps the wait for the slowest warp
@@ -471,7 +476,7 @@ extern "C" int gx_slices_fused(const gx_fused_args *h, void *stream)
     case 9: return launch_fused<9, 8>(fa, species, st);
     case 10: return launch_fused<10, 8>(fa, species, st);
     case 11: return launch_fused<11, 8>(fa, species, st);
-    case 12: return launch_fused<12, 4>(fa, species, st);
+    case 12: return launch_fused<12, GX_F2_TC12>(fa, species, st);
     case 13: return launch_fused<13, 2>(fa, species, st);
     }
     gx_set_error("gx_slices_fused: unsupported log2 size %d", fa.lay.L);

@@ -45,34 +45,54 @@ __device__ __forceinline__ double atom_y_pixel(double x, double y, double s, dou
     return gx_floordiv(__dsub_rn(gx_rot_y(x, y, s, c), shift), r, inv_r);
 }
 
+// y pixel as an integer: floor-divide with the +-1 fix-up applied to the converted integer
+// (same value as atom_y_pixel; saturates for absurdly distant atoms, which then fail `< N`)
+__device__ __forceinline__ int atom_y_pixel_int(double x, double y, double s, double c, double shift,
+                                                double r, double inv_r)
+{
+    const double a = __dsub_rn(gx_rot_y(x, y, s, c), shift);
+    const double q = floor(__dmul_rn(a, inv_r));
+    const double rem = __fma_rn(-q, r, a);
+    int qi = __double2int_rz(q);
+    qi += (rem >= r) ? 1 : 0;
+    qi -= (rem < 0.0) ? 1 : 0;
+    return qi;
+}
+
 // Count atoms [beg,end) of one z-row into the species counters: word plane
-// sp>>1 (stride NP words), 16-bit field sp&1.  Loads are issued four atoms
-// ahead of their use so that several L2 round trips overlap per thread.
+// sp>>1 (stride NP words), 16-bit field sp&1.  Four atoms per thread and
+// iteration, loads first, and NO branch around an atom: the tail of the row
+// re-reads its last atom (clamped index) and only the final ATOMS is predicated,
+// so the four ~10-deep fp64 dependency chains interleave instead of running one
+// after the other.
 __device__ __forceinline__ void scatter_species(const ProjArgs &a, int beg, int end, double s, double c,
                                                 double shift, uint32_t *words, int NP)
 {
     const int N = a.N, tid = threadIdx.x, nt = blockDim.x;
     const double r = a.r, inv_r = 1.0 / a.r;
     constexpr int U = 4;
+    const int last = end - 1;
     for (int i0 = beg + tid; i0 < end; i0 += U * nt) {
         double x[U], y[U];
         unsigned sp[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * nt;
-            if (i < end) {
-                x[u] = ld_stream_f64(a.xs + i);
-                y[u] = ld_stream_f64(a.ys + i);
-                sp[u] = ld_stream_u8(a.species + i);
-            }
+            const int i = min(i0 + u * nt, last);
+            x[u] = ld_stream_f64(a.xs + i);
+            y[u] = ld_stream_f64(a.ys + i);
+            sp[u] = ld_stream_u8(a.species + i);
         }
+        int q[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) q[u] = atom_y_pixel_int(x[u], y[u], s, c, shift, r, inv_r);
+        // no branch here either: an atom that does not count (row tail, pixel outside the grid)
+        // adds 0 to word 0
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * nt;
-            if (i < end) {
-                const double q = atom_y_pixel(x[u], y[u], s, c, shift, r, inv_r);
-                if (q < (double)N) atomicAdd(&words[(sp[u] >> 1) * NP + (int)q], 1u << ((sp[u] & 1u) * 16));
-            }
+            const bool ok = (i0 + u * nt < end) && ((unsigned)q[u] < (unsigned)N);
+            const unsigned word = ok ? (sp[u] >> 1) * NP + q[u] : 0u;
+            const unsigned inc = ok ? 1u << ((sp[u] & 1u) * 16) : 0u;
+            atomicAdd(&words[word], inc);
         }
     }
 }
