@@ -165,22 +165,28 @@ voxel_finalize_kernel(const float *__restrict__ sum, const uint32_t *__restrict_
         s_e[t] = exp(-aff.a[2 * term + 1] * (q * q) * k);
     }
     __syncthreads();
-    const size_t n = (size_t)V * V * V;
-    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (size_t)gridDim.x * blockDim.x) {
-        const int iz = (int)(o % V), ix = (int)((o / V) % V), iy = (int)(o / ((size_t)V * V));
+    // one (iy, ix) column of V voxels per loop trip: no 64-bit divisions per voxel, contiguous iz
+    const int columns = V * V;
+    for (int col = blockIdx.x; col < columns; col += gridDim.x) {
+        const int iy = col / V, ix = col - iy * V;
         const size_t yx = (size_t)(iy + lo) * q_num + (ix + lo);
-        const size_t v = yx * q_num + (iz + lo);
-        const double cnt = count3 ? (double)count3[v] : (double)count2[yx] * (double)m[iz + lo];
-        float out = 0.f;
-        if (cnt != 0.0) {
-            double f = aff.a[8];
+        const double cyx = count3 ? 0.0 : (double)count2[yx];
+        double exy[4];
 #pragma unroll
-            for (int term = 0; term < 4; ++term)
-                f += aff.a[2 * term] * (s_e[term * V + ix] * s_e[term * V + iy] * s_e[term * V + iz]);
-            f /= aff.Z;
-            out = (float)(((double)sum[v] / cnt) * f * f);
+        for (int term = 0; term < 4; ++term) exy[term] = s_e[term * V + ix] * s_e[term * V + iy];
+        for (int iz = threadIdx.x; iz < V; iz += blockDim.x) {
+            const size_t v = yx * q_num + (iz + lo);
+            const double cnt = count3 ? (double)count3[v] : cyx * (double)m[iz + lo];
+            float out = 0.f;
+            if (cnt != 0.0) {
+                double f = aff.a[8];
+#pragma unroll
+                for (int term = 0; term < 4; ++term) f += aff.a[2 * term] * (exy[term] * s_e[term * V + iz]);
+                f /= aff.Z;
+                out = (float)(((double)sum[v] / cnt) * f * f);
+            }
+            iq[(size_t)col * V + iz] = out;
         }
-        iq[o] = out;
     }
 }
 
