@@ -275,7 +275,8 @@ def run_ours(args):
         ones = lambda a: None
         ta = tb = 0.0
         n_e2e = max(1, min(args.steps, 2))
-        for it in range(1 + n_e2e):                                # first pass is warm-up
+        n_warm = 2          # steady state: pinned staging, FFT plans and the result segments exist after two calls
+        for it in range(n_warm + n_e2e):
             barrier()
             t0 = time.perf_counter()
             iq, qx, qy, qz = comparison.voxelgridmaker_fitting(coords, elements, r, q, max_q, cfg["energy"],
@@ -288,7 +289,7 @@ def run_ours(args):
                                                              cfg["thetas"], None, mirror=True)
             barrier()
             t2 = time.perf_counter()
-            if it > 0:
+            if it >= n_warm:
                 ta += t1 - t0
                 tb += t2 - t1
         tt = torch.tensor([ta / n_e2e, tb / n_e2e], dtype=torch.float64, device=dev)

@@ -70,15 +70,22 @@ def _pinned_staging(nbytes):
     return buf
 
 
-def to_host_f64(t):
-    """Device tensor -> fresh float64 NumPy array: one DMA of the tensor in its own dtype (fp32
-    voxel grids cross PCIe at half the bytes) into the persistent pinned buffer, then a
-    multi-threaded widening copy on the host."""
+def to_host_f64(t, out=None, replicated=False):
+    """Device tensor -> float64 NumPy array: one DMA of the tensor in its own dtype (fp32 voxel
+    grids cross PCIe at half the bytes) into the persistent pinned buffer, then a multi-threaded
+    widening copy on the host into a fresh array (or into `out`, a float64 NumPy view).
+    replicated=True: every rank holds the same tensor (after an all-reduce) -> the conversion is
+    shared between the ranks of the node (parallel.shared_result_f64)."""
     t = t.contiguous()
+    if replicated and out is None:
+        from . import parallel
+        shared = parallel.shared_result_f64(t, lambda dev_slice, view: to_host_f64(dev_slice, out=view))
+        if shared is not None:
+            return shared
     nbytes = t.numel() * t.element_size()
     stage = _pinned_staging(nbytes)[:nbytes].view(t.dtype).view(t.shape)
     stage.copy_(t, non_blocking=True)
-    out = torch.empty(t.shape, dtype=torch.float64)
+    out = torch.empty(t.shape, dtype=torch.float64) if out is None else torch.from_numpy(out).view(t.shape)
     torch.cuda.current_stream().synchronize()
     # torchrun pins OMP_NUM_THREADS=1; the widening copy of a large grid is worth a few host
     # threads per rank (never more than the cores this rank can fairly claim)

@@ -60,3 +60,116 @@ def upload_replicated(array, device, group=None):
         out = full[:n]
     torch_dtype = torch.from_numpy(np.empty(0, dtype=a.dtype)).dtype
     return out.view(torch_dtype).view(a.shape)
+
+
+# ---------------------------------------------------------------------------
+# result to host, once per node instead of once per rank
+# ---------------------------------------------------------------------------
+import mmap as _mmap
+import os as _os
+import weakref as _weakref
+
+_POOL_MAX = 3
+_pool = []            # segments: {"nbytes", "fd", "w" (MAP_SHARED mapping), "live" (weakref to the array handed out)}
+_pool_serial = [0]
+
+
+def _all_local(group=None):
+    try:
+        return int(_os.environ.get("LOCAL_WORLD_SIZE", "0")) == dist.get_world_size(group)
+    except Exception:
+        return False
+
+
+def _segment_free(seg):
+    return seg["live"] is None or seg["live"]() is None
+
+
+def _close_segment(seg):
+    try:
+        seg["w"].close()
+        _os.close(seg["fd"])
+    except (OSError, ValueError, BufferError):
+        pass
+
+
+def _new_segment(nbytes, rank, device, group):
+    """A POSIX shared-memory file of nbytes opened by every rank, already unlinked (it lives as long
+    as some rank keeps its descriptor or a mapping).  None on every rank if it cannot be created."""
+    _pool_serial[0] += 1
+    name = "/dev/shm/giwaxs_b200_%s_%d" % (_os.environ.get("MASTER_PORT", "0"), _pool_serial[0])
+    ok = torch.ones(1, dtype=torch.int32, device=device)
+    fd = -1
+    if rank == 0:
+        try:
+            st = _os.statvfs("/dev/shm")
+            if st.f_bavail * st.f_frsize < nbytes + (64 << 20):
+                raise OSError("not enough /dev/shm")
+            fd = _os.open(name, _os.O_CREAT | _os.O_TRUNC | _os.O_RDWR, 0o600)
+            _os.ftruncate(fd, nbytes)
+        except OSError:
+            ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)         # also the "file exists" barrier
+    if int(ok.item()) == 0:
+        if fd >= 0:
+            _os.close(fd)
+            _os.unlink(name)
+        return None
+    if rank != 0:
+        fd = _os.open(name, _os.O_RDWR)
+    dist.barrier(group=group)                                      # every rank holds a descriptor
+    if rank == 0:
+        _os.unlink(name)
+    w = _mmap.mmap(fd, nbytes, flags=_mmap.MAP_SHARED, prot=_mmap.PROT_READ | _mmap.PROT_WRITE)
+    return {"nbytes": nbytes, "fd": fd, "w": w, "live": None}
+
+
+def shared_result_f64(t, to_host_slice, group=None, min_bytes=32 << 20):
+    """float64 NumPy copy of tensor `t`, which every rank holds identically after an all-reduce.
+    One process per GPU on one node would otherwise pay the device->host copy and the fp32->fp64
+    widening of the whole grid once PER RANK on the same host cores and memory bus.  Here rank r
+    converts only slab r of the flattened tensor into a POSIX shared-memory segment
+    (`to_host_slice(dev_slice, out_f64_view)` does the copy) and every rank maps the finished segment
+    copy-on-write: each caller still owns a private, writable array (a write touches only its own
+    pages), but the bytes are produced once per node.  Segments come from a small pool and are reused
+    only when EVERY rank's previous array on that segment has been garbage collected (first touch of
+    fresh tmpfs pages costs more than the conversion itself).  Returns None - the caller converts on
+    its own - for a single rank, small tensors, ranks spread over several nodes, a /dev/shm that is too
+    small, or when all pool segments are still referenced."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = t.numel()
+    nbytes = n * 8
+    if world == 1 or nbytes < min_bytes or not _all_local(group):
+        return None
+    # agree on a segment: free on every rank (the pool evolves in lockstep, so indices match)
+    flags = torch.zeros(_POOL_MAX, dtype=torch.int32, device=t.device)
+    for i, seg in enumerate(_pool):
+        flags[i] = 1 if _segment_free(seg) else 0
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN, group=group)
+    free = [i for i in range(len(_pool)) if int(flags[i]) == 1]
+    same = [i for i in free if _pool[i]["nbytes"] == nbytes]
+    if same:
+        seg = _pool[same[0]]
+    else:
+        if len(_pool) >= _POOL_MAX:
+            if not free:
+                return None
+            _close_segment(_pool.pop(free[0]))                    # a free segment of another size makes room
+        seg = _new_segment(nbytes, rank, t.device, group)
+        if seg is None:
+            return None
+        _pool.append(seg)
+    flat = t.reshape(-1)
+    per = (n + world - 1) // world
+    lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+    if hi > lo:
+        out = np.frombuffer(seg["w"], dtype=np.float64)
+        to_host_slice(flat[lo:hi], out[lo:hi])
+        del out
+    dist.barrier(group=group)                                      # every slab is written
+    m = _mmap.mmap(seg["fd"], nbytes, flags=_mmap.MAP_PRIVATE, prot=_mmap.PROT_READ | _mmap.PROT_WRITE)
+    base = np.frombuffer(m, dtype=np.float64)
+    seg["live"] = _weakref.ref(base)                               # views of the result keep `base` alive
+    return base.reshape(tuple(t.shape))

@@ -172,7 +172,7 @@ def voxelgridmaker_fitting(coords, elements, r_voxel_size, q_voxel_size, max_q, 
                                           window=window)
     tr.lap("finalise")
     with torch.cuda.device(dev):
-        iq = engine.to_host_f64(iq_dev)                   # one DMA in fp32, widened on the host
+        iq = engine.to_host_f64(iq_dev, replicated=world > 1)   # one DMA in fp32, widened on the host
     tr.lap("result to host")
     tr.done()
     _resident["host"], _resident["device"] = iq, iq_dev
@@ -220,7 +220,9 @@ def detectormaker_fitting(iq, qx, qy, qz, num_pixels, max_q, angle_init_vals, an
     """2-D detector image summed over psi x phi x theta orientations.
     Returns (det_sum[v,h], det_h, det_v) as float64 arrays."""
     dev = engine.resolve_device()
+    tr = _Trace("detectormaker_fitting")
     gx, gy, gz, det_h, det_v = detector_base_device(num_pixels, max_q, angle_init_vals, angle_init_axs, dev)
+    tr.lap("base grids")
 
     psi_weights = np.load(psi_weights_path) if psi_weights_path else np.ones_like(psis) / len(psis)
     phi_weights = np.load(phi_weights_path) if phi_weights_path else np.ones_like(phis) / len(phis)
@@ -235,16 +237,23 @@ def detectormaker_fitting(iq, qx, qy, qz, num_pixels, max_q, angle_init_vals, an
     grid = _resident["device"] if (iq is _resident["host"] and _resident["device"] is not None
                                    and _resident["device"].device == dev) else iq
     det = engine.DetectorEngine(grid, qx, qy, qz, device=dev)
+    tr.lap("voxel grid")
     R, w = engine.orientation_tables(engine.grid_corners(gx, gy, gz), psis, psi_weights, phis, phi_weights,
                                      thetas, theta_weights)
+    tr.lap("orientation tables")
     rank, world = parallel.rank_world()
     sel = parallel.shard(np.arange(len(w)), rank, world)
     with torch.cuda.device(dev):
         image = torch.zeros(num_pixels * num_pixels, dtype=torch.float64, device=dev)
     if len(sel):
         det.accumulate(gx, gy, gz, np.ascontiguousarray(R[sel]), np.ascontiguousarray(w[sel]), image=image)
+    tr.lap("gather")
     if world > 1:
         parallel.all_reduce_sum([image])
     out = engine.detector_epilogue(image, num_pixels, num_pixels, mirror, dev, finish=True)
+    tr.lap("all-reduce + epilogue")
     with torch.cuda.device(dev):
-        return engine.to_host_f64(out), det_h.copy(), det_v.copy()
+        res = engine.to_host_f64(out, replicated=world > 1)
+    tr.lap("result to host")
+    tr.done()
+    return res, det_h.copy(), det_v.copy()

@@ -45,6 +45,41 @@ def _worker(rank, world, port, coords, f, r, q, max_q, ret):
                 assert got.shape == src.shape and np.array_equal(got.numpy(), src)
         finally:
             parallel.SHARDED_UPLOAD_MIN_BYTES = old
+        # replicated result -> one float64 host copy per node, mapped copy-on-write by every rank
+        os.environ["LOCAL_WORLD_SIZE"] = str(world)
+        grid = torch.arange(5 * 7 * 3, dtype=torch.float32).reshape(5, 7, 3) * 0.5
+
+        def widen(dev_slice, view):
+            view[:] = dev_slice.numpy().astype(np.float64)
+
+        shared = parallel.shared_result_f64(grid, widen, min_bytes=0)
+        assert shared is not None and shared.dtype == np.float64 and shared.shape == (5, 7, 3)
+        assert np.array_equal(shared, grid.numpy().astype(np.float64))
+        shared[rank, 0, 0] = -1.0 - rank                       # private pages: the other rank must not see this
+        dist.barrier()
+        assert shared[1 - rank, 0, 0] == grid[1 - rank, 0, 0].item()
+        assert not [f for f in os.listdir("/dev/shm") if f.startswith("giwaxs_b200_%d_" % port)]
+        # pool: a segment is reused only when every rank dropped its array; live arrays never change
+        second = parallel.shared_result_f64(grid * 3, widen, min_bytes=0)       # `shared` alive -> new segment
+        assert len(parallel._pool) == 2 and np.array_equal(second, 3 * grid.numpy().astype(np.float64))
+        keep = shared[2:4]                                                  # a view keeps its segment busy
+        del shared
+        third = parallel.shared_result_f64(grid * 5, widen, min_bytes=0)
+        assert len(parallel._pool) == 3 and keep[0, 1, 1] == grid[2, 1, 1].item()
+        del keep, second
+        import gc
+        gc.collect()
+        fourth = parallel.shared_result_f64(grid * 7, widen, min_bytes=0)       # segments 0 and 1 are free again
+        assert len(parallel._pool) == 3 and np.array_equal(fourth, 7 * grid.numpy().astype(np.float64))
+        assert np.array_equal(third, 5 * grid.numpy().astype(np.float64))
+        if rank == 1:
+            hold = parallel.shared_result_f64(grid, widen, min_bytes=0)         # (kept alive on rank 1 only)
+        else:
+            parallel.shared_result_f64(grid, widen, min_bytes=0)
+        fifth = parallel.shared_result_f64(grid * 9, widen, min_bytes=0)        # all three segments busy somewhere
+        assert fifth is None
+        os.environ["LOCAL_WORLD_SIZE"] = "1"                   # ranks "on different nodes": caller converts itself
+        assert parallel.shared_result_f64(grid, widen, min_bytes=0) is None
         if rank == 0:
             ret["sum"], ret["cnt"], ret["n"] = t_sum.numpy().copy(), t_cnt.numpy().copy(), len(mine)
     finally:
