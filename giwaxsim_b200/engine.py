@@ -70,6 +70,35 @@ def _pinned_staging(nbytes):
     return buf
 
 
+_host_pool = []        # [{"buf": flat float64 CPU tensor, "live": weakref to the array handed out}]
+_HOST_POOL_MAX = 2
+_HOST_POOL_MIN_BYTES = 128 << 20      # detector images (tens of MB) are not worth pooling
+
+
+def _result_buffer(shape):
+    """float64 CPU tensor for a result.  Large results come from a two-entry pool of buffers whose
+    pages are already faulted in (first touch of a fresh 0.5 GB array costs more than filling it);
+    a buffer is reused only once the array previously handed out on it - and every view of it - has
+    been garbage collected, so arrays a caller still holds never change."""
+    import weakref
+    n = int(np.prod(shape))
+    if n * 8 < _HOST_POOL_MIN_BYTES:
+        return torch.empty(shape, dtype=torch.float64), None
+    for e in _host_pool:
+        if e["buf"].numel() == n and (e["live"] is None or e["live"]() is None):
+            return e["buf"].view(shape), e
+    if len(_host_pool) >= _HOST_POOL_MAX:
+        for i, e in enumerate(_host_pool):
+            if e["live"] is None or e["live"]() is None:
+                _host_pool.pop(i)                       # a free buffer of another size makes room
+                break
+        else:
+            return torch.empty(shape, dtype=torch.float64), None
+    e = {"buf": torch.empty(n, dtype=torch.float64), "live": None}
+    _host_pool.append(e)
+    return e["buf"].view(shape), e
+
+
 def to_host_f64(t, out=None, replicated=False):
     """Device tensor -> float64 NumPy array: one DMA of the tensor in its own dtype (fp32 voxel
     grids cross PCIe at half the bytes) into the persistent pinned buffer, then a multi-threaded
@@ -85,7 +114,11 @@ def to_host_f64(t, out=None, replicated=False):
     nbytes = t.numel() * t.element_size()
     stage = _pinned_staging(nbytes)[:nbytes].view(t.dtype).view(t.shape)
     stage.copy_(t, non_blocking=True)
-    out = torch.empty(t.shape, dtype=torch.float64) if out is None else torch.from_numpy(out).view(t.shape)
+    entry = None
+    if out is None:
+        out, entry = _result_buffer(tuple(t.shape))
+    else:
+        out = torch.from_numpy(out).view(t.shape)
     torch.cuda.current_stream().synchronize()
     # torchrun pins OMP_NUM_THREADS=1; the widening copy of a large grid is worth a few host
     # threads per rank (never more than the cores this rank can fairly claim)
@@ -99,7 +132,11 @@ def to_host_f64(t, out=None, replicated=False):
             torch.set_num_threads(before)
     else:
         out.copy_(stage)
-    return out.numpy()
+    res = out.numpy()
+    if entry is not None:
+        import weakref
+        entry["live"] = weakref.ref(res)                # views of `res` keep it alive (numpy collapses .base)
+    return res
 
 
 def _dev(a, device, dtype=None):

@@ -124,7 +124,7 @@ def _new_segment(nbytes, rank, device, group):
     return {"nbytes": nbytes, "fd": fd, "w": w, "live": None}
 
 
-def shared_result_f64(t, to_host_slice, group=None, min_bytes=32 << 20):
+def shared_result_f64(t, to_host_slice, group=None, min_bytes=128 << 20):
     """float64 NumPy copy of tensor `t`, which every rank holds identically after an all-reduce.
     One process per GPU on one node would otherwise pay the device->host copy and the fp32->fp64
     widening of the whole grid once PER RANK on the same host cores and memory bus.  Here rank r
