@@ -107,3 +107,37 @@ def test_full_size_detector_kernels_agree(slab5):
     flat = ((iy * V + ix) * V + iz).reshape(P, P)
     _, ib = det.accumulate(gx, gy, gz, R, w, probe=179, kernel="affine")
     assert np.array_equal(ib.cpu().numpy().reshape(P, P)[::7, ::5], flat[::7, ::5])
+
+
+def test_config2_grid_size_2095_bluestein_slice_against_oracle():
+    """BASELINE configs[1] geometry (r = 0.3, q = 0.01 -> N = 2095 = 5 x 419, q_num = 569): the largest
+    Bluestein transform (8192-point convolution) through the fused kernels, one slice against the oracle
+    and fused == staged on three."""
+    rng = np.random.default_rng(21)
+    coords = rng.random((60_000, 3)) * [210.0, 340.0, 160.0]
+    el = rng.choice(np.array(["S", "O", "H"]), size=len(coords))
+    r, q, max_q = 0.3, 0.01, 2.0
+    dev = engine.resolve_device()
+    codes, uniq, counts = engine.encode_elements_device(el, dev)
+    table = comparison.f_table(uniq, 12700.0)
+    atoms = engine.AtomSet(coords, r, 2095, dev, species=codes, table=table)
+    N, q_num, q_axis, phis = engine.stage_a_geometry(atoms.bounds, r, q, max_q)
+    assert (N, q_num) == (2095, 569)
+    avg = np.sum(counts * np.asarray(table)) / np.prod(atoms.bounds) * r ** 3
+    mk = lambda **kw: engine.SliceEngine(None, r, q_axis, N, avg, atoms.bounds[0], atoms.bounds[1], False, 7,
+                                         atoms=atoms, **kw)
+    sel = phis[[3, 600, 1500]]
+    fused, staged = mk(), mk()
+    fused.run(sel)
+    staged.run(sel, staged=True)
+    assert np.array_equal(fused.counts(), staged.counts())
+    assert np.abs(fused.sums() - staged.sums()).max() <= 1e-5 * staged.sums().max()
+    one = mk()
+    one.run(sel[1:2])
+    f = ox.f_values_for(el, table=synth.fixed_f1f2)
+    setup = ox.stage_a_setup(coords, f, r, q, max_q)
+    q3 = (setup["q_num"],) * 3
+    vsum, vcnt = np.zeros(q3), np.zeros(q3)
+    ox.run_slice(vsum, vcnt, coords, setup, r, float(sel[1]), False, 7)
+    assert np.array_equal(one.counts(), vcnt.astype(np.int64))
+    assert np.abs(one.sums() - vsum).max() <= 1e-4 * vsum.max()

@@ -241,7 +241,7 @@ def test_worker_api_generate_detector_ints(golden):
     shm.unlink()
 
 
-@pytest.mark.parametrize("N", [16, 64, 100, 256, 262, 1024])
+@pytest.mark.parametrize("N", [16, 64, 100, 256, 262, 1024, 1048, 2048, 2095])
 def test_fft2_abs2_shift_against_numpy(N):
     """K2 alone on random complex grids with a pedestal, pow2 and Bluestein sizes."""
     from giwaxsim_b200._lib import call, ptr
