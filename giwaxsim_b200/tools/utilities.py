@@ -192,3 +192,53 @@ def calc_real_space_abc(a_mag, b_mag, c_mag, alpha_deg, beta_deg, gamma_deg):
                   c_mag * (np.cos(alpha) - np.cos(beta) * np.cos(gamma)) / (np.sin(gamma)),
                   V / (a_mag * b_mag * np.sin(gamma))])
     return a, b, c
+
+
+def load_pdb_cell_params(pdb_path):
+    """(a, b, c, alpha, beta, gamma) from the CRYST1 record of a PDB file: fixed
+    columns 7-15, 16-24, 25-33, 34-40, 41-47, 48-54 (utilities.py:163-195)."""
+    with open(pdb_path, "r") as fh:
+        for line in fh:
+            if line.startswith("CRYST1"):
+                cuts = ((6, 15), (15, 24), (24, 33), (33, 40), (40, 47), (47, 54))
+                return tuple(float(line[lo:hi].strip()) for lo, hi in cuts)
+    raise ValueError("No CRYST1 line found in the PDB file.")
+
+
+# ---------------------------------------------------------------------------
+# key=value configuration files (simulate_GIWAXS.py --config)
+# ---------------------------------------------------------------------------
+_TRUE = {"true", "t", "yes", "y", "1", "on"}
+_FALSE = {"false", "f", "no", "n", "0", "off"}
+
+
+def str_to_bool(input_value, default=False):
+    """'true'/'yes'/'1'/'on'... -> True, 'false'/'no'/'0'/'off'... -> False, anything else ->
+    `default` (ValueError when default is None) (utilities.py:10-41)."""
+    text = str(input_value).strip().lower()
+    if text in _TRUE:
+        return True
+    if text in _FALSE:
+        return False
+    if default is not None:
+        return default
+    raise ValueError(f"Invalid input for boolean conversion: {input_value}")
+
+
+def parse_config_file(file_path):
+    """{key: value-string} of every line containing '=' (split at the first one; the line is
+    stripped, keys and values are not) (utilities.py:43-50)."""
+    config = {}
+    with open(file_path, "r") as fh:
+        for line in fh:
+            if "=" in line:
+                key, value = line.strip().split("=", 1)
+                config[key] = value
+    return config
+
+
+def save_config_to_txt(config, save_path):
+    """Echo a configuration as key=value lines (utilities.py:52-55)."""
+    with open(save_path, "w") as fh:
+        for key, value in config.items():
+            fh.write(f"{key}={value}\n")

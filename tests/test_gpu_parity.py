@@ -374,3 +374,39 @@ def test_slabmaker_fitting_errors(tmp_path):
     # a slab size of zero keeps only the exact mid-plane: nothing survives -> the reference's np.min error
     with pytest.raises(ValueError, match="zero-size array"):
         comparison.slabmaker_fitting(px, 1e-9, 1e-9, 1e-9, 6.1, 7.3, 5.2, 90, 90, 90)
+
+
+def test_simulate_config_driver_end_to_end(tmp_path):
+    """The simulate_GIWAXS.py configuration interface on the B200 path: .pdb unit cell -> slab ->
+    voxel grid -> detector quadrant on disk, against the oracle pipeline on the same inputs."""
+    from giwaxsim_b200 import simulate
+    _, pp = _write_cell_files(tmp_path)
+    save = tmp_path / "out"
+    cfg = tmp_path / "cfg.txt"
+    cfg.write_text("input_filepath=%s\nx_size=30\ny_size=36\nz_size=26\nr_voxel_size=0.3\nq_voxel_size=0.1\nmax_q=1.5\n"
+                   "energy=12700\nfill_bkg=True\nsmooth=2\nnum_pixels=60\nangle_init_val1=90\nangle_init_val2=90\n"
+                   "angle_init_val3=90\nangle_init_ax1=psi\nangle_init_ax2=phi\nangle_init_ax3=psi\n"
+                   "psi_start=70\npsi_end=90\npsi_num=5\nphi_start=0\nphi_end=170\nphi_num=6\ntheta_start=0\n"
+                   "theta_end=0\ntheta_num=1\nmirror=True\nsave_folder=%s\n" % (pp, save))
+    config = utilities.parse_config_file(str(cfg))
+    out = simulate.main(config)
+    det_sum, det_h, det_v = out["cell"]
+    on_disk = np.load(str(save / "cell" / "det_sum.npy"))
+    assert np.array_equal(on_disk, det_sum) and (save / "config.txt").exists()
+    assert np.array_equal(np.load(str(save / "cell" / "det_h.npy")), det_h)
+    # oracle: same steps (comparison.py:595-870, simulate_GIWAXS.py:172-177)
+    cell = utilities.load_pdb_cell_params(pp)
+    c0, e0 = ox.read_structure(pp)
+    coords, el = ox.slabmaker(c0, e0, 30.0, 36.0, 26.0, *cell)
+    from giwaxsim_b200 import synth
+    f = ox.f_values_for(el, table=synth.fixed_f1f2)
+    iq, qx, qy, qz = ox.voxelgridmaker(coords, f, 0.3, 0.1, 1.5, True, 2)[:4]
+    psis, phis, thetas = np.linspace(70, 90, 5), np.linspace(0, 170, 6), np.linspace(0, 0, 1)
+    ones = lambda a: np.ones_like(a) / len(a)
+    o_det, o_h, o_v = ox.detectormaker(iq, qx, qy, qz, 60, 1.5, (90.0, 90.0, 90.0), ("psi", "phi", "psi"),
+                                       psis, ones(psis), phis, ones(phis), thetas, ones(thetas))
+    kh, kv = np.where(o_h >= 0)[0], np.where(o_v >= 0)[0]
+    assert np.array_equal(det_h, o_h[kh]) and np.array_equal(det_v, o_v[kv])
+    ref = o_det[np.ix_(kv, kh)]
+    assert det_sum.shape == ref.shape
+    assert np.abs(det_sum - ref).max() <= TOL_INT * ref.max()

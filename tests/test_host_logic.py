@@ -172,3 +172,31 @@ def test_structure_loaders_and_cell_vectors_match_oracle(tmp_path):
     for cell in [(4.0, 5.0, 6.0, 90.0, 90.0, 90.0), (2.456, 4.254, 6.696, 90.0, 90.0, 120.0), (7.0, 8.0, 9.0, 75.0, 85.0, 95.0)]:
         for u, v in zip(utilities.calc_real_space_abc(*cell), ox.cell_vectors(*cell)):
             assert np.array_equal(u, v)
+
+
+def test_config_parser_and_defaults(tmp_path):
+    from giwaxsim_b200 import simulate
+    from giwaxsim_b200.tools import utilities
+    cfg = tmp_path / "c.txt"
+    cfg.write_text("# a comment without the sign\ninput_filepath=cell.pdb\nmax_q=2\nq_voxel_size=0.02\nfill_bkg=True\n"
+                   "smooth=25\nmirror=yes\npsi_start=0\npsi_end=90\npsi_num=16\nphi_start=0\nphi_end=179\nphi_num=180\n"
+                   "theta_start=0\ntheta_end=0\ntheta_num=1\nangle_init_ax1=psi\nangle_init_val1=90\nnote=a=b\n")
+    config = utilities.parse_config_file(str(cfg))
+    assert config["note"] == "a=b" and "# a comment without the sign" not in config
+    s = simulate.read_settings(config)
+    assert s["num_pixels"] == 100 and s["r_voxel_size"] == 0.3 and s["energy"] == 10000.0     # reference defaults
+    assert s["fill_bkg"] is True and s["mirror"] is True and s["smooth"] == 25
+    assert s["angle_init_vals"] == (90.0, 0.0, 0.0) and s["angle_init_axs"] == ("psi", "None", "None")
+    assert np.array_equal(s["psis"], np.linspace(0.0, 90.0, 16)) and len(s["phis"]) == 180 and len(s["thetas"]) == 1
+    assert utilities.str_to_bool(" ON ") is True and utilities.str_to_bool("nope") is False
+    with pytest.raises(ValueError):
+        utilities.str_to_bool("nope", default=None)
+    out = tmp_path / "echo.txt"
+    utilities.save_config_to_txt(config, str(out))
+    assert utilities.parse_config_file(str(out)) == config
+    pdb = tmp_path / "cell.pdb"
+    pdb.write_text("CRYST1   44.456   45.726   40.097  90.00  90.00  90.00 P 1           1\n")
+    assert utilities.load_pdb_cell_params(str(pdb)) == (44.456, 45.726, 40.097, 90.0, 90.0, 90.0)
+    with pytest.raises(Exception, match="Either input_folder or input_path"):
+        simulate.main({"psi_start": "0", "psi_end": "1", "psi_num": "1", "phi_start": "0", "phi_end": "1",
+                       "phi_num": "1", "theta_start": "0", "theta_end": "1", "theta_num": "1"})
