@@ -615,7 +615,8 @@ class SliceEngine:
         return bb
 
     def fused_batch_size(self, budget_bytes=2 << 30):
-        return int(max(1, min(64, budget_bytes // (8 * self.N * self.KC))))
+        cap = int(os.environ.get("GIWAXS_B200_FUSED_BATCH", "64"))
+        return int(max(1, min(cap, budget_bytes // (8 * self.N * self.KC))))
 
     def fused(self, t, work):
         """F1 + F2 for one prepared batch (gx_slices_fused)."""
