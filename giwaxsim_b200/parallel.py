@@ -107,8 +107,9 @@ import mmap as _mmap
 import os as _os
 import weakref as _weakref
 
-_POOL_MAX = 3
-_pool = []            # segments: {"nbytes", "fd", "w" (MAP_SHARED mapping), "live" (weakref to the array handed out)}
+_POOL_MAX = 3         # segments per size class (a caller typically holds the previous result while asking for the next)
+_POOL_CLASSES = 4     # distinct result sizes kept (voxel grid, detector image, ...)
+_pool = {}            # nbytes -> [segment]; segment = {"nbytes", "fd", "w" (MAP_SHARED mapping), "live" (weakref)}
 _pool_serial = [0]
 
 
@@ -162,7 +163,7 @@ def _new_segment(nbytes, rank, device, group):
     return {"nbytes": nbytes, "fd": fd, "w": w, "live": None}
 
 
-def shared_result_f64(t, to_host_slice, group=None, min_bytes=128 << 20):
+def shared_result_f64(t, to_host_slice, group=None, min_bytes=16 << 20):
     """float64 NumPy copy of tensor `t`, which every rank holds identically after an all-reduce.
     One process per GPU on one node would otherwise pay the device->host copy and the fp32->fp64
     widening of the whole grid once PER RANK on the same host cores and memory bus.  Here rank r
@@ -181,24 +182,36 @@ def shared_result_f64(t, to_host_slice, group=None, min_bytes=128 << 20):
     nbytes = n * 8
     if world == 1 or nbytes < min_bytes or not _all_local(group):
         return None
-    # agree on a segment: free on every rank (the pool evolves in lockstep, so indices match)
-    flags = torch.zeros(_POOL_MAX, dtype=torch.int32, device=t.device)
-    for i, seg in enumerate(_pool):
-        flags[i] = 1 if _segment_free(seg) else 0
-    dist.all_reduce(flags, op=dist.ReduceOp.MIN, group=group)
-    free = [i for i in range(len(_pool)) if int(flags[i]) == 1]
-    same = [i for i in free if _pool[i]["nbytes"] == nbytes]
-    if same:
-        seg = _pool[same[0]]
-    else:
-        if len(_pool) >= _POOL_MAX:
-            if not free:
+    # agree on a segment of this size class: free on every rank (the pool evolves in lockstep on all
+    # ranks, so positions match)
+    segs = _pool.get(nbytes)
+    if segs is None:
+        if len(_pool) >= _POOL_CLASSES:
+            # drop a size class whose segments are all free everywhere (checked with the same all-reduce)
+            keys = sorted(_pool)
+            idle = torch.tensor([1 if all(_segment_free(x) for x in _pool[k]) else 0 for k in keys],
+                                dtype=torch.int32, device=t.device)
+            dist.all_reduce(idle, op=dist.ReduceOp.MIN, group=group)
+            victims = [k for k, f in zip(keys, idle.tolist()) if f == 1]
+            if not victims:
                 return None
-            _close_segment(_pool.pop(free[0]))                    # a free segment of another size makes room
+            for x in _pool.pop(victims[0]):
+                _close_segment(x)
+        segs = _pool[nbytes] = []
+    flags = torch.zeros(_POOL_MAX, dtype=torch.int32, device=t.device)
+    for i, x in enumerate(segs):
+        flags[i] = 1 if _segment_free(x) else 0
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN, group=group)
+    free = [i for i in range(len(segs)) if int(flags[i]) == 1]
+    if free:
+        seg = segs[free[0]]
+    else:
+        if len(segs) >= _POOL_MAX:
+            return None
         seg = _new_segment(nbytes, rank, t.device, group)
         if seg is None:
             return None
-        _pool.append(seg)
+        segs.append(seg)
     flat = t.reshape(-1)
     per = (n + world - 1) // world
     lo, hi = min(n, rank * per), min(n, (rank + 1) * per)

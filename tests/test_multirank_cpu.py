@@ -61,16 +61,17 @@ def _worker(rank, world, port, coords, f, r, q, max_q, ret):
         assert not [f for f in os.listdir("/dev/shm") if f.startswith("giwaxs_b200_%d_" % port)]
         # pool: a segment is reused only when every rank dropped its array; live arrays never change
         second = parallel.shared_result_f64(grid * 3, widen, min_bytes=0)       # `shared` alive -> new segment
-        assert len(parallel._pool) == 2 and np.array_equal(second, 3 * grid.numpy().astype(np.float64))
+        segs = parallel._pool[grid.numel() * 8]
+        assert len(segs) == 2 and np.array_equal(second, 3 * grid.numpy().astype(np.float64))
         keep = shared[2:4]                                                  # a view keeps its segment busy
         del shared
         third = parallel.shared_result_f64(grid * 5, widen, min_bytes=0)
-        assert len(parallel._pool) == 3 and keep[0, 1, 1] == grid[2, 1, 1].item()
+        assert len(segs) == 3 and keep[0, 1, 1] == grid[2, 1, 1].item()
         del keep, second
         import gc
         gc.collect()
         fourth = parallel.shared_result_f64(grid * 7, widen, min_bytes=0)       # segments 0 and 1 are free again
-        assert len(parallel._pool) == 3 and np.array_equal(fourth, 7 * grid.numpy().astype(np.float64))
+        assert len(segs) == 3 and np.array_equal(fourth, 7 * grid.numpy().astype(np.float64))
         assert np.array_equal(third, 5 * grid.numpy().astype(np.float64))
         if rank == 1:
             hold = parallel.shared_result_f64(grid, widen, min_bytes=0)         # (kept alive on rank 1 only)
@@ -78,6 +79,11 @@ def _worker(rank, world, port, coords, f, r, q, max_q, ret):
             parallel.shared_result_f64(grid, widen, min_bytes=0)
         fifth = parallel.shared_result_f64(grid * 9, widen, min_bytes=0)        # all three segments busy somewhere
         assert fifth is None
+        # another result size gets its own class and does not evict the first one
+        small = torch.arange(11, dtype=torch.float32)
+        other = parallel.shared_result_f64(small, widen, min_bytes=0)
+        assert np.array_equal(other, small.numpy().astype(np.float64)) and len(parallel._pool) == 2
+        assert len(parallel._pool[grid.numel() * 8]) == 3
         os.environ["LOCAL_WORLD_SIZE"] = "1"                   # ranks "on different nodes": caller converts itself
         assert parallel.shared_result_f64(grid, widen, min_bytes=0) is None
         if rank == 0:
