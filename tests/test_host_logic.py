@@ -200,3 +200,26 @@ def test_config_parser_and_defaults(tmp_path):
     with pytest.raises(Exception, match="Either input_folder or input_path"):
         simulate.main({"psi_start": "0", "psi_end": "1", "psi_num": "1", "phi_start": "0", "phi_end": "1",
                        "phi_num": "1", "theta_start": "0", "theta_end": "1", "theta_num": "1"})
+
+
+def test_ctypes_prototypes_have_the_headers_arity():
+    """Every binding in _lib._PROTOTYPES passes exactly as many arguments as the header declares."""
+    header = open(os.path.join(ROOT, "include", "giwaxs_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    decls = dict(re.findall(r"\b(gx_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", header, flags=re.S))
+    assert set(decls) == set(_lib._PROTOTYPES)
+    for name, params in decls.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_lib._PROTOTYPES[name][1]), (name, n, len(_lib._PROTOTYPES[name][1]))
+    # the two argument blocks mirror the C structs field for field
+    for cname, pyname in (("gx_fused_args", _lib.FusedArgs), ("gx_slab_args", _lib.SlabArgs), ("gx_chord", _lib.Chord)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), header, flags=re.S).group(1)
+        c_fields = []
+        for stmt in body.split(";"):
+            stmt = stmt.strip()
+            if not stmt:
+                continue
+            names = re.sub(r"^(const\s+)?(unsigned\s+)?[A-Za-z_0-9]+\s+", "", stmt)      # drop the type
+            c_fields += [re.sub(r"[\s\*]|\[.*?\]", "", x) for x in names.split(",")]
+        assert c_fields == [f[0] for f in pyname._fields_], cname
