@@ -111,3 +111,46 @@ def test_fixed_point_model_agrees_with_oracle_indices(name, q_voxel):
     # (on the dyadic axis detector pixels coincide with voxel edges exactly; no bound on the fraction)
     if q_voxel != "dyadic":
         assert frac < (0.08 if rows % 2 else 0.002)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fixed_point_model_random_geometries(seed):
+    """Random init rotations, orientation triples, detector sizes and voxel axes: every pixel the
+    kernel would not send to the exact path must carry the oracle's voxel index."""
+    rng = np.random.default_rng(1000 + seed)
+    P = int(rng.integers(17, 70))
+    max_q = float(rng.uniform(0.8, 3.0))
+    V = int(rng.integers(40, 420))
+    half = max_q * float(rng.uniform(0.7, 1.3))          # voxel box smaller or larger than the detector
+    axis = np.linspace(-half, half, V)
+    if seed % 3 == 0:
+        axis = axis - axis[V // 2]                       # q = 0 exactly on a voxel edge
+    axs_pool = ["psi", "phi", "theta", "None"]
+    init = (tuple(float(a) for a in rng.choice([0.0, 90.0, 45.0, 12.5, -30.0], 3)),
+            tuple(str(a) for a in rng.choice(axs_pool, 3)))
+    gx, gy, gz, _, _ = ox.detector_base(P, max_q, *init)
+    psis = np.sort(rng.uniform(0, 90, 3))
+    phis = np.array([0.0, float(rng.uniform(0, 180))])
+    thetas = np.array([0.0, float(rng.uniform(-5, 5))])
+    if seed % 4 == 1:
+        psis[0], phis, thetas = 0.0, np.array([0.0]), np.array([0.0])
+    w = [np.ones_like(a) / len(a) for a in (psis, phis, thetas)]
+    R, wt = engine.orientation_tables(engine.grid_corners(gx, gy, gz), psis, w[0], phis, w[1], thetas, w[2])
+    corners, dev3 = base_fit(gx, gy, gz)
+    shape = (V, V, V)
+    mins, dq = (axis.min(),) * 3, float(np.diff(axis)[0])
+    got = engine.affine_plan_host(shape, mins, dq, corners, dev3, P, P, R, wt)
+    assert got is not None
+    _, rec, plan = got
+    em = emulate(rec.view(engine.AFFINE_RECORD), plan, P, P, shape)
+    todo = ox.orientation_list(psis, w[0], phis, w[1], thetas, w[2])
+    checked = 0
+    for o, (psi, phi, theta, _) in enumerate(todo):
+        g = ox.rotate_psi_phi_theta(gx, gy, gz, psi, phi, theta)
+        ix, iy, iz = (a.reshape(P, P) for a in ox.detector_voxel_indices(shape, axis, axis, axis, *g))
+        ex, ey, ez, flag = em[o]
+        ok = ~flag
+        assert np.array_equal(ex[ok], ix[ok]) and np.array_equal(ey[ok], iy[ok]) and np.array_equal(ez[ok], iz[ok]), \
+            (seed, o)
+        checked += int(ok.sum())
+    assert checked > 0
