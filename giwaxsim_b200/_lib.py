@@ -82,6 +82,7 @@ _PROTOTYPES = {
     "gx_bin_slices": (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p]),
     "gx_row_histogram": (_i, [_p, _i, _i, _p, _p]),
     "gx_voxel_finalize": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _d, _p, _p]),
+    "gx_voxel_shell_scale": (_i, [_p, _i, _p, _d, _d, _d, _p]),
     "gx_slice_col_range": (_i, [_p, _i, _i, _p, _p]),
     "gx_window_indices": (_i, [_p, _i64, _i, _i, _i, _i, _p]),
     "gx_slices_fused": (_i, [_p, _p]),
@@ -142,7 +143,7 @@ _LAUNCHES = {
     "gx_coords_minmax": 3, "gx_atoms_sort_rows": 3, "gx_slice_bbox": 3, "gx_atom_pixel_indices": 1,
     "gx_slice_vectors": 1, "gx_project_slices": 1, "gx_fft2_abs2_shift": 2, "gx_slice_col_index": 1,
     "gx_axis_col_index": 1, "gx_axis_row_index": 1, "gx_bin_slices": 1, "gx_row_histogram": 1,
-    "gx_voxel_finalize": 1, "gx_rotate_points": 1, "gx_detector_accumulate": 1, "gx_detector_epilogue": 1,
+    "gx_voxel_finalize": 1, "gx_voxel_shell_scale": 1, "gx_rotate_points": 1, "gx_detector_accumulate": 1, "gx_detector_epilogue": 1,
     "gx_detector_accumulate_fast": 1, "gx_detector_accumulate_affine": 1, "gx_grid_affine_fit": 1,
     "gx_slices_fused": 2, "gx_species_histogram": 1, "gx_species_codes": 1, "gx_window_indices": 1, "gx_slab_minmax": 3, "gx_slab_count": 3, "gx_slab_write": 1, "gx_slice_col_range": 1, "gx_extreme_atoms": 1, "gx_hull_filter": 1,
 }

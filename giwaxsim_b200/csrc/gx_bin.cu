@@ -155,7 +155,7 @@ struct Aff { double a[9]; double Z; };
 __global__ void __launch_bounds__(256)
 voxel_finalize_kernel(const float *__restrict__ sum, const uint32_t *__restrict__ count3,
                       const uint32_t *__restrict__ count2, const uint32_t *__restrict__ m,
-                      int q_num, int lo, int V, const double *__restrict__ axis, Aff aff, float *iq)
+                      int q_num, int lo, int V, const double *__restrict__ axis, Aff aff, int weighted, float *iq)
 {
     extern __shared__ double s_e[];                 // [4][V]
     const double k = 1.0 / (16.0 * 3.14159265358979323846 * 3.14159265358979323846);
@@ -178,7 +178,9 @@ voxel_finalize_kernel(const float *__restrict__ sum, const uint32_t *__restrict_
             const size_t v = yx * q_num + (iz + lo);
             const double cnt = count3 ? (double)count3[v] : cyx * (double)m[iz + lo];
             float out = 0.f;
-            if (cnt != 0.0) {
+            if (cnt != 0.0 && !weighted) {
+                out = (float)((double)sum[v] / cnt);        // generate_voxel_grid_low_mem: no f0 weighting
+            } else if (cnt != 0.0) {
                 double f = aff.a[8];
 #pragma unroll
                 for (int term = 0; term < 4; ++term) f += aff.a[2 * term] * (exy[term] * s_e[term * V + iz]);
@@ -194,12 +196,12 @@ extern "C" int gx_voxel_finalize(const float *d_sum, const uint32_t *d_count3, c
                                  const uint32_t *d_m, int q_num, int lo, int hi, const double *d_axis,
                                  const double *h_aff9, double Z, float *d_iq, void *stream)
 {
-    GX_REQUIRE(d_sum && d_axis && h_aff9 && d_iq, "NULL pointer");
+    GX_REQUIRE(d_sum && d_axis && d_iq, "NULL pointer");
     GX_REQUIRE(d_count3 || (d_count2 && d_m), "count grids missing");
-    GX_REQUIRE(q_num > 0 && lo >= 0 && hi > lo && hi <= q_num && Z != 0.0, "bad crop range");
+    GX_REQUIRE(q_num > 0 && lo >= 0 && hi > lo && hi <= q_num && (Z != 0.0 || !h_aff9), "bad crop range");
     Aff aff;
-    for (int i = 0; i < 9; ++i) aff.a[i] = h_aff9[i];
-    aff.Z = Z;
+    for (int i = 0; i < 9; ++i) aff.a[i] = h_aff9 ? h_aff9[i] : 0.0;
+    aff.Z = h_aff9 ? Z : 1.0;
     const int V = hi - lo;
     const size_t n = (size_t)V * V * V;
     size_t blocks = (n + 255) / 256;
@@ -212,8 +214,39 @@ extern "C" int gx_voxel_finalize(const float *d_sum, const uint32_t *d_count3, c
     GX_CUDA(cudaFuncSetAttribute(voxel_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (blocks > (size_t)GX_SM_COUNT * 8) blocks = (size_t)GX_SM_COUNT * 8;
     voxel_finalize_kernel<<<(int)blocks, 256, smem, gx_stream(stream)>>>(d_sum, d_count3, d_count2, d_m, q_num,
-                                                                        lo, V, d_axis, aff, d_iq);
+                                                                        lo, V, d_axis, aff, h_aff9 != nullptr, d_iq);
     return gx_check_launch("gx_voxel_finalize");
+}
+
+// ---------------------------------------------------- shell scaling (N4) ----
+// aff_num_qs > 1 branch of generate_voxel_grid_low_mem (voxelgrids.py:650-707): voxels with
+// lower < |q| <= upper are multiplied by `factor`.  |q| is the reference's
+// sqrt(qx_mesh**2 + qy_mesh**2 + qz_mesh**2) with every operation rounded separately; the grid is
+// indexed [qy, qx, qz] (np.meshgrid default 'xy').
+__global__ void __launch_bounds__(256)
+voxel_shell_scale_kernel(float *iq, int V, const double *__restrict__ axis, double lower, double upper, float factor)
+{
+    const int columns = V * V;
+    for (int col = blockIdx.x; col < columns; col += gridDim.x) {
+        const int iy = col / V, ix = col - iy * V;
+        const double x = axis[ix], y = axis[iy];
+        const double xy = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+        for (int iz = threadIdx.x; iz < V; iz += blockDim.x) {
+            const double z = axis[iz];
+            const double qr = __dsqrt_rn(__dadd_rn(xy, __dmul_rn(z, z)));
+            if (qr <= upper && qr > lower) iq[(size_t)col * V + iz] *= factor;
+        }
+    }
+}
+
+extern "C" int gx_voxel_shell_scale(float *d_iq, int V, const double *d_axis, double lower, double upper,
+                                    double factor, void *stream)
+{
+    GX_REQUIRE(d_iq && d_axis && V > 0, "bad arguments");
+    int64_t blocks = (int64_t)V * V;
+    if (blocks > GX_SM_COUNT * 8) blocks = GX_SM_COUNT * 8;
+    voxel_shell_scale_kernel<<<(int)blocks, 256, 0, gx_stream(stream)>>>(d_iq, V, d_axis, lower, upper, (float)factor);
+    return gx_check_launch("gx_voxel_shell_scale");
 }
 
 // ---------------------------------------------------------- crop window ----

@@ -459,7 +459,7 @@ detector_epilogue_kernel(const double *__restrict__ img, int rows, int cols, int
         if (finish) {
             if (v != v) v = 1e-6;
             if (v <= 0.0) v = 1e-6;
-            v = v * 1e-6;
+            if (finish == 1) v = v * 1e-6;
         }
         out[o] = v;
     }

@@ -765,15 +765,17 @@ def crop_range(axis, max_val):
     return int(idx[0]), int(idx[-1]) + 1
 
 
-def finalize_voxels(vsum, count3, count2, row_hist, q_axis, max_q, device, window=None):
+def finalize_voxels(vsum, count3, count2, row_hist, q_axis, max_q, device, window=None, crop=True, f0=True):
     """sum/count, crop, carbon f0 weighting -> (iq fp32 device [V,V,V], axis).
-    window: the accumulators already cover only that index window (SliceEngine(window=...))."""
+    window: the accumulators already cover only that index window (SliceEngine(window=...)).
+    crop=False keeps the whole axis and f0=False skips the weighting: the plain grid
+    generate_voxel_grid_low_mem returns (voxelgrids.py:633-641)."""
     q_num = int(q_axis.shape[0])
-    lo, hi = crop_range(q_axis, max_q)
+    lo, hi = crop_range(q_axis, max_q) if crop else (0, q_num)
     V = hi - lo
     with torch.cuda.device(device):
         iq = torch.empty(V * V * V, dtype=torch.float32, device=device)
-        aff = np.asarray(CARBON_AFF, dtype=np.float64)
+        aff = np.asarray(CARBON_AFF, dtype=np.float64) if f0 else None
         if window is not None:
             if tuple(window) != (lo, hi):
                 raise ValueError("accumulator window %s is not the crop range %s" % (tuple(window), (lo, hi)))
@@ -786,6 +788,16 @@ def finalize_voxels(vsum, count3, count2, row_hist, q_axis, max_q, device, windo
                  ptr(d_axis), ptr(aff), CARBON_Z, ptr(iq), _stream())
         torch.cuda.current_stream().synchronize()
     return iq.view(V, V, V), q_axis[lo:hi].copy()
+
+
+def scale_shell(iq, axis, lower, upper, factor, device):
+    """iq[qy,qx,qz] *= factor for lower < |q| <= upper, in place on the device
+    (shell mask of voxelgrids.py:650,706-707)."""
+    V = int(iq.shape[0])
+    with torch.cuda.device(device):
+        d_axis = _dev(np.asarray(axis, dtype=np.float64), device)
+        call("gx_voxel_shell_scale", ptr(iq), V, ptr(d_axis), float(lower), float(upper), float(factor), _stream())
+        torch.cuda.current_stream().synchronize()
 
 
 # ---------------------------------------------------------------------------
@@ -1024,7 +1036,7 @@ def rotate_points(R, gx, gy, gz, device=None):
 def detector_epilogue(image, rows, cols, mirror, device, finish=True):
     with torch.cuda.device(device):
         out = torch.empty(rows * cols, dtype=torch.float64, device=device)
-        call("gx_detector_epilogue", ptr(image), int(rows), int(cols), int(bool(mirror)), int(bool(finish)),
+        call("gx_detector_epilogue", ptr(image), int(rows), int(cols), int(bool(mirror)), int(finish),
              ptr(out), _stream())
         torch.cuda.current_stream().synchronize()
     return out.view(rows, cols)

@@ -18,6 +18,15 @@ def rank_world():
     return 0, 1
 
 
+def init_from_env():
+    """Under torchrun (RANK / WORLD_SIZE > 1 in the environment): bind this process to its GPU and
+    join the NCCL group.  A plain `python -m ...` call is a single-rank run and does nothing."""
+    import os
+    if "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1 and not dist.is_initialized():
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+
+
 def shard(items, rank, world):
     """Round-robin share of `items` for `rank` (balances the phi-dependent
     number of kept columns across ranks)."""

@@ -104,11 +104,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser(description="GIWAXS forward simulation on the B200 path")
     ap.add_argument("--config", type=str, required=True, help="key=value configuration file")
     args = ap.parse_args()
-    if "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-        dist.init_process_group("nccl")
+    parallel.init_from_env()
     t0 = time.time()
     main(parse_config_file(args.config))
     print(f'\nTotal Time: {str(np.round(time.time() - t0, 1))}s')

@@ -112,17 +112,14 @@ def _resident_slab(coords, elements, dev):
     return _slab["d_coords"], _slab["d_codes"], _slab["uniq"], _slab["counts"]
 
 
-def voxelgridmaker_fitting(coords, elements, r_voxel_size, q_voxel_size, max_q, energy, num_cpus=None,
-                           fill_bkg=False, smooth=0, phis=None, return_state=False):
-    """3-D I(q) voxel grid of a slab by the projection-slice method.
-
-    Returns (iq[y,x,z], qx, qy, qz) as float64 arrays.  `num_cpus` is accepted
-    and ignored, as in the reference.  Extra keyword `phis` overrides the
-    reference-derived rotation list (benchmarks); `return_state` also returns
-    the engine (parity probes).
-    """
+def voxelgrid_device(coords, elements, table_of, r_voxel_size, q_voxel_size, max_q, fill_bkg, smooth,
+                     phis=None, crop=True, f0=True, trace=None):
+    """Stage A on the device, shared by voxelgridmaker_fitting (crop + carbon f0 weight) and
+    tools.voxelgrids.generate_voxel_grid_low_mem (whole axis, no weight).
+    table_of(unique elements) -> complex f per unique element.
+    Returns (iq fp32 device [V,V,V], axis [V], engine, world size)."""
     dev = engine.resolve_device()
-    tr = _Trace("voxelgridmaker_fitting")
+    tr = trace if trace is not None else _Trace("stage A")
     resident = _resident_slab(coords, elements, dev)
     coords = np.asarray(coords, dtype=np.float64)
     # grid size first (needed to sort atoms by pixel row); bounds come back from the device
@@ -138,9 +135,13 @@ def voxelgridmaker_fitting(coords, elements, r_voxel_size, q_voxel_size, max_q, 
     tr.lap("species")
     if enc is not None:
         codes, uniq, counts = enc                    # coded on the device, counted there too
-        table = f_table(uniq, energy)
+        table = table_of(uniq)
     else:
-        codes, uniq, table = species_table(elements, energy)
+        elements = np.asarray(elements)
+        codes, uniq = engine.encode_values(elements)
+        if codes is None:
+            uniq = list(np.unique(elements))
+        table = table_of(uniq)
         counts = np.bincount(codes, minlength=len(table)) if codes is not None else None
     with torch.cuda.device(dev):
         if codes is not None:
@@ -158,7 +159,7 @@ def voxelgridmaker_fitting(coords, elements, r_voxel_size, q_voxel_size, max_q, 
         phis = ref_phis
     avg_voxel_f = (sum_f / (x_bound * y_bound * z_bound)) * r_voxel_size ** 3     # comparison.py:742-744
     # only the voxels downselect_voxelgrid keeps are accumulated (the crop commutes with the sum)
-    window = engine.crop_range(q_axis, max_q)
+    window = engine.crop_range(q_axis, max_q) if crop else None
     eng = engine.SliceEngine(None, r_voxel_size, q_axis, grid_size, avg_voxel_f, x_bound, y_bound,
                              fill_bkg, smooth, device=dev, atoms=atoms, window=window)
     rank, world = parallel.rank_world()
@@ -169,9 +170,25 @@ def voxelgridmaker_fitting(coords, elements, r_voxel_size, q_voxel_size, max_q, 
         parallel.all_reduce_sum([eng.vsum, eng.count2])
     tr.lap("all-reduce")
     iq_dev, axis = engine.finalize_voxels(eng.vsum, None, eng.count2, eng.row_hist, q_axis, max_q, dev,
-                                          window=window)
+                                          window=window, crop=crop, f0=f0)
     tr.lap("finalise")
-    with torch.cuda.device(dev):
+    return iq_dev, axis, eng, world
+
+
+def voxelgridmaker_fitting(coords, elements, r_voxel_size, q_voxel_size, max_q, energy, num_cpus=None,
+                           fill_bkg=False, smooth=0, phis=None, return_state=False):
+    """3-D I(q) voxel grid of a slab by the projection-slice method.
+
+    Returns (iq[y,x,z], qx, qy, qz) as float64 arrays.  `num_cpus` is accepted
+    and ignored, as in the reference.  Extra keyword `phis` overrides the
+    reference-derived rotation list (benchmarks); `return_state` also returns
+    the engine (parity probes).
+    """
+    tr = _Trace("voxelgridmaker_fitting")
+    iq_dev, axis, eng, world = voxelgrid_device(coords, elements, lambda uniq: f_table(uniq, energy),
+                                                r_voxel_size, q_voxel_size, max_q, fill_bkg, smooth,
+                                                phis=phis, trace=tr)
+    with torch.cuda.device(iq_dev.device):
         iq = engine.to_host_f64(iq_dev, replicated=world > 1)   # one DMA in fp32, widened on the host
     tr.lap("result to host")
     tr.done()

@@ -22,14 +22,59 @@ ATOMIC_NUMBER = {
     'Pb': 82, 'Bi': 83, 'Po': 84, 'At': 85, 'Rn': 86, 'Fr': 87, 'Ra': 88, 'Ac': 89, 'Th': 90, 'Pa': 91,
     'U': 92}
 
-# Cromer-Mann a1,b1,...,a4,b4,c (International Tables C, table 6.1.1.4) for the
-# light elements; the path itself only ever uses carbon (comparison.py:785).
+# Cromer-Mann a1,b1,...,a4,b4,c (International Tables C, table 6.1.1.4) of the
+# neutral atoms that occur in organic / hybrid films; the fitting path itself only
+# ever uses carbon (comparison.py:785), the two-step driver the most common element
+# of the input file (old_modules/voxelgridmaker.py:66-68).  Extend with
+# register_cromer_mann for anything else (the reference's own table has no neutral
+# 'Si' entry, for instance: ptable_dict.py).
 CROMER_MANN = {
     'H': (0.489918, 20.6593, 0.262003, 7.74039, 0.196767, 49.5519, 0.049879, 2.20159, 0.001305),
+    'B': (2.0545, 23.2185, 1.3326, 1.021, 1.0979, 60.3498, 0.7068, 0.1403, -0.1932),
     'C': (2.31, 20.8439, 1.02, 10.2075, 1.5886, 0.5687, 0.865, 51.6512, 0.2156),
     'N': (12.2126, 0.0057, 3.1322, 9.8933, 2.0125, 28.9975, 1.1663, 0.5826, -11.529),
     'O': (3.0485, 13.2771, 2.2868, 5.7011, 1.5463, 0.3239, 0.867, 32.9089, 0.2508),
+    'F': (3.5392, 10.2825, 2.6412, 4.2944, 1.517, 0.2615, 1.0243, 26.1476, 0.2776),
+    'Na': (4.7626, 3.285, 3.1736, 8.8422, 1.2674, 0.3136, 1.1128, 129.424, 0.676),
+    'Mg': (5.4204, 2.8275, 2.1735, 79.2611, 1.2269, 0.3808, 2.3073, 7.1937, 0.8584),
+    'Al': (6.4202, 3.0387, 1.9002, 0.7426, 1.5936, 31.5472, 1.9646, 85.0886, 1.1151),
+    'P': (6.4345, 1.9067, 4.1791, 27.157, 1.78, 0.526, 1.4908, 68.1645, 1.1149),
+    'S': (6.9053, 1.4679, 5.2034, 22.2151, 1.4379, 0.2536, 1.5863, 56.172, 0.8669),
+    'Cl': (11.4604, 0.0104, 7.1964, 1.1662, 6.2556, 18.5194, 1.6455, 47.7784, -9.5574),
+    'K': (8.2186, 12.7949, 7.4398, 0.7748, 1.0519, 213.187, 0.8659, 41.6841, 1.4228),
+    'Ca': (8.6266, 10.4421, 7.3873, 0.6599, 1.5899, 85.7484, 1.0211, 178.437, 1.3751),
+    'Ti': (9.7595, 7.8508, 7.3558, 0.5, 1.6991, 35.6338, 1.9021, 116.105, 1.2807),
+    'Fe': (11.7695, 4.7611, 7.3573, 0.3072, 3.5222, 15.3535, 2.3045, 76.8805, 1.0369),
+    'Cu': (13.338, 3.5828, 7.1676, 0.247, 5.6158, 11.3966, 1.6735, 64.8126, 1.191),
+    'Zn': (14.0743, 3.2655, 7.0318, 0.2333, 5.1652, 10.3163, 2.41, 58.7097, 1.3041),
+    'Se': (17.0006, 2.4098, 5.8196, 0.2726, 3.9731, 15.2372, 4.3543, 43.8163, 2.8409),
+    'Br': (17.1789, 2.1723, 5.2358, 16.5796, 5.6377, 0.2609, 3.9851, 41.4328, 2.9557),
+    'I': (20.1472, 4.347, 18.9949, 0.3814, 7.5138, 27.766, 2.2735, 66.8776, 4.0712),
+    'Au': (16.8819, 0.4611, 18.5913, 8.6216, 25.5582, 1.4826, 5.86, 36.3956, 12.0658),
+    'Pb': (31.0617, 0.6902, 13.0637, 2.3576, 18.442, 8.618, 5.9696, 47.2579, 13.4118),
 }
+
+
+def register_cromer_mann(element, coefficients):
+    """Add / replace the nine Cromer-Mann coefficients (a1,b1,..,a4,b4,c) of an element."""
+    coefficients = tuple(float(v) for v in coefficients)
+    if len(coefficients) != 9:
+        raise ValueError("nine coefficients expected: a1, b1, a2, b2, a3, b3, a4, b4, c")
+    CROMER_MANN[str(element)] = coefficients
+
+
+def get_element_f0_dict(q_val, elements):
+    """{element: f0} of the distinct elements at q_val (utilities.py:319-340).  The
+    reference's exponent is -b*q/(16 pi^2) - q, not q^2 - and this mirrors it."""
+    out = {}
+    for element in set(elements):
+        aff = CROMER_MANN[element]
+        out[element] = (aff[0] * np.exp(-aff[1] * (q_val) / (16 * np.pi ** 2)) +
+                        aff[2] * np.exp(-aff[3] * (q_val) / (16 * np.pi ** 2)) +
+                        aff[4] * np.exp(-aff[5] * (q_val) / (16 * np.pi ** 2)) +
+                        aff[6] * np.exp(-aff[7] * (q_val) / (16 * np.pi ** 2)) +
+                        aff[8])
+    return out
 
 _f1f2_provider = None
 
@@ -177,6 +222,27 @@ def load_pdb(pdb_path):
                 symbols.append(line[76:78].strip())
                 coords.append([float(line[30:38]), float(line[38:46]), float(line[46:54])])
     return np.array(coords), np.array(symbols)
+
+
+def load_structure(input_path):
+    """load_xyz / load_pdb by the last three characters of the path, with the
+    reference's error for anything else (voxelgrids.py:573-578)."""
+    if input_path[-3:] == 'xyz':
+        return load_xyz(input_path)
+    if input_path[-3:] == 'pdb':
+        return load_pdb(input_path)
+    raise Exception('files must be a .pdb or .xyz file')
+
+
+def most_common_element(input_path):
+    """Most frequent element symbol of a structure file; ties go to the element
+    seen first, like collections.Counter.most_common (utilities.py:61-75)."""
+    _, elements = load_structure(input_path)
+    first_seen, counts = {}, {}
+    for i, el in enumerate(elements.tolist()):
+        counts[el] = counts.get(el, 0) + 1
+        first_seen.setdefault(el, i)
+    return max(counts, key=lambda el: (counts[el], -first_seen[el]))
 
 
 def calc_real_space_abc(a_mag, b_mag, c_mag, alpha_deg, beta_deg, gamma_deg):

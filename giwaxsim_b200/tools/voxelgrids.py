@@ -5,6 +5,7 @@ same names, argument order and side effects, work done by the sm_100a kernels.
     process_file2(...)                  voxelgrids.py:464-506
     downselect_voxelgrid(...)           voxelgrids.py:16-48
     add_f0_q_3d(...)                    voxelgrids.py:828-857
+    generate_voxel_grid_low_mem(...)    voxelgrids.py:535-722  (file -> whole I(q) grid, two-step CLI)
 
 The two accumulator arguments are names of device shared arrays created with
 tools.utilities.create_shared_array (they replace the POSIX shm names).
@@ -14,7 +15,8 @@ import torch
 
 from .. import engine
 from .._lib import call, ptr
-from .utilities import ATOMIC_NUMBER, CROMER_MANN, lookup_shared_array
+from .utilities import (ATOMIC_NUMBER, CROMER_MANN, get_element_f0_dict, get_element_f1_f2_dict, load_structure,
+                        lookup_shared_array)
 
 _engine_cache = {}
 _ENGINE_CACHE_MAX = 2
@@ -110,3 +112,57 @@ def add_f0_q_3d(iq, qx_axis, qy_axis, qz_axis, element):
         call("gx_voxel_finalize", ptr(d_sum), ptr(ones), None, None, V, 0, V, ptr(d_axis),
              ptr(aff), float(ATOMIC_NUMBER[element]), ptr(out), engine._stream())
         return out.cpu().to(torch.float64).numpy().reshape(V, V, V)
+
+
+def generate_voxel_grid_low_mem(input_path, r_voxel_size, q_voxel_size, max_q, aff_num_qs, energy, gen_name,
+                                output_dir=None, scratch_folder=None, num_cpus=None, fill_bkg=False, smooth=0):
+    """Whole (uncropped, unweighted) 3-D I(q) grid of a structure file by the projection-slice
+    method (voxelgrids.py:535-722).  Returns (iq[qy,qx,qz], qx, qy, qz) as float64 arrays, or
+    writes `<output_dir>/<gen_name>_output_files/<gen_name>_{iq,qx,qy,qz}.npy` and returns None.
+    `scratch_folder` and `num_cpus` are accepted and unused (nothing is staged on disk here).
+
+    aff_num_qs == 1: f = Z + f' + i f'' per atom (:603-609).
+    aff_num_qs > 1: the reference loops over |q| shells with f = f0(q_shell) + f' + i f'', but
+    every pass REPLACES the grid by that shell's whole sum/count (:699) before adding the masked
+    copy (:706-707), so what it returns is the last shell's grid, doubled inside that shell.
+    Earlier passes cannot influence the result and are not run; the returned array is the same.
+    """
+    from .. import parallel
+    from .comparison import f_table, voxelgrid_device
+    import os
+
+    coords, elements = load_structure(input_path)
+    if aff_num_qs == 1:
+        shell = None
+
+        def table_of(uniq):
+            return f_table(uniq, energy)
+    elif aff_num_qs > 1:
+        max_q_diag = np.sqrt(2) * max_q
+        max_q_diag = max_q_diag + max_q_diag % q_voxel_size          # voxelgrids.py:590
+        step = (max_q_diag / (int(aff_num_qs)))
+        q_val = 0.5 * step + (int(aff_num_qs) - 1) * step            # last pass of the loop :660-662
+        shell = (q_val - step / 2, q_val + step / 2)
+
+        def table_of(uniq):
+            names = [str(e) for e in uniq]
+            f0, f12 = get_element_f0_dict(q_val, names), get_element_f1_f2_dict(energy, names)
+            return [complex(f0[e] + f12[e]) for e in names]
+    else:
+        raise Exception('Invalid aff_num_qs value. Must be non-negative integer')
+    iq_dev, axis, _, world = voxelgrid_device(coords, elements, table_of, r_voxel_size, q_voxel_size, max_q,
+                                              fill_bkg, smooth, crop=False, f0=False)
+    if shell is not None:
+        engine.scale_shell(iq_dev, axis, shell[0], shell[1], 2.0, iq_dev.device)
+    with torch.cuda.device(iq_dev.device):
+        iq = engine.to_host_f64(iq_dev, replicated=world > 1)
+    if output_dir:
+        save_path = f'{output_dir}/{gen_name}_output_files/'
+        if parallel.rank_world()[0] == 0:
+            if not os.path.exists(save_path):
+                os.mkdir(save_path)
+            np.save(f'{save_path}{gen_name}_iq.npy', iq)
+            for name in ('qx', 'qy', 'qz'):
+                np.save(f'{save_path}{gen_name}_{name}.npy', axis)
+        return None
+    return iq, axis.copy(), axis.copy(), axis.copy()

@@ -208,10 +208,19 @@ int gx_row_histogram(const int32_t *d_row, int n, int q_num, uint32_t *d_m, void
 /* iq = sum/count (0 where count == 0), cropped to [lo,hi)^3, times
  * ((sum_i a_i exp(-b_i q^2/16pi^2) + c)/Z)^2.  count = count3, or
  * count2[iy,ix]*m[iz] when d_count3 is NULL.  d_axis [q_num] fp64 voxel axis.
- * d_iq [(hi-lo)^3] fp32.     (comparison.py:769-786, vg.py:16-48,828-857)  */
+ * d_iq [(hi-lo)^3] fp32.     (comparison.py:769-786, vg.py:16-48,828-857)
+ * h_aff9 == NULL: plain sum/count without the f0 weight, as returned by
+ * generate_voxel_grid_low_mem (vg.py:633-641).                              */
 int gx_voxel_finalize(const float *d_sum, const uint32_t *d_count3, const uint32_t *d_count2,
                       const uint32_t *d_m, int q_num, int lo, int hi, const double *d_axis,
                       const double *h_aff9, double Z, float *d_iq, void *stream);
+
+/* d_iq[iy,ix,iz] *= factor where lower < sqrt(qx^2+qy^2+qz^2) <= upper, the
+ * radius formed like NumPy forms it (each product, sum and the root rounded
+ * once): the shell mask of the aff_num_qs > 1 branch (vg.py:650-707).
+ * d_iq [V^3] fp32 in place, d_axis [V] fp64.                                 */
+int gx_voxel_shell_scale(float *d_iq, int V, const double *d_axis, double lower, double upper,
+                         double factor, void *stream);
 
 /* ------------------------------------------- fused slice pipeline (A) -- */
 /* [first, one-past-last) kept column of every rotation from the table that
@@ -364,8 +373,9 @@ int gx_detector_accumulate_affine(const float *d_iq, int Vy, int Vx, int Vz, dou
 int gx_host_orientation_matrices(const double *h_corners, const double *h_cs, int n, double *h_R);
 
 /* mirror != 0: four-fold mirror with the odd-size centre rules
- * (detector.py:246-275).  finish != 0: NaN/<=0 -> 1e-6, then *1e-6
- * (comparison.py:859-868).  Out of place.                                  */
+ * (detector.py:246-275).  finish == 1: NaN/<=0 -> 1e-6, then *1e-6
+ * (comparison.py:859-868); finish == 2: the floor only, as the two-step
+ * driver does (old_modules/detectormaker.py:152-153).  Out of place.        */
 int gx_detector_epilogue(const double *d_image, int rows, int cols, int mirror, int finish,
                          double *d_out, void *stream);
 

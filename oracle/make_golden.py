@@ -11,6 +11,8 @@ Cases
   silicon256   silicon_medium.xyz cluster,  N=256 (pow2), no background, no smoothing
   clipped128   graphite cluster on a grid smaller than its y/x extent (valid-mask path)
   detector     stage B on the graphite262 voxel grid: 64^2 and 65^2 detectors
+  twostep      two seeded clusters through the reference's generate_voxel_grid_low_mem (aff_num_qs 1
+               and 3, N=210 -> Bluestein) and the old_modules/voxelgridmaker.py crop/average/f0 loop
   pm6          config_templates/simulate_GIWAXS_config.txt end to end (N=1048, 892 slices,
                2880 orientations x 500^2) + the reference's own golden det_sum.npy
 """
@@ -185,9 +187,50 @@ def pm6():
     np.save(os.path.join(OUT, "pm6_det_sum_ref.npy"), gold)
 
 
+def write_xyz(path, coords, elements):
+    """XYZ text that load_xyz parses back to the very same doubles."""
+    with open(path, "w") as fh:
+        fh.write("%d\ncluster\n" % len(coords))
+        for el, (x, y, z) in zip(elements, coords):
+            fh.write("%s %.17g %.17g %.17g\n" % (el, x, y, z))
+
+
+def twostep():
+    import tempfile
+    ref = ref_shim.load()
+    r, q, max_q, energy, fill_bkg, smooth = 0.3, 0.1, 1.5, 12700.0, True, 3
+    out = dict(r=r, q=q, max_q=max_q, energy=energy, fill_bkg=fill_bkg, smooth=smooth)
+    tmp = tempfile.mkdtemp()
+    paths = []
+    for k, seed in enumerate((21, 22)):
+        rng = np.random.default_rng(seed)
+        coords = rng.random((400, 3)) * np.array([30.0, 22.0, 26.0])
+        elements = rng.choice(np.array(["C", "H", "S", "O", "F"]), size=400, p=[0.5, 0.3, 0.08, 0.07, 0.05])
+        out["coords_%d" % k], out["elements_%d" % k] = coords, elements
+        paths.append(os.path.join(tmp, "c%d.xyz" % k))
+        write_xyz(paths[-1], coords, elements)
+    t0 = time.time()
+    total = None
+    for k, path in enumerate(paths):
+        iq, qx, qy, qz = ref_shim.voxel_grid_low_mem_serial(path, r, q, max_q, 1, energy, fill_bkg, smooth)
+        if k == 0:
+            out["iq_full_aff1"], out["axis"] = iq.copy(), qx.copy()
+        small, qxs, qys, qzs = ref.voxelgrids.downselect_voxelgrid(iq, qx, qy, qz, max_q)
+        total = small.copy() if k == 0 else total + small
+    total /= len(paths)
+    element = ref.utilities.most_common_element(paths[0])
+    out["two_step_iq"] = ref.voxelgrids.add_f0_q_3d(total, qxs, qys, qzs, element)
+    out["two_step_axis"], out["element"] = qxs.copy(), np.array(element)
+    out["iq_full_aff3"] = ref_shim.voxel_grid_low_mem_serial(paths[0], r, q, max_q, 3, energy, fill_bkg, smooth)[0]
+    print("twostep: q_num %d, crop %d, %.1f s" % (len(out["axis"]), len(qxs), time.time() - t0))
+    np.savez_compressed(os.path.join(OUT, "twostep.npz"), **out)
+
+
 def main(argv):
     os.makedirs(OUT, exist_ok=True)
-    todo = argv or ["graphite262", "silicon256", "clipped128", "detector", "pm6"]
+    todo = argv or ["graphite262", "silicon256", "clipped128", "detector", "twostep", "pm6"]
+    if "twostep" in todo:
+        twostep()
     iq = q = None
     if "graphite262" in todo:
         iq, q = graphite262()

@@ -218,3 +218,38 @@ def detectormaker_serial(iq, qx, qy, qz, num_pixels, max_q, angle_init_vals, ang
     det_sum[det_sum <= 0] = 1e-6
     det_sum *= 1e-6
     return det_sum, det_h, det_v
+
+
+class _SerialExecutor:
+    """Stand-in for ThreadPoolExecutor that runs every task at submit time: the reference's
+    threaded accumulation loses updates, parity is defined against the serial order."""
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def submit(self, fn, *args, **kwargs):
+        from concurrent.futures import Future
+        fut = Future()
+        fut.set_result(fn(*args, **kwargs))
+        return fut
+
+
+def voxel_grid_low_mem_serial(input_path, r_voxel_size, q_voxel_size, max_q, aff_num_qs, energy,
+                              fill_bkg=False, smooth=0):
+    """The reference's generate_voxel_grid_low_mem (tools/voxelgrids.py:535-722), unmodified,
+    with its thread pool replaced by serial execution."""
+    import contextlib
+    import io
+    ref = load()
+    saved = ref.voxelgrids.ThreadPoolExecutor
+    ref.voxelgrids.ThreadPoolExecutor = _SerialExecutor
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            return ref.voxelgrids.generate_voxel_grid_low_mem(input_path, r_voxel_size, q_voxel_size, max_q,
+                                                              aff_num_qs, energy, "shim", fill_bkg=fill_bkg,
+                                                              smooth=smooth)
+    finally:
+        ref.voxelgrids.ThreadPoolExecutor = saved

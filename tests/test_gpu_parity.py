@@ -410,3 +410,100 @@ def test_simulate_config_driver_end_to_end(tmp_path):
     ref = o_det[np.ix_(kv, kh)]
     assert det_sum.shape == ref.shape
     assert np.abs(det_sum - ref).max() <= TOL_INT * ref.max()
+
+
+# ---- two-step command line, .npy hand-off, aff_num_qs > 1 ----
+def _write_xyz(path, coords, elements):
+    with open(path, "w") as fh:
+        fh.write("%d\ncluster\n" % len(coords))
+        for el, (x, y, z) in zip(elements, coords):
+            fh.write("%s %.17g %.17g %.17g\n" % (el, x, y, z))
+
+
+def _twostep_files(golden, tmp_path):
+    g = golden("twostep.npz")
+    folder = tmp_path / "structures"
+    folder.mkdir()
+    for k in range(2):
+        _write_xyz(str(folder / ("c%d.xyz" % k)), g["coords_%d" % k], g["elements_%d" % k])
+    return g, folder
+
+
+@pytest.mark.parametrize("aff_num_qs", [1, 3])
+def test_generate_voxel_grid_low_mem(golden, tmp_path, aff_num_qs):
+    g, folder = _twostep_files(golden, tmp_path)
+    args = (str(folder / "c0.xyz"), float(g["r"]), float(g["q"]), float(g["max_q"]), aff_num_qs, float(g["energy"]), "gen")
+    kw = dict(fill_bkg=bool(g["fill_bkg"]), smooth=int(g["smooth"]))
+    iq, qx, qy, qz = voxelgrids.generate_voxel_grid_low_mem(*args, **kw)
+    ref = g["iq_full_aff%d" % aff_num_qs]
+    assert iq.dtype == np.float64 and iq.shape == ref.shape
+    assert np.array_equal(qx, g["axis"]) and np.array_equal(qy, g["axis"]) and np.array_equal(qz, g["axis"])
+    assert np.array_equal(iq == 0, ref == 0)                    # never-hit voxels are exactly zero in both
+    assert np.abs(iq - ref).max() <= TOL_INT * ref.max()
+    # output_dir: the .npy hand-off files instead of a return value (voxelgrids.py:712-720)
+    out_dir = tmp_path / "out"
+    out_dir.mkdir()
+    assert voxelgrids.generate_voxel_grid_low_mem(*args, output_dir=str(out_dir), **kw) is None
+    assert np.array_equal(np.load(str(out_dir / "gen_output_files" / "gen_iq.npy")), iq)
+    assert np.array_equal(np.load(str(out_dir / "gen_output_files" / "gen_qz.npy")), g["axis"])
+    with pytest.raises(Exception, match="must be a .pdb or .xyz"):
+        voxelgrids.generate_voxel_grid_low_mem(str(folder / "c0.cif"), *args[1:], **kw)
+    with pytest.raises(Exception, match="Invalid aff_num_qs"):
+        voxelgrids.generate_voxel_grid_low_mem(*args[:4], 0, *args[5:], **kw)
+
+
+def test_shell_mask_bit_exact_against_numpy():
+    """gx_voxel_shell_scale picks exactly the voxels of (qr <= upper) & (qr > lower) with NumPy's qr."""
+    rng = np.random.default_rng(5)
+    for V, lo_hi in [(43, (0.7136, 1.4272)), (31, (0.0, 0.9)), (57, (1.1, 1.1000001))]:
+        axis = np.linspace(-2.1408, 2.1408, V)
+        mx, my, mz = np.meshgrid(axis, axis, axis)
+        qr = np.sqrt(mx ** 2 + my ** 2 + mz ** 2)
+        # put the bounds ON values qr takes, so <= / > decide on the last bit
+        lower, upper = np.sort(rng.choice(qr.reshape(-1), 2)) if lo_hi[0] == 0.0 else lo_hi
+        mask = (qr <= upper) & (qr > lower)
+        iq = torch.ones(V, V, V, dtype=torch.float32, device=engine.resolve_device())
+        engine.scale_shell(iq, axis, lower, upper, 2.0, iq.device)
+        assert np.array_equal(iq.cpu().numpy() == 2.0, mask)
+
+
+def test_two_step_drivers_npy_handoff(golden, tmp_path):
+    """voxelgridmaker (folder of structures -> averaged, cropped, f0-weighted .npy) then detectormaker
+    (.npy -> detector image) against the reference fixture / the oracle (old_modules/*.py)."""
+    from giwaxsim_b200 import detectormaker, voxelgridmaker
+    g, folder = _twostep_files(golden, tmp_path)
+    out_dir = tmp_path / "work"
+    out_dir.mkdir()
+    cfg = {"input_folder": str(folder), "filetype": "xyz", "gen_name": "mix", "r_voxel_size": str(float(g["r"])),
+           "q_voxel_size": str(float(g["q"])), "aff_num_qs": "1", "energy": str(float(g["energy"])),
+           "max_q": str(float(g["max_q"])), "output_dir": str(out_dir), "smooth": str(int(g["smooth"])),
+           "fill_bkg": "True"}
+    iq, qx, qy, qz = voxelgridmaker.main(cfg)
+    files = out_dir / "mix_output_files"
+    assert np.array_equal(np.load(str(files / "mix_iq.npy")), iq) and (files / "mix_config.txt").exists()
+    assert np.array_equal(np.load(str(files / "mix_qx.npy")), g["two_step_axis"])
+    ref = g["two_step_iq"]
+    assert iq.shape == ref.shape and np.abs(iq - ref).max() <= TOL_INT * ref.max()
+
+    # second step from the REFERENCE's grid on disk (either producer's files must work)
+    np.save(str(files / "mix_iq.npy"), ref)
+    dcfg = {"iq_output_folder": str(files), "gen_name": "mix", "max_q": "1.5", "num_pixels": "65",
+            "angle_init_val1": "90", "angle_init_val2": "90", "angle_init_val3": "90", "angle_init_ax1": "psi",
+            "angle_init_ax2": "phi", "angle_init_ax3": "psi", "psi_start": "60", "psi_end": "90", "psi_num": "4",
+            "phi_start": "0", "phi_end": "150", "phi_num": "5", "theta_start": "0", "theta_end": "3",
+            "theta_num": "2", "mirror": "True"}
+    det_sum, det_h, det_v = detectormaker.main(dcfg)
+    sub = files / "mix_det_sum"
+    assert np.array_equal(np.load(str(sub / "mix_det_sum.npy")), det_sum) and (sub / "mix_config.txt").exists()
+    assert np.array_equal(np.load(str(sub / "mix_det_h.npy")), det_h)
+    psis, phis, thetas = np.linspace(60, 90, 4), np.linspace(0, 150, 5), np.linspace(0, 3, 2)
+    ones = lambda a: np.ones_like(a) / len(a)
+    acc, o_h, o_v = ox.detectormaker(ref, qx, qy, qz, 65, 1.5, (90.0, 90.0, 90.0), ("psi", "phi", "psi"),
+                                     psis, ones(psis), phis, ones(phis), thetas, ones(thetas), raw=True)
+    want = ox.detector_epilogue_two_step(acc, mirror=True)
+    assert np.array_equal(det_h, o_h) and np.abs(det_sum - want).max() <= TOL_INT * want.max()
+    # a second run must not overwrite the first result folder (old_modules/detectormaker.py:60-65)
+    detectormaker.main(dict(dcfg, mirror="False"))
+    assert (files / "mix_det_sum1" / "mix_det_sum.npy").exists()
+    with pytest.raises(Exception, match="Path does not exist"):
+        detectormaker.main(dict(dcfg, iq_output_folder=str(tmp_path / "nowhere")))

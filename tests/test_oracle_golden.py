@@ -116,3 +116,20 @@ def test_pm6_oracle_end_to_end_reproduces_fixture(golden):
                                  ones(g["phis"]), g["thetas"], ones(g["thetas"]), threads=os.cpu_count())
     quad = det[np.ix_(np.where(v >= 0)[0], np.where(h >= 0)[0])]
     assert np.abs(quad - g["det_quadrant_oracle"]).max() <= 1e-9 * g["det_quadrant_oracle"].max()
+
+
+def test_two_step_matches_reference_fixture(golden):
+    """generate_voxel_grid_low_mem (aff_num_qs 1 and 3) and the old_modules/voxelgridmaker.py
+    crop / average / f0 loop, restated in the oracle, against the live-reference fixture."""
+    g = golden("twostep.npz")
+    kw = dict(fill_bkg=bool(g["fill_bkg"]), smooth=int(g["smooth"]))
+    r, q, max_q, energy = float(g["r"]), float(g["q"]), float(g["max_q"]), float(g["energy"])
+    s0 = (g["coords_0"], g["elements_0"])
+    s1 = (g["coords_1"], g["elements_1"])
+    iq1, ax, _, _ = ox.voxel_grid_low_mem(*s0, r, q, max_q, 1, energy, **kw)
+    assert np.array_equal(ax, g["axis"]) and np.array_equal(iq1, g["iq_full_aff1"])
+    iq3 = ox.voxel_grid_low_mem(*s0, r, q, max_q, 3, energy, **kw)[0]
+    assert np.array_equal(iq3, g["iq_full_aff3"])
+    assert ox.most_common_element(s0[1]) == str(g["element"])
+    two, tax, _, _ = ox.two_step_voxelgrid([s0, s1], r, q, max_q, 1, energy, **kw)
+    assert np.array_equal(tax, g["two_step_axis"]) and np.array_equal(two, g["two_step_iq"])

@@ -78,3 +78,75 @@ def test_slabmaker_bit_exact(name, size, cell):
     assert np.array_equal(c0, rc0) and np.array_equal(e0, re0)
     o_coords, o_el = ox.slabmaker(c0, e0, *size, *cell)
     assert np.array_equal(o_coords, r_coords) and np.array_equal(o_el, r_el)
+
+
+# ---- two-step command line and the aff_num_qs > 1 branch ----
+def _write_xyz(path, coords, elements):
+    with open(path, "w") as fh:
+        fh.write("%d\ncluster\n" % len(coords))
+        for el, (x, y, z) in zip(elements, coords):
+            fh.write("%s %.17g %.17g %.17g\n" % (el, x, y, z))
+
+
+@pytest.mark.parametrize("aff_num_qs,fill_bkg,smooth", [(1, True, 3), (3, False, 0), (2, True, 2)])
+def test_voxel_grid_low_mem_bit_exact(tmp_path, aff_num_qs, fill_bkg, smooth):
+    coords, elements = _cluster(n=120)
+    path = str(tmp_path / "cluster.xyz")
+    _write_xyz(path, coords, elements)
+    r, q, max_q = 0.3, 0.16, 1.5
+    a = ref_shim.voxel_grid_low_mem_serial(path, r, q, max_q, aff_num_qs, 12700.0, fill_bkg, smooth)
+    c, e = ox.read_structure(path)
+    b = ox.voxel_grid_low_mem(c, e, r, q, max_q, aff_num_qs, 12700.0, fill_bkg, smooth)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    if aff_num_qs > 1:
+        # what the reference returns is the LAST shell's grid doubled inside that shell: earlier
+        # passes are overwritten (voxelgrids.py:699), so running only the last pass is equivalent
+        max_q_diag = np.sqrt(2) * max_q
+        max_q_diag = max_q_diag + max_q_diag % q
+        step = max_q_diag / aff_num_qs
+        q_val = 0.5 * step + (aff_num_qs - 1) * step
+        f0 = ox.f0_values(q_val, e)
+        f = np.array([f0[x] for x in e]) + np.array([complex(*ox.ftable.f1_f2(x)) for x in e])
+        last, axis, _ = ox._whole_grid(c, f, r, q, max_q, fill_bkg, smooth)
+        mx, my, mz = np.meshgrid(axis, axis, axis)
+        qr = np.sqrt(mx ** 2 + my ** 2 + mz ** 2)
+        shell = (qr <= q_val + step / 2) & (qr > q_val - step / 2)
+        assert np.array_equal(a[0], np.where(shell, 2 * last, last))
+
+
+def test_f0_tables_match_reference():
+    ref = ref_shim.load()
+    from giwaxsim_b200.tools import utilities as ours
+    aff = ref.utilities.aff_dict
+    for el, coeff in ox.AFF.items():
+        assert tuple(aff[el]) == coeff
+    for el, coeff in ours.CROMER_MANN.items():
+        assert tuple(aff[el]) == coeff and ours.ATOMIC_NUMBER[el] == ref.utilities.ptable[el]
+    els = ["C", "H", "S", "O", "F", "N"]
+    for q_val in (0.0, 0.37, 2.9):
+        a = ref.utilities.get_element_f0_dict(q_val, els)
+        assert a == ox.f0_values(q_val, els) == ours.get_element_f0_dict(q_val, els)
+
+
+def test_most_common_element_and_two_step_average(tmp_path):
+    ref = ref_shim.load()
+    from giwaxsim_b200.tools import utilities as ours
+    paths = []
+    for k, seed in enumerate((3, 4)):
+        coords, elements = _cluster(seed=seed, n=90)
+        paths.append(str(tmp_path / ("c%d.xyz" % k)))
+        _write_xyz(paths[-1], coords, elements)
+    for p in paths:
+        assert ref.utilities.most_common_element(p) == ours.most_common_element(p) \
+            == ox.most_common_element(ox.read_structure(p)[1])
+    # the reference's driver loop (old_modules/voxelgridmaker.py:33-68) on its own functions
+    r, q, max_q = 0.3, 0.16, 1.5
+    total = None
+    for i, p in enumerate(paths):
+        iq, qx, qy, qz = ref_shim.voxel_grid_low_mem_serial(p, r, q, max_q, 1, 12700.0, True, 2)
+        small, qxs, qys, qzs = ref.voxelgrids.downselect_voxelgrid(iq, qx, qy, qz, max_q)
+        total = small if i == 0 else total + small
+    total = total / len(paths)
+    want = ref.voxelgrids.add_f0_q_3d(total, qxs, qys, qzs, ref.utilities.most_common_element(paths[0]))
+    got = ox.two_step_voxelgrid([ox.read_structure(p) for p in paths], r, q, max_q, 1, 12700.0, True, 2)
+    assert np.array_equal(got[0], want) and np.array_equal(got[1], qxs)
