@@ -444,7 +444,9 @@ def test_generate_voxel_grid_low_mem(golden, tmp_path, aff_num_qs):
     out_dir = tmp_path / "out"
     out_dir.mkdir()
     assert voxelgrids.generate_voxel_grid_low_mem(*args, output_dir=str(out_dir), **kw) is None
-    assert np.array_equal(np.load(str(out_dir / "gen_output_files" / "gen_iq.npy")), iq)
+    on_disk = np.load(str(out_dir / "gen_output_files" / "gen_iq.npy"))
+    # a second run: fp32 atomic accumulation order differs, so equal only to fp32 round-off
+    assert on_disk.dtype == np.float64 and np.abs(on_disk - iq).max() <= 1e-5 * iq.max()
     assert np.array_equal(np.load(str(out_dir / "gen_output_files" / "gen_qz.npy")), g["axis"])
     with pytest.raises(Exception, match="must be a .pdb or .xyz"):
         voxelgrids.generate_voxel_grid_low_mem(str(folder / "c0.cif"), *args[1:], **kw)
