@@ -59,42 +59,57 @@ __device__ __forceinline__ int atom_y_pixel_int(double x, double y, double s, do
     return qi;
 }
 
-// Count atoms [beg,end) of one z-row into the species counters: word plane
-// sp>>1 (stride NP words), 16-bit field sp&1.  Four atoms per thread and
-// iteration, loads first, and NO branch around an atom: the tail of the row
-// re-reads its last atom (clamped index) and only the final ATOMS is predicated,
-// so the four ~10-deep fp64 dependency chains interleave instead of running one
-// after the other.
+// U atoms per thread, loads first, NO branch around an atom: an index past the row end re-reads the
+// last atom (clamped) and only the final ATOMS is neutralised (adds 0 to word 0), so the U ~10-deep
+// fp64 dependency chains interleave instead of running one after the other.
+template <int U, bool TAIL>
+__device__ __forceinline__ void scatter_batch(const ProjArgs &a, int i0, int end, int nt, double s, double c,
+                                              double shift, double r, double inv_r, uint32_t *words, int NP)
+{
+    const int N = a.N, last = end - 1;
+    double x[U], y[U];
+    unsigned sp[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int i = TAIL ? min(i0 + u * nt, last) : i0 + u * nt;
+        x[u] = ld_stream_f64(a.xs + i);
+        y[u] = ld_stream_f64(a.ys + i);
+        sp[u] = ld_stream_u8(a.species + i);
+    }
+    int q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) q[u] = atom_y_pixel_int(x[u], y[u], s, c, shift, r, inv_r);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const bool ok = (!TAIL || i0 + u * nt < end) && ((unsigned)q[u] < (unsigned)N);
+        const unsigned word = ok ? (sp[u] >> 1) * NP + q[u] : 0u;
+        const unsigned inc = ok ? 1u << ((sp[u] & 1u) * 16) : 0u;
+        atomicAdd(&words[word], inc);
+    }
+}
+
+// Count atoms [beg,end) of one z-row into the species counters: word plane sp>>1 (stride NP
+// words), 16-bit field sp&1.  Whole batches of 4 x blockDim atoms first, then the remainder in
+// batches of 2 and 1 (a row of 2441 atoms costs 2 x 4 + 1 + a partial single instead of 3 x 4:
+// the clamped tail of a 4-batch did the full arithmetic for atoms that do not exist).
 __device__ __forceinline__ void scatter_species(const ProjArgs &a, int beg, int end, double s, double c,
                                                 double shift, uint32_t *words, int NP)
 {
-    const int N = a.N, tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x, nt = blockDim.x;
     const double r = a.r, inv_r = 1.0 / a.r;
-    constexpr int U = 4;
-    const int last = end - 1;
-    for (int i0 = beg + tid; i0 < end; i0 += U * nt) {
-        double x[U], y[U];
-        unsigned sp[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = min(i0 + u * nt, last);
-            x[u] = ld_stream_f64(a.xs + i);
-            y[u] = ld_stream_f64(a.ys + i);
-            sp[u] = ld_stream_u8(a.species + i);
-        }
-        int q[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) q[u] = atom_y_pixel_int(x[u], y[u], s, c, shift, r, inv_r);
-        // no branch here either: an atom that does not count (row tail, pixel outside the grid)
-        // adds 0 to word 0
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const bool ok = (i0 + u * nt < end) && ((unsigned)q[u] < (unsigned)N);
-            const unsigned word = ok ? (sp[u] >> 1) * NP + q[u] : 0u;
-            const unsigned inc = ok ? 1u << ((sp[u] & 1u) * 16) : 0u;
-            atomicAdd(&words[word], inc);
-        }
+    int i0 = beg + tid;
+    int left = end - beg;                                   // atoms not yet claimed by a batch (CTA-uniform)
+    for (; left >= 4 * nt; left -= 4 * nt, i0 += 4 * nt)
+        scatter_batch<4, false>(a, i0, end, nt, s, c, shift, r, inv_r, words, NP);
+    if (left >= 2 * nt) {
+        scatter_batch<2, false>(a, i0, end, nt, s, c, shift, r, inv_r, words, NP);
+        left -= 2 * nt; i0 += 2 * nt;
     }
+    if (left >= nt) {
+        scatter_batch<1, false>(a, i0, end, nt, s, c, shift, r, inv_r, words, NP);
+        left -= nt; i0 += nt;
+    }
+    if (i0 < end) scatter_batch<1, false>(a, i0, end, nt, s, c, shift, r, inv_r, words, NP);   // per-thread tail
 }
 
 // value of a pixel relative to the pedestal P:
