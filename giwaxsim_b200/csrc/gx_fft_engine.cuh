@@ -182,6 +182,68 @@ template <> struct GxDft<16> {
     }
 };
 
+// ---- band-limited last pass ------------------------------------------------
+// The last DIF pass (S = 1) of a 16-16-16 schedule decides the MOST significant digit k2 of the
+// output index k = k0 + 16 k1 + 256 k2.  A caller that keeps only the coefficients |k| < 512
+// around DC (k2 in {0, 1} or {14, 15}; the slice kernels keep ~ +-290 of 4096) needs at most
+// X[0], X[1], X[14], X[15] of each 16-point butterfly, and for |k| < 256 only X[0] and X[15].
+// With p_n = v[n] + v[16-n], m_n = v[n] - v[16-n] (n = 1..7) and W = e^{-2 pi i/16}:
+//   X[0]  = v0 + v8 + sum p_n
+//   X[+-1] = A -+ iB,   A = (v0 - v8) + c1 (p1 - p7) + h (p2 - p6) + s1 (p3 - p5)
+//                       B = s1 (m1 + m7) + h (m2 + m6) + c1 (m3 + m5) + m4
+//   X[+-2] = A2 -+ iB2, A2 = (v0 + v8 - p4) + h ((p1 + p7) - (p3 + p5))
+//                       B2 = (m2 - m6) + h ((m1 + m3) - (m5 + m7))
+// 38 complex additions + 7 real-by-complex multiply-adds for X[0], X[15] (76 flops instead of the
+// ~170 of the full radix-16 butterfly, 2 stores instead of 16); `wide` adds X[1] and X[14].
+// Results go to the slots the full pass would use (base + k2); the other slots keep stale data.
+GX_HD void gx_dft16_lowband(const float2 *v, bool wide, float2 *sb)
+{
+    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
+    const float h = 0.70710678118654752440f;
+    float2 p[8], m[8];
+#pragma unroll
+    for (int n = 1; n < 8; ++n) { p[n] = gx_cadd(v[n], v[16 - n]); m[n] = gx_csub(v[n], v[16 - n]); }
+    const float2 e = gx_cadd(v[0], v[8]), o = gx_csub(v[0], v[8]);
+    const float2 x0 = gx_cadd(gx_cadd(gx_cadd(e, p[4]), gx_cadd(p[1], p[7])),
+                              gx_cadd(gx_cadd(p[2], p[6]), gx_cadd(p[3], p[5])));
+    const float2 d17 = gx_csub(p[1], p[7]), d26 = gx_csub(p[2], p[6]), d35 = gx_csub(p[3], p[5]);
+    const float2 A = make_float2(o.x + c1 * d17.x + h * d26.x + s1 * d35.x, o.y + c1 * d17.y + h * d26.y + s1 * d35.y);
+    const float2 a17 = gx_cadd(m[1], m[7]), a26 = gx_cadd(m[2], m[6]), a35 = gx_cadd(m[3], m[5]);
+    const float2 B = make_float2(m[4].x + s1 * a17.x + h * a26.x + c1 * a35.x, m[4].y + s1 * a17.y + h * a26.y + c1 * a35.y);
+    sb[gx_phys(0)] = x0;
+    sb[gx_phys(15)] = make_float2(A.x - B.y, A.y + B.x);            // A + iB
+    if (wide) {
+        sb[gx_phys(1)] = make_float2(A.x + B.y, A.y - B.x);         // A - iB
+        const float2 s17 = gx_cadd(p[1], p[7]), s35 = gx_cadd(p[3], p[5]);
+        const float2 t = gx_csub(s17, s35), u = gx_csub(e, p[4]);
+        const float2 A2 = make_float2(u.x + h * t.x, u.y + h * t.y);
+        const float2 w = gx_csub(gx_cadd(m[1], m[3]), gx_cadd(m[5], m[7])), g = gx_csub(m[2], m[6]);
+        const float2 B2 = make_float2(g.x + h * w.x, g.y + h * w.y);
+        sb[gx_phys(14)] = make_float2(A2.x - B2.y, A2.y + B2.x);    // A2 + iB2
+    }
+}
+
+// Last pass of the 16-16-16 transform for a caller that reads only coefficients
+// k in [0, khi) and [M + klo, M) with klo >= -512, khi <= 512 (checked by the caller).
+// Thread t owns butterfly (k0, k1) = (t & 15, t >> 4): the few butterflies that need X[1]
+// (k0 + 16 k1 + 256 < khi) or X[14] (k0 + 16 k1 + 3584 >= M + klo) sit in the first / last warps.
+template <int M>
+GX_HD void gx_fft_lastpass16_lowband(float2 *s, int klo, int khi, int tid, int nthreads)
+{
+    constexpr int NBFLY = M / 16;
+    for (int w = tid; w < NBFLY; w += nthreads) {
+        const int k0 = w & 15, k1 = w >> 4;
+        const int low = k0 + 16 * k1;
+        const int blk = 16 * k0 + k1;                      // butterfly index of the generic pass (base = 16 blk)
+        float2 *sb = s + gx_phys(16 * blk);
+        float2 v[16];
+#pragma unroll
+        for (int n = 0; n < 16; ++n) v[n] = sb[gx_phys(n)];
+        const bool wide = (low + 256 < khi) || (low + 3584 >= M + klo);
+        gx_dft16_lowband(v, wide, sb);
+    }
+}
+
 // ---- twiddles of one butterfly ---------------------------------------------
 // v[k] *= W^{t k}, k = 1..R-1, table row k-1 at twt[(k-1)*S].
 // TWP == 0: every factor is read from the table (fp32-rounded exact values).

@@ -69,7 +69,10 @@ __device__ __forceinline__ void active_band(const ProjArgs &a, int p, int &za, i
 // 64-register cap).  px arrives holding the prefetched (d, my) of each pixel and leaves holding v.
 // NPAIR > 0: number of counter planes known at compile time (f-values in registers);
 // NPAIR == 0: any number of planes, f-values re-read from shared memory.
-template <int NPAIR, int NB0, int R0, int S0, int NT>
+// EXACT: N == S0 * R0 (power-of-two grid, no Bluestein padding) and NB0 * NT == S0: every pixel index is
+// in range, so clamps, range selects and the butterfly-count test disappear and all counter loads
+// become one base register plus immediates.
+template <int NPAIR, int NB0, int R0, int S0, int NT, bool EXACT>
 __device__ __forceinline__ void flush_finish(float2 (&px)[NB0][R0], const uint32_t *words, int NP,
                                              const float2 *s_table, const float2 (&f)[GX_MAX_SPECIES], int npair,
                                              int tid, int N, float af_re, float af_im, float mzv)
@@ -77,7 +80,7 @@ __device__ __forceinline__ void flush_finish(float2 (&px)[NB0][R0], const uint32
 #pragma unroll
     for (int i = 0; i < NB0; ++i) {
         const int t = tid + i * NT;
-        if (t >= S0) {
+        if (!EXACT && t >= S0) {
 #pragma unroll
             for (int n = 0; n < R0; ++n) px[i][n] = make_float2(0.f, 0.f);
             continue;
@@ -87,14 +90,14 @@ __device__ __forceinline__ void flush_finish(float2 (&px)[NB0][R0], const uint32
 #pragma unroll
         for (int n = 0; n < R0; ++n) {
             const int y = t + S0 * n;
-            const int yy = min(y, N - 1);
+            const int yy = EXACT ? y : min(y, N - 1);
             float sx = 0.f, sy = 0.f;
             if (NPAIR > 0) {
 #pragma unroll
                 for (int w = 0; w < NPAIR; ++w) {
                     // counts -> fp32 through the 2^23 mantissa trick (LOP/PRMT + FADD, no I2F)
                     const uint32_t cnt = words[w * NP + yy];
-                    const float n0 = __uint_as_float(0x4B000000u | (cnt & 0xffffu)) - 8388608.f;
+                    const float n0 = __uint_as_float(__byte_perm(cnt, 0x4B000000u, 0x7610)) - 8388608.f;
                     const float n1 = __uint_as_float(__byte_perm(cnt, 0x4B000000u, 0x7632)) - 8388608.f;
                     sx = fmaf(n1, f[2 * w + 1].x, fmaf(n0, f[2 * w].x, sx));
                     sy = fmaf(n1, f[2 * w + 1].y, fmaf(n0, f[2 * w].y, sy));
@@ -110,7 +113,7 @@ __device__ __forceinline__ void flush_finish(float2 (&px)[NB0][R0], const uint32
                 }
             }
             const float2 dm = px[i][n];
-            const float m = (y < N) ? mzv * dm.y : 0.f;
+            const float m = (EXACT || y < N) ? mzv * dm.y : 0.f;
             px[i][n] = make_float2(fmaf(dm.x, af_re, sx) * m, fmaf(dm.x, af_im, sy) * m);
         }
     }
@@ -138,7 +141,9 @@ slice_rows_fused(FusedArgs fa)
     __shared__ float2 s_table[GX_MAX_SPECIES];
     const ProjArgs &a = fa.proj;
     const int p = blockIdx.x, z = blockIdx.y;
-    const int N = a.N, tid = threadIdx.x;
+    const int N = BLUE ? a.N : M;                          // power-of-two grids are transformed at their own length
+    const int tid = threadIdx.x;
+    constexpr bool EXACT = !BLUE && NB0 * NT == S0;        // every pixel index t + S0 n is a pixel of the row
     // every per-rotation / per-row scalar is requested before the first branch, so the CTA
     // pays one L2 round trip for all of them instead of one per dependent use
     const int z_min = __ldg(a.bbox + 4 * p + 2), z_max = __ldg(a.bbox + 4 * p + 3);
@@ -176,10 +181,10 @@ slice_rows_fused(FusedArgs fa)
 #pragma unroll
                 for (int n = 0; n < R0; ++n) {
                     const int t = tid + i * NT, y = t + S0 * n;
-                    px[i][n] = __ldg(dmy + min(y, N - 1));            // clamped: pixels beyond N are zeroed later
+                    px[i][n] = __ldg(dmy + (EXACT ? y : min(y, N - 1)));   // clamped: pixels beyond N are zeroed later
                 }
             __syncthreads();
-            flush_finish<NPAIR, NB0, R0, S0, NT>(px, words, NP, s_table, fa.ftab, npair, tid, N, fa.af_re, fa.af_im, mzv);
+            flush_finish<NPAIR, NB0, R0, S0, NT, EXACT>(px, words, NP, s_table, fa.ftab, npair, tid, N, fa.af_re, fa.af_im, mzv);
             __syncthreads();   // every counter read is done before buf is written
             finished = true;
         } else {
@@ -280,7 +285,21 @@ slice_rows_fused(FusedArgs fa)
         }
     }
     __syncthreads();
-    gx_dft_block<L, 1, 0, BLUE ? 1 : 0, true>(buf, fa.lay, fa.plan, tid, NT);
+    // only the coefficients jlo - N/2 <= k < jhi - N/2 are read below: when they lie within +-512 of DC
+    // (always for the 4096 grids of the path: ~ +-290) the last pass computes 2 (a few butterflies: 4)
+    // of its 16 outputs per butterfly
+    bool full = true;
+    if constexpr (L == 12 && !BLUE) {
+        const int klo = jlo - M / 2, khi = jhi - M / 2;
+        if (klo >= -512 && khi <= 512) {
+            gx_fft_pass<16, 16, M, 1, 0, false>(buf, fa.plan + fa.lay.tw_off[1], tid, NT);
+            __syncthreads();
+            gx_fft_lastpass16_lowband<M>(buf, klo, khi, tid, NT);
+            __syncthreads();
+            full = false;
+        }
+    }
+    if (full) gx_dft_block<L, 1, 0, BLUE ? 1 : 0, true>(buf, fa.lay, fa.plan, tid, NT);
 
     // kept q-columns only; shifted column j holds unshifted coefficient j - N/2 (mod N)
     float2 *dst = fa.work + ((size_t)p * N + z) * fa.KC;

@@ -53,3 +53,23 @@ extern "C" int emul_offsets_ok()
            gx_fft_offsets_ok<8>() & gx_fft_offsets_ok<9>() & gx_fft_offsets_ok<10>() & gx_fft_offsets_ok<11>() &
            gx_fft_offsets_ok<12>() & gx_fft_offsets_ok<13>();
 }
+
+// 4096-point transform with the band-limited last pass (gx_fft_lastpass16_lowband): passes 0 and 1
+// as usual, then only X[0], X[15] (and X[1], X[14] where the band needs them) of every last-pass
+// butterfly.  out[k - klo] for klo <= k < khi (negative k = coefficient M + k).
+extern "C" int emul_dft_lowband(const float *plan, const float *in, float *out, int klo, int khi, int nthreads)
+{
+    constexpr int L = 12, M = 1 << L;
+    GxFftLayout g = gx_fft_layout(M);
+    if (klo < -512 || khi > 512) return -1;
+    const float2 *p = reinterpret_cast<const float2 *>(plan);
+    const float2 *x = reinterpret_cast<const float2 *>(in);
+    float2 *o = reinterpret_cast<float2 *>(out);
+    std::vector<float2> s(gx_phys_len(M));
+    for (int n = 0; n < M; ++n) s[gx_phys(n)] = x[n];
+    gx_fft_pass<16, M / 16, M, 1, 0, false>(s.data(), p + g.tw_off[0], 0, 1);
+    gx_fft_pass<16, M / 256, M, 1, 0, false>(s.data(), p + g.tw_off[1], 0, 1);
+    for (int t = 0; t < nthreads; ++t) gx_fft_lastpass16_lowband<M>(s.data(), klo, khi, t, nthreads);
+    for (int k = klo; k < khi; ++k) o[k - klo] = gx_dft_result<L, 0>(s.data(), g, p, k < 0 ? k + M : k);
+    return 0;
+}

@@ -67,6 +67,23 @@ def test_fft_engine_host_build_matches_numpy(fft_emul, N):
     assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("klo,khi,nthreads", [(-288, 288, 256), (-200, 203, 256), (-512, 512, 256), (-1, 1, 64),
+                                              (-300, 17, 1), (-256, 256, 256), (-257, 257, 512)])
+def test_fft_lowband_last_pass_matches_numpy(fft_emul, klo, khi, nthreads):
+    """Band-limited last pass of the 4096-point transform (only X[0], X[15] (+ X[1], X[14]) of every
+    last-pass butterfly): every coefficient of the band equals numpy's."""
+    N = 4096
+    plan = np.zeros(_lib.cdll().gx_fft_plan_bytes(N) // 4, np.float32)
+    _lib.call("gx_fft_plan_fill", N, _lib.ptr(plan))
+    rng = np.random.default_rng(khi - klo)
+    x = (rng.normal(size=N) + 1j * rng.normal(size=N) + 3.0).astype(np.complex64)
+    out = np.zeros(khi - klo, np.complex64)
+    assert fft_emul.emul_dft_lowband(_lib.ptr(plan), _lib.ptr(x), _lib.ptr(out), klo, khi, nthreads) == 0
+    ref = np.fft.fft(x.astype(np.complex128))[np.arange(klo, khi) % N]
+    assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
+    assert fft_emul.emul_dft_lowband(_lib.ptr(plan), _lib.ptr(x), _lib.ptr(out), -513, 10, 256) == -1
+
+
 def test_orientation_matrices_match_oracle_chain():
     gx, gy, gz, _, _ = ox.detector_base(33, 2.0, (90.0, 90.0, 90.0), ("psi", "phi", "psi"))
     psis, phis, thetas = np.linspace(75, 90, 4), np.linspace(0, 179, 5), np.linspace(0, 1, 2)
