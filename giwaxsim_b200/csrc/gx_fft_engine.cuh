@@ -227,15 +227,16 @@ GX_HD void gx_dft16_lowband(const float2 *v, bool wide, float2 *sb)
 // k in [0, khi) and [M + klo, M) with klo >= -512, khi <= 512 (checked by the caller).
 // Thread t owns butterfly (k0, k1) = (t & 15, t >> 4): the few butterflies that need X[1]
 // (k0 + 16 k1 + 256 < khi) or X[14] (k0 + 16 k1 + 3584 >= M + klo) sit in the first / last warps.
-template <int M>
+template <int M, int NBUF = 1, int BUFSTRIDE = 0>
 GX_HD void gx_fft_lastpass16_lowband(float2 *s, int klo, int khi, int tid, int nthreads)
 {
     constexpr int NBFLY = M / 16;
-    for (int w = tid; w < NBFLY; w += nthreads) {
-        const int k0 = w & 15, k1 = w >> 4;
+    for (int w = tid; w < NBUF * NBFLY; w += nthreads) {
+        const int buf = w / NBFLY, b = w - buf * NBFLY;
+        const int k0 = b & 15, k1 = b >> 4;
         const int low = k0 + 16 * k1;
         const int blk = 16 * k0 + k1;                      // butterfly index of the generic pass (base = 16 blk)
-        float2 *sb = s + gx_phys(16 * blk);
+        float2 *sb = s + buf * BUFSTRIDE + gx_phys(16 * blk);
         float2 v[16];
 #pragma unroll
         for (int n = 0; n < 16; ++n) v[n] = sb[gx_phys(n)];

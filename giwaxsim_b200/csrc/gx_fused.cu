@@ -67,12 +67,13 @@ __device__ __forceinline__ void active_band(const ProjArgs &a, int p, int &za, i
 // pixel-outer / plane-inner so that every counter load is independent of every other (the
 // plane-outer accumulation into px serialised on the LDS latency and spilled px under the
 // 64-register cap).  px arrives holding the prefetched (d, my) of each pixel and leaves holding v.
-// NPAIR > 0: number of counter planes known at compile time (f-values in registers);
-// NPAIR == 0: any number of planes, f-values re-read from shared memory.
+// NSP > 0: number of species known at compile time (planes = (NSP + 1) / 2, f-values constant-bank
+//          operands, and the unused upper half of the last plane of an odd count costs nothing);
+// NSP == 0: any number of planes, f-values re-read from shared memory.
 // EXACT: N == S0 * R0 (power-of-two grid, no Bluestein padding) and NB0 * NT == S0: every pixel index is
 // in range, so clamps, range selects and the butterfly-count test disappear and all counter loads
 // become one base register plus immediates.
-template <int NPAIR, int NB0, int R0, int S0, int NT, bool EXACT>
+template <int NSP, int NB0, int R0, int S0, int NT, bool EXACT>
 __device__ __forceinline__ void flush_finish(float2 (&px)[NB0][R0], const uint32_t *words, int NP,
                                              const float2 *s_table, const float2 (&f)[GX_MAX_SPECIES], int npair,
                                              int tid, int N, float af_re, float af_im, float mzv)
@@ -86,21 +87,25 @@ __device__ __forceinline__ void flush_finish(float2 (&px)[NB0][R0], const uint32
             continue;
         }
         // no branch per pixel (a pixel beyond N reads a clamped address and is zeroed by a select):
-        // the R0 x NPAIR counter loads are then free to be issued back to back
+        // the R0 x planes counter loads are then free to be issued back to back
 #pragma unroll
         for (int n = 0; n < R0; ++n) {
             const int y = t + S0 * n;
             const int yy = EXACT ? y : min(y, N - 1);
             float sx = 0.f, sy = 0.f;
-            if (NPAIR > 0) {
+            if (NSP > 0) {
 #pragma unroll
-                for (int w = 0; w < NPAIR; ++w) {
-                    // counts -> fp32 through the 2^23 mantissa trick (LOP/PRMT + FADD, no I2F)
+                for (int w = 0; w < (NSP + 1) / 2; ++w) {
+                    // counts -> fp32 through the 2^23 mantissa trick (PRMT + FADD, no I2F)
                     const uint32_t cnt = words[w * NP + yy];
                     const float n0 = __uint_as_float(__byte_perm(cnt, 0x4B000000u, 0x7610)) - 8388608.f;
-                    const float n1 = __uint_as_float(__byte_perm(cnt, 0x4B000000u, 0x7632)) - 8388608.f;
-                    sx = fmaf(n1, f[2 * w + 1].x, fmaf(n0, f[2 * w].x, sx));
-                    sy = fmaf(n1, f[2 * w + 1].y, fmaf(n0, f[2 * w].y, sy));
+                    sx = fmaf(n0, f[2 * w].x, sx);
+                    sy = fmaf(n0, f[2 * w].y, sy);
+                    if (2 * w + 1 < NSP) {
+                        const float n1 = __uint_as_float(__byte_perm(cnt, 0x4B000000u, 0x7632)) - 8388608.f;
+                        sx = fmaf(n1, f[2 * w + 1].x, sx);
+                        sy = fmaf(n1, f[2 * w + 1].y, sy);
+                    }
                 }
             } else {
                 for (int w = 0; w < npair; ++w) {
@@ -124,9 +129,9 @@ __device__ __forceinline__ void flush_finish(float2 (&px)[NB0][R0], const uint32
 // species counts of exactly those pixels, completes them in registers and feeds
 // them straight into its radix-R0 butterfly: the finished row is never written
 // to shared memory in natural order and never read back by pass 0.
-// NPAIR: number of species-counter planes fixed at compile time (1..3; the flush is then fully
+// NSP: number of species fixed at compile time (1..6; the flush is then fully
 // unrolled with the f-values as constant-bank operands), 0 = any number (generic loop).
-template <int L, bool SPECIES, bool BLUE, int NPAIR>
+template <int L, bool SPECIES, bool BLUE, int NSP>
 __global__ void __launch_bounds__(PROJ_THREADS, (L >= 13) ? 2 : GX_F1_MINBLOCKS)
 slice_rows_fused(FusedArgs fa)
 {
@@ -184,7 +189,7 @@ slice_rows_fused(FusedArgs fa)
                     px[i][n] = __ldg(dmy + (EXACT ? y : min(y, N - 1)));   // clamped: pixels beyond N are zeroed later
                 }
             __syncthreads();
-            flush_finish<NPAIR, NB0, R0, S0, NT, EXACT>(px, words, NP, s_table, fa.ftab, npair, tid, N, fa.af_re, fa.af_im, mzv);
+            flush_finish<NSP, NB0, R0, S0, NT, EXACT>(px, words, NP, s_table, fa.ftab, npair, tid, N, fa.af_re, fa.af_im, mzv);
             __syncthreads();   // every counter read is done before buf is written
             finished = true;
         } else {
@@ -345,7 +350,21 @@ slice_cols_fused(FusedArgs fa)
         smem[cc * BS + gx_phys(n)] = v;
     }
     __syncthreads();
-    gx_dft_block<L, TC, BS, BLUE ? 1 : 0>(smem, fa.lay, fa.plan, tid, nt);
+    // only the q-rows row_lo - N/2 <= kz < row_hi - N/2 are binned below: band-limited last pass as in F1
+    bool full = true;
+    if constexpr (L == 12 && !BLUE) {
+        const int klo = fa.row_lo - M / 2, khi = fa.row_hi - M / 2;
+        if (klo >= -512 && khi <= 512) {
+            gx_fft_pass<16, M / 16, M, TC, BS, false>(smem, fa.plan + fa.lay.tw_off[0], tid, nt);
+            __syncthreads();
+            gx_fft_pass<16, 16, M, TC, BS, false>(smem, fa.plan + fa.lay.tw_off[1], tid, nt);
+            __syncthreads();
+            gx_fft_lastpass16_lowband<M, TC, BS>(smem, klo, khi, tid, nt);
+            __syncthreads();
+            full = false;
+        }
+    }
+    if (full) gx_dft_block<L, TC, BS, BLUE ? 1 : 0>(smem, fa.lay, fa.plan, tid, nt);
 
     const int half = N / 2;
     const int kr = fa.row_hi - fa.row_lo;
@@ -418,21 +437,25 @@ static int launch_fused(const FusedArgs &fa, bool species, cudaStream_t st)
                                      (int)smem1));                                                          \
         slice_rows_fused<L, SP, BL, NPR><<<grid1, PROJ_THREADS, smem1, st>>>(fa);                          \
     } while (0)
-    // compile-time plane counts only for the large transforms (L >= 10), where F1 dominates the run
-    const int npair = (fa.proj.n_species + 1) / 2;
-    const int npr = (species && L >= 10 && npair >= 1 && npair <= 3) ? npair : 0;
-    if (species && blue) {
-        if (L >= 10 && npr == 1) GX_LAUNCH_ROWS(true, true, (L >= 10 ? 1 : 0));
-        else if (L >= 10 && npr == 2) GX_LAUNCH_ROWS(true, true, (L >= 10 ? 2 : 0));
-        else if (L >= 10 && npr == 3) GX_LAUNCH_ROWS(true, true, (L >= 10 ? 3 : 0));
-        else GX_LAUNCH_ROWS(true, true, 0);
-    } else if (species) {
-        if (L >= 10 && npr == 1) GX_LAUNCH_ROWS(true, false, (L >= 10 ? 1 : 0));
-        else if (L >= 10 && npr == 2) GX_LAUNCH_ROWS(true, false, (L >= 10 ? 2 : 0));
-        else if (L >= 10 && npr == 3) GX_LAUNCH_ROWS(true, false, (L >= 10 ? 3 : 0));
-        else GX_LAUNCH_ROWS(true, false, 0);
-    } else if (blue) GX_LAUNCH_ROWS(false, true, 0);
+    // compile-time species counts only for the large transforms (L >= 10), where F1 dominates the run
+    const int nsp = (species && L >= 10 && fa.proj.n_species >= 1 && fa.proj.n_species <= 6) ? fa.proj.n_species : 0;
+#define GX_ROWS_NSP(BL)                                                                  \
+    do {                                                                                 \
+        switch (nsp) {                                                                   \
+        case 1: GX_LAUNCH_ROWS(true, BL, (L >= 10 ? 1 : 0)); break;                      \
+        case 2: GX_LAUNCH_ROWS(true, BL, (L >= 10 ? 2 : 0)); break;                      \
+        case 3: GX_LAUNCH_ROWS(true, BL, (L >= 10 ? 3 : 0)); break;                      \
+        case 4: GX_LAUNCH_ROWS(true, BL, (L >= 10 ? 4 : 0)); break;                      \
+        case 5: GX_LAUNCH_ROWS(true, BL, (L >= 10 ? 5 : 0)); break;                      \
+        case 6: GX_LAUNCH_ROWS(true, BL, (L >= 10 ? 6 : 0)); break;                      \
+        default: GX_LAUNCH_ROWS(true, BL, 0); break;                                     \
+        }                                                                                \
+    } while (0)
+    if (species && blue) GX_ROWS_NSP(true);
+    else if (species) GX_ROWS_NSP(false);
+    else if (blue) GX_LAUNCH_ROWS(false, true, 0);
     else GX_LAUNCH_ROWS(false, false, 0);
+#undef GX_ROWS_NSP
 #undef GX_LAUNCH_ROWS
     if (int e = gx_check_launch("slice_rows_fused")) return e;
     int nt = TC * M / 16;
