@@ -170,10 +170,18 @@ slice_rows_fused(FusedArgs fa)
 
     if (SPECIES) {
         const bool single = end - beg <= 65535;            // 16-bit counters cannot wrap: one scatter, one flush
-        if (tid < GX_MAX_SPECIES) s_table[tid] = tid < a.n_species ? a.table[tid] : make_float2(0.f, 0.f);
+        // the f-value table in shared memory is only read by the generic flush and by chunked rows
+        if ((NSP == 0 || !single) && tid < GX_MAX_SPECIES)
+            s_table[tid] = tid < a.n_species ? a.table[tid] : make_float2(0.f, 0.f);
         const int npair = (a.n_species + 1) >> 1;
         uint4 *words4 = reinterpret_cast<uint4 *>(smem_raw);
-        for (int y = tid; y < npair * (NP / 4); y += NT) words4[y] = make_uint4(0u, 0u, 0u, 0u);
+        if constexpr (EXACT && NSP > 0 && (M / 4) % NT == 0) {
+            // plane count and length known at compile time: straight-line 16-byte stores, immediate offsets
+#pragma unroll
+            for (int k = 0; k < ((NSP + 1) / 2) * (M / 4) / NT; ++k) words4[tid + k * NT] = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+            for (int y = tid; y < npair * (NP / 4); y += NT) words4[y] = make_uint4(0u, 0u, 0u, 0u);
+        }
         __syncthreads();
         if (single) {
             // (hand-pipelining the atom loads across the zeroing barrier and across batches was
