@@ -141,3 +141,99 @@ def test_config2_grid_size_2095_bluestein_slice_against_oracle():
     ox.run_slice(vsum, vcnt, coords, setup, r, float(sel[1]), False, 7)
     assert np.array_equal(one.counts(), vcnt.astype(np.int64))
     assert np.abs(one.sums() - vsum).max() <= 1e-4 * vsum.max()
+
+
+def _graphite_crystal(nx, ny, nz):
+    """AB-stacked graphite (a = 2.456 A, c = 6.696 A) as an orthorhombic 8-atom cell replicated
+    nx x ny x nz times: coordinates on a lattice, like test_input_files/graphite_large.xyz, so that
+    whole atom columns share a pixel and many (y' - min y') are exact multiples of lattice steps."""
+    a, c = 2.456, 6.696
+    b = a * np.sqrt(3.0)
+    basis = np.array([[0, 0, 0], [0, 1 / 3, 0], [0.5, 0.5, 0], [0.5, 5 / 6, 0],
+                      [0, 0, 0.5], [0, 2 / 3, 0.5], [0.5, 0.5, 0.5], [0.5, 1 / 6, 0.5]])
+    cells = np.stack(np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij"), -1).reshape(-1, 1, 3)
+    frac = (cells + basis[None]).reshape(-1, 3)
+    return frac * np.array([a, b, c])
+
+
+def test_config3_graphite_crystal_1024_fill_bkg_smooth_against_oracle():
+    """BASELINE configs[2] geometry (graphite crystal, fill_bkg, smooth = 25, N = 1024, q_num = 277):
+    lattice coordinates put hundreds of atoms into one pixel at the symmetric rotations and make
+    floor-divide arguments land on exact multiples; phi = 0 / 30 / 90 take the special chord branches."""
+    coords = _graphite_crystal(28, 12, 8)                                    # 21504 atoms, 69 x 51 x 54 A
+    el = np.array(["C"] * len(coords))
+    r, max_q = 0.3, 2.0
+    q = synth.pow2_q_voxel(r, 1024)
+    dev = engine.resolve_device()
+    codes, uniq, counts = engine.encode_elements_device(el, dev)
+    table = comparison.f_table(uniq, 12700.0)
+    atoms = engine.AtomSet(coords, r, 1024, dev, species=codes, table=table)
+    N, q_num, q_axis, phis = engine.stage_a_geometry(atoms.bounds, r, q, max_q)
+    assert (N, q_num) == (1024, 277)
+    avg = np.sum(counts * np.asarray(table)) / np.prod(atoms.bounds) * r ** 3
+    mk = lambda **kw: engine.SliceEngine(None, r, q_axis, N, avg, atoms.bounds[0], atoms.bounds[1], True, 25,
+                                         atoms=atoms, **kw)
+    sel = np.array([0.0, 30.0, 90.0, float(phis[217]), 120.0])
+    fused, staged = mk(), mk()
+    fused.run(sel)
+    staged.run(sel, staged=True)
+    assert np.array_equal(fused.counts(), staged.counts())
+    assert np.abs(fused.sums() - staged.sums()).max() <= 1e-5 * staged.sums().max()
+    f = ox.f_values_for(el, table=synth.fixed_f1f2)
+    setup = ox.stage_a_setup(coords, f, r, q, max_q)
+    q3 = (setup["q_num"],) * 3
+    vsum, vcnt = np.zeros(q3), np.zeros(q3)
+    for phi in sel:
+        y_idx, z_idx, valid = ox.atom_pixel_indices(coords, phi, N, r)
+        gy, gz, bbox = fused.atom_indices(phi)
+        assert valid.all() and np.array_equal(gy, y_idx) and np.array_equal(gz, z_idx), phi
+        ox.run_slice(vsum, vcnt, coords, setup, r, float(phi), True, 25)
+    assert np.array_equal(fused.counts(), vcnt.astype(np.int64))
+    assert np.abs(fused.sums() - vsum).max() <= 1e-4 * vsum.max()
+
+
+def test_config4_pm6_2048_grid_and_psi_weight_file_against_oracle(golden, tmp_path):
+    """BASELINE configs[3] geometry: the PM6 polymer slab on a 2048^2 grid (q_num = 555) - two slices
+    against the oracle - and the experimental-comparison detector set-up: 91 psi orientations weighted
+    from a .npy file (as test_experimental_data/resampled_ints_PM65CN_91.npy is used), max_q = 2."""
+    g = golden("pm6.npz")
+    coords = g["coords"]
+    el = np.array([str(n) for n in g["element_names"]])[g["element_codes"]]
+    r, max_q = 0.3, 2.0
+    q = synth.pow2_q_voxel(r, 2048)
+    dev = engine.resolve_device()
+    codes, uniq, counts = engine.encode_elements_device(el, dev)
+    table = comparison.f_table(uniq, 12700.0)
+    atoms = engine.AtomSet(coords, r, 2048, dev, species=codes, table=table)
+    N, q_num, q_axis, phis = engine.stage_a_geometry(atoms.bounds, r, q, max_q)
+    assert (N, q_num) == (2048, 555)
+    avg = np.sum(counts * np.asarray(table)) / np.prod(atoms.bounds) * r ** 3
+    eng = engine.SliceEngine(None, r, q_axis, N, avg, atoms.bounds[0], atoms.bounds[1], True, 25, atoms=atoms)
+    sel = phis[[5, 1100]]
+    eng.run(sel)
+    f = ox.f_values_for(el, table=synth.fixed_f1f2)
+    setup = ox.stage_a_setup(coords, f, r, q, max_q)
+    q3 = (setup["q_num"],) * 3
+    vsum, vcnt = np.zeros(q3), np.zeros(q3)
+    for phi in sel:
+        ox.run_slice(vsum, vcnt, coords, setup, r, float(phi), True, 25)
+    assert np.array_equal(eng.counts(), vcnt.astype(np.int64))
+    assert np.abs(eng.sums() - vsum).max() <= 1e-4 * vsum.max()
+
+    # stage B: psi weights from a file; a 120^3 stand-in grid keeps the oracle loop short
+    rng = np.random.default_rng(4)
+    V = 120
+    iq = rng.random((V, V, V)) * 1e5
+    ax = np.linspace(-2.03, 2.03, V)
+    psis, phis_d, thetas = np.linspace(0, 90, 91), np.linspace(0, 179, 5), np.array([0.0])
+    w = np.exp(-0.5 * ((psis - 20.0) / 9.0) ** 2) + 0.02
+    w /= w.sum()
+    wpath = str(tmp_path / "psi_weights_91.npy")
+    np.save(wpath, w)
+    args = (200, max_q, (90.0, 90.0, 90.0), ("psi", "phi", "psi"))
+    det, h, v = comparison.detectormaker_fitting(iq, ax, ax, ax, *args, psis, wpath, phis_d, None, thetas, None)
+    ones = lambda a: np.ones_like(a) / len(a)
+    o_det, o_h, _ = ox.detectormaker(iq, ax, ax, ax, *args, psis, w, phis_d, ones(phis_d), thetas, ones(thetas))
+    assert np.array_equal(h, o_h) and np.abs(det - o_det).max() <= 1e-4 * o_det.max()
+    with pytest.raises(AssertionError, match="psi weights length"):
+        comparison.detectormaker_fitting(iq, ax, ax, ax, *args, psis[:-1], wpath, phis_d, None, thetas, None)
