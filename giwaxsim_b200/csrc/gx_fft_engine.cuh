@@ -105,8 +105,38 @@ template <int L> GX_HD int gx_fft_pos(int k)
 }
 
 // ---- complex helpers -------------------------------------------------------
+// sm_100a has packed fp32x2 arithmetic (add/sub/fma.rn.f32x2 -> FADD2 / FFMA2: one instruction, one
+// issue slot, both halves of an aligned register pair).  A complex add is exactly that shape, and the
+// slice kernels are bound by instruction issue, so the butterflies' additions are issued packed; nvcc
+// does not form these from scalar code on its own.  Results are bit-identical to the scalar forms
+// (same round-to-nearest operations).  The host build (tests/host_emul) uses the scalar forms.
+#if defined(__CUDA_ARCH__) && !defined(GX_NO_F32X2)
+#define GX_F32X2_OP(name, op)                                                                             \
+    __device__ __forceinline__ float2 name(float2 a, float2 b)                                            \
+    {                                                                                                     \
+        float2 r;                                                                                         \
+        asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; " op " rc, ra, rb; "       \
+            "mov.b64 {%0,%1}, rc; }"                                                                      \
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));                             \
+        return r;                                                                                         \
+    }
+GX_F32X2_OP(gx_cadd, "add.rn.f32x2")
+GX_F32X2_OP(gx_csub, "sub.rn.f32x2")
+#undef GX_F32X2_OP
+// acc + c * d with a real coefficient c (both components)
+__device__ __forceinline__ float2 gx_caxpy(float c, float2 d, float2 acc)
+{
+    float2 r;
+    asm("{ .reg .b64 rc, rd, ra, rr; mov.b64 rc, {%2,%2}; mov.b64 rd, {%3,%4}; mov.b64 ra, {%5,%6}; "
+        "fma.rn.f32x2 rr, rc, rd, ra; mov.b64 {%0,%1}, rr; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(c), "f"(d.x), "f"(d.y), "f"(acc.x), "f"(acc.y));
+    return r;
+}
+#else
 GX_HD float2 gx_cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 GX_HD float2 gx_csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+GX_HD float2 gx_caxpy(float c, float2 d, float2 acc) { return make_float2(acc.x + c * d.x, acc.y + c * d.y); }
+#endif
 GX_HD float2 gx_cmul(float2 a, float2 b)
 {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -121,10 +151,13 @@ GX_HD void gx_dft2(float2 &a, float2 &b)
 }
 GX_HD void gx_dft4(float2 &v0, float2 &v1, float2 &v2, float2 &v3)
 {
-    float2 a0 = gx_cadd(v0, v2), a1 = gx_csub(v0, v2);
-    float2 a2 = gx_cadd(v1, v3), a3 = gx_mul_mi(gx_csub(v1, v3));
-    v0 = gx_cadd(a0, a2); v1 = gx_cadd(a1, a3);
-    v2 = gx_csub(a0, a2); v3 = gx_csub(a1, a3);
+    const float2 a0 = gx_cadd(v0, v2), a1 = gx_csub(v0, v2);
+    const float2 a2 = gx_cadd(v1, v3), d = gx_csub(v1, v3);
+    v0 = gx_cadd(a0, a2);
+    v2 = gx_csub(a0, a2);
+    // a1 -+ i d, component by component: the swapped operand would cost moves in a packed add
+    v1 = make_float2(a1.x + d.y, a1.y - d.x);
+    v3 = make_float2(a1.x - d.y, a1.y + d.x);
 }
 
 template <int R> struct GxDft;
@@ -207,18 +240,18 @@ GX_HD void gx_dft16_lowband(const float2 *v, bool wide, float2 *sb)
     const float2 x0 = gx_cadd(gx_cadd(gx_cadd(e, p[4]), gx_cadd(p[1], p[7])),
                               gx_cadd(gx_cadd(p[2], p[6]), gx_cadd(p[3], p[5])));
     const float2 d17 = gx_csub(p[1], p[7]), d26 = gx_csub(p[2], p[6]), d35 = gx_csub(p[3], p[5]);
-    const float2 A = make_float2(o.x + c1 * d17.x + h * d26.x + s1 * d35.x, o.y + c1 * d17.y + h * d26.y + s1 * d35.y);
+    const float2 A = gx_caxpy(s1, d35, gx_caxpy(h, d26, gx_caxpy(c1, d17, o)));
     const float2 a17 = gx_cadd(m[1], m[7]), a26 = gx_cadd(m[2], m[6]), a35 = gx_cadd(m[3], m[5]);
-    const float2 B = make_float2(m[4].x + s1 * a17.x + h * a26.x + c1 * a35.x, m[4].y + s1 * a17.y + h * a26.y + c1 * a35.y);
+    const float2 B = gx_caxpy(c1, a35, gx_caxpy(h, a26, gx_caxpy(s1, a17, m[4])));
     sb[gx_phys(0)] = x0;
     sb[gx_phys(15)] = make_float2(A.x - B.y, A.y + B.x);            // A + iB
     if (wide) {
         sb[gx_phys(1)] = make_float2(A.x + B.y, A.y - B.x);         // A - iB
         const float2 s17 = gx_cadd(p[1], p[7]), s35 = gx_cadd(p[3], p[5]);
         const float2 t = gx_csub(s17, s35), u = gx_csub(e, p[4]);
-        const float2 A2 = make_float2(u.x + h * t.x, u.y + h * t.y);
+        const float2 A2 = gx_caxpy(h, t, u);
         const float2 w = gx_csub(gx_cadd(m[1], m[3]), gx_cadd(m[5], m[7])), g = gx_csub(m[2], m[6]);
-        const float2 B2 = make_float2(g.x + h * w.x, g.y + h * w.y);
+        const float2 B2 = gx_caxpy(h, w, g);
         sb[gx_phys(14)] = make_float2(A2.x - B2.y, A2.y + B2.x);    // A2 + iB2
     }
 }
