@@ -341,7 +341,7 @@ def run_ours(args):
         roofline["slices_per_launch"] = per_launch
         roofline["algorithmic_bytes_per_launch"] = alg.get(top, 0.0) * per_launch
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(top)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r03_traffic.json"))).get(top)
             if tr:
                 roofline["traffic"] = tr["dram_bytes_per_slice"] * per_launch
                 roofline["traffic_source"] = tr["source"]
@@ -354,12 +354,12 @@ def run_ours(args):
                             "2-D FFT and binning kernels they replace (SURVEY 8(d)), so frac > 1 means the fused pair "
                             "is faster than ANY implementation that moves those bytes through HBM; measured DRAM "
                             "traffic is ~21x lower (dram_frac) because the N x N grid and image never reach HBM - "
-                            "the kernels are bound by instruction issue (profiles/r02_summary.md)")
+                            "the kernels are bound by instruction issue (profiles/r03_summary.md)")
     det_bytes = 4.0 * P * P
     det_ach = det_bytes * len(w) / world / (ms_b * 1e-3) / 1e9
     det_traffic = None
     try:
-        det_traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["detector_affine"]
+        det_traffic = json.load(open(os.path.join(ROOT, "profiles", "r03_traffic.json")))["detector_affine"]
     except Exception:
         pass
     line = {"metric": METRIC, "value": len(phis_all) / (ms_a * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -375,7 +375,7 @@ def run_ours(args):
                                                   if det_traffic else None),
                                       "algorithmic_bytes_per_orientation": det_bytes,
                                       "note": "whole stage-B step (host model, gather kernel, mirror epilogue) per "
-                                              "rank; the gather kernel alone: profiles/r02_summary.md"}},
+                                              "rank; the gather kernel alone: profiles/r03_summary.md"}},
             "roofline": roofline, "clocks": clocks, "gpu_launches": launches}
     if e2e is not None:
         line["e2e"] = e2e
