@@ -70,6 +70,8 @@ def _pinned_staging(nbytes):
     return buf
 
 
+PIPELINED_DOWNLOAD_MIN_BYTES = 64 << 20
+PIPELINED_DOWNLOAD_CHUNKS = 8
 _host_pool = []        # [{"buf": flat float64 CPU tensor, "live": weakref to the array handed out}]
 _HOST_POOL_MAX = 2
 _HOST_POOL_MIN_BYTES = 128 << 20      # detector images (tens of MB) are not worth pooling
@@ -113,25 +115,42 @@ def to_host_f64(t, out=None, replicated=False):
             return shared
     nbytes = t.numel() * t.element_size()
     stage = _pinned_staging(nbytes)[:nbytes].view(t.dtype).view(t.shape)
-    stage.copy_(t, non_blocking=True)
     entry = None
     if out is None:
         out, entry = _result_buffer(tuple(t.shape))
     else:
         out = torch.from_numpy(out).view(t.shape)
-    torch.cuda.current_stream().synchronize()
     # torchrun pins OMP_NUM_THREADS=1; the widening copy of a large grid is worth a few host
     # threads per rank (never more than the cores this rank can fairly claim)
     before = torch.get_num_threads()
     want = max(1, min(16, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
-    if nbytes >= (8 << 20) and want > before:
+    threaded = nbytes >= (8 << 20) and want > before
+    if threaded:
         torch.set_num_threads(want)
-        try:
+    try:
+        if nbytes >= PIPELINED_DOWNLOAD_MIN_BYTES and out.is_contiguous():
+            # large grids: the DMA is cut into chunks and chunk k is widened on the host while chunk
+            # k+1 is still on the wire (PCIe time + one chunk instead of PCIe time + the whole widening)
+            src, dst, stg = t.view(-1), out.view(-1), stage.view(-1)
+            n = src.numel()
+            step = -(-n // PIPELINED_DOWNLOAD_CHUNKS)
+            marks = []
+            for lo in range(0, n, step):
+                hi = min(n, lo + step)
+                stg[lo:hi].copy_(src[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                marks.append((lo, hi, ev))
+            for lo, hi, ev in marks:
+                ev.synchronize()
+                dst[lo:hi].copy_(stg[lo:hi])
+        else:
+            stage.copy_(t, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
             out.copy_(stage)
-        finally:
+    finally:
+        if threaded:
             torch.set_num_threads(before)
-    else:
-        out.copy_(stage)
     res = out.numpy()
     if entry is not None:
         import weakref

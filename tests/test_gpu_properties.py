@@ -269,3 +269,17 @@ def test_to_host_f64_roundtrip():
         assert np.array_equal(out, t.cpu().double().numpy())
         out2 = engine.to_host_f64(t * 2)                 # the staging buffer is reused, results are not aliased
         assert np.array_equal(out, t.cpu().double().numpy()) and np.array_equal(out2, 2 * out)
+
+
+def test_to_host_f64_pipelined_chunks(monkeypatch):
+    """Large results are downloaded in chunks, each widened while the next is on the wire."""
+    dev = engine.resolve_device()
+    monkeypatch.setattr(engine, "PIPELINED_DOWNLOAD_MIN_BYTES", 1024)
+    for chunks in (1, 3, 8, 1000):
+        monkeypatch.setattr(engine, "PIPELINED_DOWNLOAD_CHUNKS", chunks)
+        t = torch.randn(101, 67, 13, device=dev, dtype=torch.float32)
+        out = engine.to_host_f64(t)
+        assert out.dtype == np.float64 and np.array_equal(out, t.cpu().double().numpy())
+        view = np.zeros((101, 67, 13))
+        engine.to_host_f64(t, out=view)
+        assert np.array_equal(view, out)
