@@ -173,7 +173,7 @@ def run_reference(args):
                                      "to it; the reference itself is Python and /root/reference is absent here"},
             "e2e": {"value": sa, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------- our arm
@@ -386,10 +386,21 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": sa, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "%d phi slices and %d orientations of the same workload" % (na, nb),
                                 "detector_value": sb, "detector_unit": "orientations/s"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else was diverted to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+# Libraries write banners to fd 1 (NCCL prints "NCCL version ..." on the first communicator): keep
+# the process's stdout for the single JSON line and send every other byte to stderr.
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 if __name__ == "__main__":
     a = parse()
