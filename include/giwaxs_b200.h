@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define GX_ABI_VERSION 2
+#define GX_ABI_VERSION 3   /* 3: gx_voxel_shell_scale, unweighted gx_voxel_finalize, epilogue finish == 2 */
 
 #define GX_OK 0
 #define GX_ERR_INVALID (-1)     /* bad argument                              */

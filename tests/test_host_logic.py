@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libgiwaxs_b200.so does not export %s" % name
     assert declared == set(_lib.exported_symbols())
-    assert _lib.cdll().gx_abi_version() == 2
+    assert _lib.cdll().gx_abi_version() == 3
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="a GPU is present")
@@ -240,3 +240,47 @@ def test_ctypes_prototypes_have_the_headers_arity():
             names = re.sub(r"^(const\s+)?(unsigned\s+)?[A-Za-z_0-9]+\s+", "", stmt)      # drop the type
             c_fields += [re.sub(r"[\s\*]|\[.*?\]", "", x) for x in names.split(",")]
         assert c_fields == [f[0] for f in pyname._fields_], cname
+
+
+def test_two_step_host_helpers(tmp_path):
+    """Host pieces of the two-step command line: structure dispatch by extension, most common element
+    with Counter's tie rule (first seen wins), f0(q) table and its registration hook."""
+    from collections import Counter
+    from giwaxsim_b200.tools import utilities
+    path = str(tmp_path / "tie.xyz")
+    with open(path, "w") as fh:
+        fh.write("6\ncomment\nS 0 0 0\nC1 1 0 0\nS 0 1 0\nC2 0 0 1\nO 1 1 1\nH 2 2 2\n")
+    coords, el = utilities.load_structure(path)
+    assert coords.shape == (6, 3) and list(el) == ["S", "C", "S", "C", "O", "H"]
+    assert utilities.most_common_element(path) == Counter(list(el)).most_common(1)[0][0] == "S"
+    with pytest.raises(Exception, match="must be a .pdb or .xyz"):
+        utilities.load_structure(str(tmp_path / "x.cif"))
+    f0 = utilities.get_element_f0_dict(0.0, ["C", "H", "C"])
+    assert set(f0) == {"C", "H"}
+    assert f0["C"] == pytest.approx(sum(utilities.CROMER_MANN["C"][0:8:2]) + utilities.CROMER_MANN["C"][8])
+    assert abs(f0["C"] - 6.0) < 0.01 and abs(f0["H"] - 1.0) < 0.01          # f0(0) = Z
+    a = utilities.get_element_f0_dict(1.3, ["S"])["S"]
+    c = utilities.CROMER_MANN["S"]
+    # the reference's exponent uses q, not q^2 (utilities.py:331-335)
+    want = sum(c[2 * i] * np.exp(-c[2 * i + 1] * 1.3 / (16 * np.pi ** 2)) for i in range(4)) + c[8]
+    assert a == pytest.approx(want, rel=1e-15)
+    with pytest.raises(KeyError):
+        utilities.get_element_f0_dict(0.5, ["Xx"])
+    utilities.register_cromer_mann("Xx", range(9))
+    try:
+        assert utilities.get_element_f0_dict(0.0, ["Xx"])["Xx"] == 0 + 2 + 4 + 6 + 8
+        with pytest.raises(ValueError):
+            utilities.register_cromer_mann("Yy", (1, 2, 3))
+    finally:
+        del utilities.CROMER_MANN["Xx"]
+
+
+def test_two_step_config_errors_need_no_gpu(tmp_path):
+    """Argument errors of the two-step drivers are raised before any device work."""
+    from giwaxsim_b200 import detectormaker, voxelgridmaker
+    with pytest.raises(Exception, match="Either input_folder or input_path"):
+        voxelgridmaker.main({"gen_name": "x"})
+    with pytest.raises(Exception, match="Path does not exist"):
+        detectormaker.main({"iq_output_folder": str(tmp_path / "missing"), "gen_name": "x", "psi_start": "0",
+                            "psi_end": "1", "psi_num": "2", "phi_start": "0", "phi_end": "1", "phi_num": "2",
+                            "theta_start": "0", "theta_end": "0", "theta_num": "1"})
