@@ -73,12 +73,12 @@ def _pinned_staging(nbytes):
 PIPELINED_DOWNLOAD_MIN_BYTES = 64 << 20
 PIPELINED_DOWNLOAD_CHUNKS = 8
 _host_pool = []        # [{"buf": flat float64 CPU tensor, "live": weakref to the array handed out}]
-_HOST_POOL_MAX = 2
-_HOST_POOL_MIN_BYTES = 128 << 20      # detector images (tens of MB) are not worth pooling
+_HOST_POOL_MAX = 4
+_HOST_POOL_MIN_BYTES = 16 << 20       # first touch of a fresh 33 MB detector image costs as much as its DMA
 
 
 def _result_buffer(shape):
-    """float64 CPU tensor for a result.  Large results come from a two-entry pool of buffers whose
+    """float64 CPU tensor for a result.  Large results come from a small pool of buffers whose
     pages are already faulted in (first touch of a fresh 0.5 GB array costs more than filling it);
     a buffer is reused only once the array previously handed out on it - and every view of it - has
     been garbage collected, so arrays a caller still holds never change."""
