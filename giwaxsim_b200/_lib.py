@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgiwaxs_b200.so")
+# GIWAXS_B200_LIB: another build of the same library (kernel experiments, scripts/build_variant.py)
+LIB_PATH = os.environ.get("GIWAXS_B200_LIB") or os.path.join(_HERE, "libgiwaxs_b200.so")
 
 GX_OK = 0
 GX_ERR_INVALID = -1

@@ -26,6 +26,9 @@
 #ifndef GX_F2_TC12
 #define GX_F2_TC12 4        // columns per F2 CTA at N = 4096 (2 -> 3 CTAs/SM was measured: 1 % slower)
 #endif
+#ifndef GX_F2_TILE_FAST
+#define GX_F2_TILE_FAST 0   // F2 grid order: 0 = rotation fastest, 1 = column tile fastest
+#endif
 #ifndef GX_F1_MINBLOCKS
 #define GX_F1_MINBLOCKS 4   // CTAs/SM the row kernel is compiled for (3 would leave ~84 KB of L1: measured no faster)
 #endif
@@ -338,7 +341,11 @@ slice_cols_fused(FusedArgs fa)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *smem = reinterpret_cast<float2 *>(smem_raw);
     const ProjArgs &a = fa.proj;
+#if GX_F2_TILE_FAST
+    const int p = blockIdx.y, tile = blockIdx.x;          // neighbouring CTAs read neighbouring columns of one rotation
+#else
     const int p = blockIdx.x, tile = blockIdx.y;
+#endif
     const int N = a.N, tid = threadIdx.x, nt = blockDim.x;
     const int jlo = fa.colrange[2 * p], jhi = fa.colrange[2 * p + 1];
     const int kc = jhi - jlo;
@@ -468,7 +475,11 @@ static int launch_fused(const FusedArgs &fa, bool species, cudaStream_t st)
     if (int e = gx_check_launch("slice_rows_fused")) return e;
     int nt = TC * M / 16;
     nt = nt < 64 ? 64 : (nt > 512 ? 512 : nt);
+#if GX_F2_TILE_FAST
+    const dim3 grid2((fa.KC + TC - 1) / TC, fa.n_phi);
+#else
     const dim3 grid2(fa.n_phi, (fa.KC + TC - 1) / TC);
+#endif
     if (blue) {
         GX_CUDA(cudaFuncSetAttribute(slice_cols_fused<L, TC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         slice_cols_fused<L, TC, true><<<grid2, nt, smem2, st>>>(fa);
