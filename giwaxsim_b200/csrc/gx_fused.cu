@@ -29,6 +29,9 @@
 #ifndef GX_F2_TILE_FAST
 #define GX_F2_TILE_FAST 0   // F2 grid order: 0 = rotation fastest, 1 = column tile fastest
 #endif
+#ifndef GX_PASS1_TWP
+#define GX_PASS1_TWP GX_TWP  // twiddles of the middle pass (16 distinct sets, 1.9 KB): 1 = four loads + products, 0 = fifteen loads
+#endif
 #ifndef GX_F1_MINBLOCKS
 #define GX_F1_MINBLOCKS 4   // CTAs/SM the row kernel is compiled for (3 would leave ~84 KB of L1: measured no faster)
 #endif
@@ -308,7 +311,7 @@ slice_rows_fused(FusedArgs fa)
     if constexpr (L == 12 && !BLUE) {
         const int klo = jlo - M / 2, khi = jhi - M / 2;
         if (klo >= -512 && khi <= 512) {
-            gx_fft_pass<16, 16, M, 1, 0, false>(buf, fa.plan + fa.lay.tw_off[1], tid, NT);
+            gx_fft_pass<16, 16, M, 1, 0, false, GX_PASS1_TWP>(buf, fa.plan + fa.lay.tw_off[1], tid, NT);
             __syncthreads();
             gx_fft_lastpass16_lowband<M>(buf, klo, khi, tid, NT);
             __syncthreads();
@@ -372,7 +375,7 @@ slice_cols_fused(FusedArgs fa)
         if (klo >= -512 && khi <= 512) {
             gx_fft_pass<16, M / 16, M, TC, BS, false>(smem, fa.plan + fa.lay.tw_off[0], tid, nt);
             __syncthreads();
-            gx_fft_pass<16, 16, M, TC, BS, false>(smem, fa.plan + fa.lay.tw_off[1], tid, nt);
+            gx_fft_pass<16, 16, M, TC, BS, false, GX_PASS1_TWP>(smem, fa.plan + fa.lay.tw_off[1], tid, nt);
             __syncthreads();
             gx_fft_lastpass16_lowband<M, TC, BS>(smem, klo, khi, tid, nt);
             __syncthreads();
