@@ -20,6 +20,7 @@
 // Grid order: the rotation index is the fastest-varying block index, so the
 // CTAs resident at any moment work on the same few z-rows for all rotations of
 // the batch and the row's atoms are fetched from HBM once and re-read from L2.
+#include <stdlib.h>
 #include "gx_project.cuh"
 #include "gx_fft_engine.cuh"
 
@@ -35,6 +36,18 @@
 #ifndef GX_F1_MINBLOCKS
 #define GX_F1_MINBLOCKS 4   // CTAs/SM the row kernel is compiled for (3 would leave ~84 KB of L1: measured no faster)
 #endif
+
+// Per-rotation / per-row scalars of the row kernel, staged through constant memory by gx_slices_fused
+// (device-to-device cudaMemcpyToSymbolAsync on the launch stream): a CTA reads them with uniform
+// constant-bank loads instead of opening with an L2 round trip before it can even decide whether its
+// row is active.  One launch at a time per device may use them (the path runs on one stream per GPU).
+#ifndef GX_CONST_BATCH
+#define GX_CONST_BATCH 128      // rotations per launch the constant tables hold
+#endif
+#define GX_CONST_ROWS 8192      // largest grid side
+__constant__ double c_sn[GX_CONST_BATCH], c_cs[GX_CONST_BATCH], c_yrange[2 * GX_CONST_BATCH];
+__constant__ int32_t c_bbox[4 * GX_CONST_BATCH], c_colrange[2 * GX_CONST_BATCH];
+__constant__ int32_t c_row_start[GX_CONST_ROWS + 2];
 
 struct FusedArgs {
     ProjArgs proj;
@@ -55,6 +68,7 @@ struct FusedArgs {
     uint32_t *count2;
     float dc_re, dc_im;        // pedestal * N^2
     int n_phi;
+    int use_const;             // row-kernel scalars are in the constant tables
 };
 
 __device__ __forceinline__ void active_band(const ProjArgs &a, int p, int &za, int &zb)
@@ -157,10 +171,19 @@ slice_rows_fused(FusedArgs fa)
     constexpr bool EXACT = !BLUE && NB0 * NT == S0;        // every pixel index t + S0 n is a pixel of the row
     // every per-rotation / per-row scalar is requested before the first branch, so the CTA
     // pays one L2 round trip for all of them instead of one per dependent use
-    const int z_min = __ldg(a.bbox + 4 * p + 2), z_max = __ldg(a.bbox + 4 * p + 3);
-    const int jlo = __ldg(fa.colrange + 2 * p), jhi = __ldg(fa.colrange + 2 * p + 1);
-    const double s = __ldg(a.sn + p), c = __ldg(a.cs + p), shift = __ldg(a.yrange + 2 * p);
-    const int beg = __ldg(a.row_start + z), end = __ldg(a.row_start + z + 1);
+    int z_min, z_max, jlo, jhi, beg, end;
+    double s, c, shift;
+    if (fa.use_const) {
+        z_min = c_bbox[4 * p + 2]; z_max = c_bbox[4 * p + 3];
+        jlo = c_colrange[2 * p]; jhi = c_colrange[2 * p + 1];
+        s = c_sn[p]; c = c_cs[p]; shift = c_yrange[2 * p];
+        beg = c_row_start[z]; end = c_row_start[z + 1];
+    } else {
+        z_min = __ldg(a.bbox + 4 * p + 2); z_max = __ldg(a.bbox + 4 * p + 3);
+        jlo = __ldg(fa.colrange + 2 * p); jhi = __ldg(fa.colrange + 2 * p + 1);
+        s = __ldg(a.sn + p); c = __ldg(a.cs + p); shift = __ldg(a.yrange + 2 * p);
+        beg = __ldg(a.row_start + z); end = __ldg(a.row_start + z + 1);
+    }
     const float mzv = __ldg(a.mz + (size_t)p * N + z);
     int za, zb;
     if (a.fill_bkg) { za = z_min; zb = z_max - 1; }
@@ -531,6 +554,17 @@ extern "C" int gx_slices_fused(const gx_fused_args *h, void *stream)
     fa.n_phi = h->n_phi;
     const bool species = h->n_species > 0;
     cudaStream_t st = gx_stream(stream);
+    fa.use_const = (h->n_phi <= GX_CONST_BATCH && h->N <= GX_CONST_ROWS && !getenv("GIWAXS_B200_NO_CONST")) ? 1 : 0;
+    if (fa.use_const) {
+        const size_t n = (size_t)h->n_phi;
+        const cudaMemcpyKind dd = cudaMemcpyDeviceToDevice;
+        GX_CUDA(cudaMemcpyToSymbolAsync(c_sn, h->d_sin, n * sizeof(double), 0, dd, st));
+        GX_CUDA(cudaMemcpyToSymbolAsync(c_cs, h->d_cos, n * sizeof(double), 0, dd, st));
+        GX_CUDA(cudaMemcpyToSymbolAsync(c_yrange, h->d_yrange, 2 * n * sizeof(double), 0, dd, st));
+        GX_CUDA(cudaMemcpyToSymbolAsync(c_bbox, h->d_bbox, 4 * n * sizeof(int32_t), 0, dd, st));
+        GX_CUDA(cudaMemcpyToSymbolAsync(c_colrange, h->d_colrange, 2 * n * sizeof(int32_t), 0, dd, st));
+        GX_CUDA(cudaMemcpyToSymbolAsync(c_row_start, h->d_row_start, ((size_t)h->N + 2) * sizeof(int32_t), 0, dd, st));
+    }
     switch (fa.lay.L) {
     case 4: return launch_fused<4, 8>(fa, species, st);
     case 5: return launch_fused<5, 8>(fa, species, st);
