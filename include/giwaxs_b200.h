@@ -235,7 +235,10 @@ int gx_slice_col_range(const int32_t *d_col, int n_phi, int N, int32_t *d_range,
  * of voxel (iy,ix,iz) is d_count2[iy,ix] * m[iz], m from gx_row_histogram).
  * The per-rotation tables are those of gx_slice_yrange / gx_slice_bbox /
  * gx_slice_vectors / gx_slice_col_index / gx_slice_col_range; row_lo/row_hi
- * bound the kept shifted rows of d_row_index. */
+ * bound the kept shifted rows of d_row_index.  For n_phi <= 128 the small
+ * per-rotation tables and d_row_start are copied device-to-device into
+ * __constant__ memory on `stream` first: issue the fused launches of one
+ * device on one stream. */
 typedef struct gx_fused_args {
     const double *d_xs, *d_ys;
     const uint8_t *d_species;
