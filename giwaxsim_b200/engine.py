@@ -670,6 +670,9 @@ class SliceEngine:
             raise ValueError("the fused path accumulates rank-1 counts (count3d=False)")
         with torch.cuda.device(self.device):
             B = self.fused_batch_size()
+            if len(phis) > B:
+                # equal batches (1800 rotations: 29 x 63 instead of 28 x 64 + 8): no short last launch pair
+                B = -(-len(phis) // -(-len(phis) // B))
             N = self.N
             work = torch.empty(min(B, len(phis)) * N * self.KC * 2, dtype=torch.float32, device=self.device)
             # per-rotation tables for the whole run in one set of launches, then one
