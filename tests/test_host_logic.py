@@ -284,3 +284,21 @@ def test_two_step_config_errors_need_no_gpu(tmp_path):
         detectormaker.main({"iq_output_folder": str(tmp_path / "missing"), "gen_name": "x", "psi_start": "0",
                             "psi_end": "1", "psi_num": "2", "phi_start": "0", "phi_end": "1", "phi_num": "2",
                             "theta_start": "0", "theta_end": "0", "theta_num": "1"})
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): stdout is exactly one JSON
+    line with the contract's keys; everything else goes to stderr.  Tiny sample of the real workload."""
+    import json
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--cpu-slices", "1", "--atoms", "20000", "--pixels", "128",
+                        "--orientations", "2"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = p.stdout.splitlines()
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "slices/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("BASELINE configs[4]") and d["gpu_launches"] == 0
