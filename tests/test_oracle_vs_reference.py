@@ -150,3 +150,33 @@ def test_most_common_element_and_two_step_average(tmp_path):
     want = ref.voxelgrids.add_f0_q_3d(total, qxs, qys, qzs, ref.utilities.most_common_element(paths[0]))
     got = ox.two_step_voxelgrid([ox.read_structure(p) for p in paths], r, q, max_q, 1, 12700.0, True, 2)
     assert np.array_equal(got[0], want) and np.array_equal(got[1], qxs)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_randomised_pipeline_bit_exact(seed):
+    """Random voxel sizes, q ranges, smoothing widths, detector sizes and init rotations: the oracle's whole
+    pipeline (stage A grid, crop, f0 weight, stage B image) equals the unmodified reference's bit for bit."""
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(40, 400))
+    box = rng.uniform(6.0, 30.0, size=3)
+    coords = rng.random((n, 3)) * box
+    elements = rng.choice(np.array(["C", "H", "S", "O", "N", "F"]), size=n)
+    r = float(rng.choice([0.25, 0.3, 0.41]))
+    max_q = float(rng.choice([1.0, 1.5, 2.0]))
+    q = float(rng.uniform(0.12, 0.2))
+    fill_bkg, smooth = bool(rng.integers(0, 2)), int(rng.integers(0, 5))
+    if 2 * np.pi / q < np.min(coords.max(0) - coords.min(0)):
+        q = 2 * np.pi / (1.5 * np.max(box))
+    a = ref_shim.voxelgridmaker_serial(coords, elements, r, q, max_q, 12700.0, fill_bkg, smooth)
+    b = ox.voxelgridmaker(coords, ox.f_values_for(elements), r, q, max_q, fill_bkg, smooth)[:4]
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    P = int(rng.integers(17, 40))
+    vals = tuple(float(v) for v in rng.choice([0.0, 90.0, 33.0, 7.5], size=3))
+    axs = tuple(str(v) for v in rng.choice(["psi", "phi", "theta", "None"], size=3))
+    psis, phis, thetas = np.linspace(0, 90, 3), np.linspace(0, 175, 4), np.linspace(0, 5, 2)
+    w = [np.ones_like(x) / len(x) for x in (psis, phis, thetas)]
+    mirror = bool(rng.integers(0, 2))
+    da = ref_shim.detectormaker_serial(a[0], a[1], a[2], a[3], P, max_q, vals, axs, psis, w[0], phis, w[1], thetas, w[2],
+                                       mirror=mirror)
+    db = ox.detectormaker(b[0], b[1], b[2], b[3], P, max_q, vals, axs, psis, w[0], phis, w[1], thetas, w[2], mirror=mirror)
+    assert all(np.array_equal(x, y) for x, y in zip(da, db))
