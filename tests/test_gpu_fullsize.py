@@ -237,3 +237,26 @@ def test_config4_pm6_2048_grid_and_psi_weight_file_against_oracle(golden, tmp_pa
     assert np.array_equal(h, o_h) and np.abs(det - o_det).max() <= 1e-4 * o_det.max()
     with pytest.raises(AssertionError, match="psi weights length"):
         comparison.detectormaker_fitting(iq, ax, ax, ax, *args, psis[:-1], wpath, phis_d, None, thetas, None)
+
+
+@pytest.mark.parametrize("n_species", [1, 2, 3, 4, 6, 7])
+def test_species_count_specialisations_1024_against_oracle(n_species):
+    """The row kernel is compiled per species count for large transforms (1..6; 7 takes the generic
+    flush): each one against the oracle on a 1024^2 grid, three rotations, counts bit-exact."""
+    rng = np.random.default_rng(40 + n_species)
+    names = np.array(["C", "H", "S", "O", "F", "N", "P"])[:n_species]
+    coords = rng.random((6000, 3)) * [120.0, 90.0, 100.0]
+    el = rng.choice(names, size=len(coords))
+    r, max_q = 0.3, 2.0
+    q = synth.pow2_q_voxel(r, 1024)
+    phis = np.array([0.0, 41.3, 133.7])
+    fill_bkg, smooth = bool(n_species % 2), 3 * (n_species % 3)
+    iq, qx, qy, qz, eng = comparison.voxelgridmaker_fitting(coords, el, r, q, max_q, 12700.0, fill_bkg=fill_bkg,
+                                                            smooth=smooth, phis=phis, return_state=True)
+    assert eng.N == 1024 and eng.atoms.n_species == n_species
+    f = ox.f_values_for(el, table=synth.fixed_f1f2)
+    o_iq, o_qx, _, _, o_sum, o_cnt, _ = ox.voxelgridmaker(coords, f, r, q, max_q, fill_bkg, smooth, phis=phis)
+    lo, hi = eng.window
+    assert np.array_equal(eng.counts(), o_cnt.astype(np.int64)[lo:hi, lo:hi, lo:hi])
+    assert np.array_equal(qx, o_qx)
+    assert np.abs(iq - o_iq).max() <= 1e-4 * o_iq.max()
