@@ -260,3 +260,33 @@ def test_species_count_specialisations_1024_against_oracle(n_species):
     assert np.array_equal(eng.counts(), o_cnt.astype(np.int64)[lo:hi, lo:hi, lo:hi])
     assert np.array_equal(qx, o_qx)
     assert np.abs(iq - o_iq).max() <= 1e-4 * o_iq.max()
+
+
+def test_wide_q_window_uses_the_full_last_pass():
+    """A 4096^2 grid whose kept q-columns reach beyond +-512 of DC (max_q = 12 at r = 0.05): the
+    band-limited last FFT pass does not apply and the kernels fall back to the full pass.  Fused ==
+    staged (the staged kernels always run full transforms), counts bit-exact."""
+    rng = np.random.default_rng(9)
+    r, max_q = 0.05, 12.0
+    coords = rng.random((20_000, 3)) * [150.0, 100.0, 150.0]
+    el = rng.choice(np.array(["C", "H", "O"]), size=len(coords))
+    q = synth.pow2_q_voxel(r, 4096)
+    dev = engine.resolve_device()
+    codes, uniq, counts = engine.encode_elements_device(el, dev)
+    table = comparison.f_table(uniq, 12700.0)
+    atoms = engine.AtomSet(coords, r, 4096, dev, species=codes, table=table)
+    N, q_num, q_axis, phis = engine.stage_a_geometry(atoms.bounds, r, q, max_q)
+    assert N == 4096 and q_num > 1024
+    avg = np.sum(counts * np.asarray(table)) / np.prod(atoms.bounds) * r ** 3
+    window = engine.crop_range(q_axis, max_q)
+    mk = lambda: engine.SliceEngine(None, r, q_axis, N, avg, atoms.bounds[0], atoms.bounds[1], True, 5,
+                                    atoms=atoms, window=window)
+    fused, staged = mk(), mk()
+    assert fused.KC > 1024                                  # kept columns beyond +-512
+    sel = np.array([17.0, 93.0])
+    fused.run(sel)
+    staged.run(sel, staged=True)
+    a, b = fused.count2.cpu().numpy(), staged.count2.cpu().numpy()
+    assert np.array_equal(a, b) and a.sum() > 0
+    fs, ss = fused.vsum, staged.vsum
+    assert float((fs - ss).abs().max()) <= 1e-5 * float(ss.max())
