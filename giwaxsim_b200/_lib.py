@@ -17,6 +17,7 @@ GX_ERR_CUDA = -2
 GX_ERR_UNSUPPORTED = -3
 GX_ERR_NO_DEVICE = -4
 GX_MAX_SPECIES = 16
+ABI_VERSION = 4          # GX_ABI_VERSION of include/giwaxs_b200.h this binding was written for
 
 
 class GxError(RuntimeError):
@@ -41,7 +42,7 @@ class FusedArgs(ctypes.Structure):
                  "d_work", "d_sum", "d_count2")] + \
                [(n, ctypes.c_double) for n in ("r", "pedestal_re", "pedestal_im", "avg_f_re", "avg_f_im")] + \
                [(n, ctypes.c_int32) for n in ("n_species", "n_phi", "N", "KC", "q_num", "row_lo", "row_hi",
-                                              "fill_bkg", "smooth_sigma", "pad")] + \
+                                              "fill_bkg", "smooth_sigma", "phases")] + \
                [("table", ctypes.c_float * (2 * GX_MAX_SPECIES))]
 
 
@@ -66,6 +67,7 @@ _PROTOTYPES = {
     "gx_atoms_sort_rows": (_i, [_p, _i64, _d, _d, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gx_species_histogram": (_i, [_p, _i, _i64, _p, _p]),
     "gx_species_codes": (_i, [_p, _i, _i64, _p, _p, _p]),
+    "gx_checksum64": (_i, [_p, _i64, _i, _p, _p]),
     "gx_slice_yrange": (_i, [_p, _p, _i64, _p, _p, _i, _p, _p]),
     "gx_extreme_atoms": (_i, [_p, _p, _i64, _p, _p, _p, _i, _p, _p]),
     "gx_hull_filter": (_i, [_p, _p, _i64, _p, _i, _d, _p, _p, _p, _i, _p]),
@@ -146,7 +148,7 @@ _LAUNCHES = {
     "gx_axis_col_index": 1, "gx_axis_row_index": 1, "gx_bin_slices": 1, "gx_row_histogram": 1,
     "gx_voxel_finalize": 1, "gx_voxel_shell_scale": 1, "gx_rotate_points": 1, "gx_detector_accumulate": 1, "gx_detector_epilogue": 1,
     "gx_detector_accumulate_fast": 1, "gx_detector_accumulate_affine": 1, "gx_grid_affine_fit": 1,
-    "gx_slices_fused": 2, "gx_species_histogram": 1, "gx_species_codes": 1, "gx_window_indices": 1, "gx_slab_minmax": 3, "gx_slab_count": 3, "gx_slab_write": 1, "gx_slice_col_range": 1, "gx_extreme_atoms": 1, "gx_hull_filter": 1,
+    "gx_slices_fused": 2, "gx_species_histogram": 1, "gx_species_codes": 1, "gx_checksum64": 1, "gx_window_indices": 1, "gx_slab_minmax": 3, "gx_slab_count": 3, "gx_slab_write": 1, "gx_slice_col_range": 1, "gx_extreme_atoms": 1, "gx_hull_filter": 1,
 }
 _launch_count = 0
 
@@ -168,6 +170,9 @@ def call(name, *args):
         raise GxError(rc, last_error())
     if name == "gx_slice_yrange":
         _launch_count += 2 + (int(args[5]) + 255) // 256
+    elif name == "gx_slices_fused":
+        ph = getattr(getattr(args[0], "_obj", None), "phases", 0)
+        _launch_count += 2 if ph in (0, 3) else 1
     else:
         _launch_count += _LAUNCHES.get(name, 0)
     return rc

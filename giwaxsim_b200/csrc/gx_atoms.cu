@@ -515,3 +515,38 @@ extern "C" int gx_species_codes(const uint32_t *d_codepoints, int width, int64_t
     species_code_kernel<<<(int)blocks, ATOM_THREADS, 0, gx_stream(stream)>>>(d_codepoints, width, A, d_lut, d_codes);
     return gx_check_launch("gx_species_codes");
 }
+
+
+// ---------------------------------------------------------------- content checksum ----
+// Wrap-around sum of the 64-bit words of a device array; fp32 input is widened to fp64 first, so the
+// value equals the same sum taken on the host over the float64 copy a driver hands to its caller.
+// Used to decide whether a host array still equals the device copy it was made from.
+__global__ void __launch_bounds__(ATOM_THREADS)
+checksum64_kernel(const void *__restrict__ data, int64_t n, int widen, unsigned long long *out)
+{
+    unsigned long long acc = 0ull;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (widen) {
+        const float *p = static_cast<const float *>(data);
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+            acc += (unsigned long long)__double_as_longlong((double)p[i]);
+    } else {
+        const unsigned long long *p = static_cast<const unsigned long long *>(data);
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc += p[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+extern "C" int gx_checksum64(const void *d_data, int64_t n, int widen_f32, uint64_t *d_out, void *stream)
+{
+    GX_REQUIRE(d_data && d_out && n >= 0, "bad arguments");
+    GX_CUDA(cudaMemsetAsync(d_out, 0, sizeof(uint64_t), gx_stream(stream)));
+    if (n == 0) return GX_OK;
+    int64_t blocks = (n + ATOM_THREADS - 1) / ATOM_THREADS;
+    if (blocks > GX_SM_COUNT * 8) blocks = GX_SM_COUNT * 8;
+    checksum64_kernel<<<(int)blocks, ATOM_THREADS, 0, gx_stream(stream)>>>(d_data, n, widen_f32,
+                                                                          reinterpret_cast<unsigned long long *>(d_out));
+    return gx_check_launch("gx_checksum64");
+}

@@ -453,7 +453,7 @@ extern "C" int gx_slice_col_range(const int32_t *d_col, int n_phi, int N, int32_
 
 // ---------------------------------------------------------------- launch ----
 template <int L, int TC>
-static int launch_fused(const FusedArgs &fa, bool species, cudaStream_t st)
+static int launch_fused(const FusedArgs &fa, bool species, int phases, cudaStream_t st)
 {
     constexpr int M = 1 << L;
     constexpr int BS0 = M + (M >> 4) + (M >> 8) + 1;
@@ -492,13 +492,16 @@ static int launch_fused(const FusedArgs &fa, bool species, cudaStream_t st)
         default: GX_LAUNCH_ROWS(true, BL, 0); break;                                     \
         }                                                                                \
     } while (0)
-    if (species && blue) GX_ROWS_NSP(true);
-    else if (species) GX_ROWS_NSP(false);
-    else if (blue) GX_LAUNCH_ROWS(false, true, 0);
-    else GX_LAUNCH_ROWS(false, false, 0);
+    if (phases & 1) {
+        if (species && blue) GX_ROWS_NSP(true);
+        else if (species) GX_ROWS_NSP(false);
+        else if (blue) GX_LAUNCH_ROWS(false, true, 0);
+        else GX_LAUNCH_ROWS(false, false, 0);
+        if (int e = gx_check_launch("slice_rows_fused")) return e;
+    }
 #undef GX_ROWS_NSP
 #undef GX_LAUNCH_ROWS
-    if (int e = gx_check_launch("slice_rows_fused")) return e;
+    if (!(phases & 2)) return GX_OK;
     int nt = TC * M / 16;
     nt = nt < 64 ? 64 : (nt > 512 ? 512 : nt);
 #if GX_F2_TILE_FAST
@@ -553,9 +556,11 @@ extern "C" int gx_slices_fused(const gx_fused_args *h, void *stream)
     fa.dc_im = has_ped ? (float)(h->pedestal_im * n2) : 0.f;
     fa.n_phi = h->n_phi;
     const bool species = h->n_species > 0;
+    GX_REQUIRE(h->phases >= 0 && h->phases <= 3, "phases must be 0 (both), 1 (rows), 2 (columns) or 3");
+    const int phases = h->phases == 0 ? 3 : h->phases;
     cudaStream_t st = gx_stream(stream);
     fa.use_const = (h->n_phi <= GX_CONST_BATCH && h->N <= GX_CONST_ROWS && !getenv("GIWAXS_B200_NO_CONST")) ? 1 : 0;
-    if (fa.use_const) {
+    if (fa.use_const && (phases & 1)) {
         const size_t n = (size_t)h->n_phi;
         const cudaMemcpyKind dd = cudaMemcpyDeviceToDevice;
         GX_CUDA(cudaMemcpyToSymbolAsync(c_sn, h->d_sin, n * sizeof(double), 0, dd, st));
@@ -566,16 +571,16 @@ extern "C" int gx_slices_fused(const gx_fused_args *h, void *stream)
         GX_CUDA(cudaMemcpyToSymbolAsync(c_row_start, h->d_row_start, ((size_t)h->N + 2) * sizeof(int32_t), 0, dd, st));
     }
     switch (fa.lay.L) {
-    case 4: return launch_fused<4, 8>(fa, species, st);
-    case 5: return launch_fused<5, 8>(fa, species, st);
-    case 6: return launch_fused<6, 8>(fa, species, st);
-    case 7: return launch_fused<7, 8>(fa, species, st);
-    case 8: return launch_fused<8, 8>(fa, species, st);
-    case 9: return launch_fused<9, 8>(fa, species, st);
-    case 10: return launch_fused<10, 8>(fa, species, st);
-    case 11: return launch_fused<11, 8>(fa, species, st);
-    case 12: return launch_fused<12, GX_F2_TC12>(fa, species, st);
-    case 13: return launch_fused<13, 2>(fa, species, st);
+    case 4: return launch_fused<4, 8>(fa, species, phases, st);
+    case 5: return launch_fused<5, 8>(fa, species, phases, st);
+    case 6: return launch_fused<6, 8>(fa, species, phases, st);
+    case 7: return launch_fused<7, 8>(fa, species, phases, st);
+    case 8: return launch_fused<8, 8>(fa, species, phases, st);
+    case 9: return launch_fused<9, 8>(fa, species, phases, st);
+    case 10: return launch_fused<10, 8>(fa, species, phases, st);
+    case 11: return launch_fused<11, 8>(fa, species, phases, st);
+    case 12: return launch_fused<12, GX_F2_TC12>(fa, species, phases, st);
+    case 13: return launch_fused<13, 2>(fa, species, phases, st);
     }
     gx_set_error("gx_slices_fused: unsupported log2 size %d", fa.lay.L);
     return GX_ERR_UNSUPPORTED;

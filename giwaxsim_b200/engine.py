@@ -158,6 +158,34 @@ def to_host_f64(t, out=None, replicated=False):
     return res
 
 
+def device_checksum(t, widen_f32=False):
+    """Wrap-around 64-bit word sum of a device tensor (gx_checksum64) as a Python int; with
+    widen_f32 the sum of the float64 bit patterns of an fp32 tensor - what host_checksum()
+    returns for the widened host copy."""
+    t = t.contiguous()
+    out = torch.zeros(1, dtype=torch.int64, device=t.device)
+    n = t.numel() if widen_f32 else t.numel() * t.element_size() // 8
+    with torch.cuda.device(t.device):
+        call("gx_checksum64", ptr(t), int(n), int(bool(widen_f32)), ptr(out), _stream())
+        return int(out.item()) & 0xFFFFFFFFFFFFFFFF
+
+
+def host_checksum(a):
+    """The same checksum of a C-contiguous host array whose byte size is a multiple of 8
+    (multi-threaded: ~20 ms for a 0.5 GB grid), or None for anything else."""
+    if not isinstance(a, np.ndarray) or not a.flags.c_contiguous or a.nbytes % 8:
+        return None
+    flat = torch.from_numpy(a.reshape(-1).view(np.uint8)).view(torch.int64)
+    before = torch.get_num_threads()
+    want = max(1, min(16, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+    try:
+        if a.nbytes >= (8 << 20) and want > before:
+            torch.set_num_threads(want)
+        return int(flat.sum().item()) & 0xFFFFFFFFFFFFFFFF
+    finally:
+        torch.set_num_threads(before)
+
+
 def _dev(a, device, dtype=None):
     t = torch.from_numpy(np.ascontiguousarray(a))
     if dtype is not None:
@@ -308,6 +336,17 @@ class FftPlan:
         if key not in cls._cache:
             cls._cache[key] = cls(N, device)
         return cls._cache[key]
+
+
+def check_grid_size(grid_size):
+    """Raise a clear error for a real-space grid side the row / column transforms do not cover
+    (grid_size = ceil(2 pi / (q_voxel_size r_voxel_size)), comparison.py:710, is unconstrained in
+    the reference); called before any upload."""
+    if int(call("gx_fft_plan_bytes", int(grid_size))) < 0:
+        raise _lib.GxError(_lib.GX_ERR_UNSUPPORTED,
+                           "real-space grid of %d^2 pixels is not supported (%s); choose q_voxel_size / "
+                           "r_voxel_size so that ceil(2 pi / (q r)) is within the supported sizes"
+                           % (grid_size, _lib.last_error()))
 
 
 def stage_a_geometry(bounds, r_voxel_size, q_voxel_size, max_q):
@@ -661,7 +700,13 @@ class SliceEngine:
         args.n_species, args.n_phi, args.N, args.KC, args.q_num = a.n_species, n, self.N, self.KC, self.q_out
         args.row_lo, args.row_hi = self.row_lo, self.row_hi
         args.fill_bkg, args.smooth_sigma = int(self.fill_bkg), self.sigma
-        call("gx_slices_fused", ctypes.byref(args), _stream())
+        if self.timers is None:
+            call("gx_slices_fused", ctypes.byref(args), _stream())
+        else:
+            # per-kernel CUDA-event timing (bench.py): the two launches are issued by two calls
+            for name, phase in (("rows", 1), ("cols", 2)):
+                args.phases = phase
+                self._timed(name, call, "gx_slices_fused", ctypes.byref(args), _stream())
 
     def run_fused(self, phis):
         """Production path: two fused launches per batch, nothing N x N in HBM."""
@@ -679,14 +724,18 @@ class SliceEngine:
             # pair of fused launches per batch on views of them
             full = self._timed("prepare", self.prepare, phis)
             per_phi = {"sin": 1, "cos": 1, "yrange": 2, "bbox": 4, "base": 2 * N, "my": N, "mz": N, "dmy": 2 * N, "col": N}
+            ranges = []
             for i0 in range(0, len(phis), B):
                 n = min(B, len(phis) - i0)
                 t = {k: full[k][i0 * w:(i0 + n) * w] for k, w in per_phi.items()}
                 t["n"] = n
-                self._timed("fused", self.fused, t, work)
+                self.fused(t, work)
+                ranges.append(t["colrange"])
                 self.slices_done += n
             torch.cuda.current_stream().synchronize()
             self.check_bbox(full)
+            cr = torch.cat(ranges).cpu().numpy().reshape(-1, 2)
+            self.mean_kept_columns = float(np.maximum(cr[:, 1] - cr[:, 0], 0).mean())
 
     def run(self, phis, capture=None, staged=None):
         """Accumulate the given phi slices.  capture: optional dict receiving

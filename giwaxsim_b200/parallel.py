@@ -42,6 +42,16 @@ def all_reduce_sum(tensors, group=None):
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
 
+def combine_and_finalize(eng, q_axis, max_q, device, window=None, crop=True, f0=True, group=None):
+    """Partial voxel sums / counts of every rank -> the finished iq grid on every rank
+    (reference: the shared `+=` of voxelgrids.py:502-503 followed by comparison.py:765-786).
+    One rank: just the finalise kernel."""
+    from . import engine
+    all_reduce_sum([eng.vsum, eng.count2], group=group)
+    return engine.finalize_voxels(eng.vsum, None, eng.count2, eng.row_hist, q_axis, max_q, device,
+                                  window=window, crop=crop, f0=f0)
+
+
 SHARDED_UPLOAD_MIN_BYTES = 8 << 20
 STAGED_UPLOAD_MIN_BYTES = 32 << 20
 STAGED_UPLOAD_CHUNK = 32 << 20

@@ -20,8 +20,11 @@ from .detector import rotate_about_horizontal, rotate_about_normal, rotate_about
 from .utilities import ATOMIC_NUMBER, calc_real_space_abc, get_element_f1_f2_dict, load_pdb, load_xyz
 
 # device copy of the last voxel grid returned by voxelgridmaker_fitting, so a
-# following detectormaker_fitting(iq, ...) on the same array skips the upload
-_resident = {"host": None, "device": None}
+# following detectormaker_fitting(iq, ...) on the same array skips the upload.  The copy is used
+# only while the caller's array still has the content it was handed out with (checksum over the
+# whole array: an in-place edit - mask, scale, clip, noise - is always seen; the reference reads
+# the host array, comparison.py:790).
+_resident = {"host": None, "device": None, "sum": None}
 _TRACE = os.environ.get("GIWAXS_B200_TRACE", "0") == "1"
 
 
@@ -60,16 +63,22 @@ def species_table(elements, energy):
 
 
 # device copy of the last slab returned by slabmaker_fitting: a following
-# voxelgridmaker_fitting(coords, elements, ...) on the same arrays skips upload and species coding
-_slab = {"coords": None, "elements": None, "probe": None, "d_coords": None, "d_codes": None, "uniq": None,
+# voxelgridmaker_fitting(coords, elements, ...) on the same arrays skips upload and species coding,
+# provided BOTH arrays still hold what was handed out (whole-array checksums)
+_slab = {"coords": None, "elements": None, "sums": None, "d_coords": None, "d_codes": None, "uniq": None,
          "counts": None}
 
 
-def _slab_probe(coords):
-    """A few entries of the array: detects in-place edits between the two calls."""
-    flat = coords.reshape(-1)
-    idx = np.linspace(0, flat.size - 1, num=min(flat.size, 16)).astype(np.int64)
-    return flat[idx].copy()
+def _elements_checksum(elements):
+    """Checksum of a NumPy unicode element array (its code points), None if not checkable."""
+    e = np.asarray(elements)
+    if e.dtype.kind != "U" or not e.flags.c_contiguous:
+        return None
+    raw = e.view(np.uint8).reshape(-1)
+    pad = (-raw.size) % 8
+    if pad:
+        raw = np.concatenate([raw, np.zeros(pad, dtype=np.uint8)])
+    return engine.host_checksum(raw)
 
 
 def slabmaker_fitting(input_filepath, x_size, y_size, z_size, a, b, c, alpha, beta, gamma):
@@ -95,8 +104,9 @@ def slabmaker_fitting(input_filepath, x_size, y_size, z_size, a, b, c, alpha, be
         h_codes = d_codes.cpu().numpy()
     elements = uniq[h_codes]
     counts = np.bincount(h_codes, minlength=len(uniq)).astype(np.int64)
-    _slab.update(coords=coords, elements=elements, probe=_slab_probe(coords), d_coords=d_coords, d_codes=d_codes,
-                 uniq=[u for u in uniq], counts=counts)
+    _slab.update(coords=coords, elements=elements,
+                 sums=(engine.device_checksum(d_coords), _elements_checksum(elements)),
+                 d_coords=d_coords, d_codes=d_codes, uniq=[u for u in uniq], counts=counts)
     return coords, elements
 
 
@@ -105,8 +115,10 @@ def _resident_slab(coords, elements, dev):
     just returned, untouched and on this device; else None."""
     if coords is not _slab["coords"] or elements is not _slab["elements"] or _slab["d_coords"] is None:
         return None
-    if _slab["d_coords"].device != dev or not np.array_equal(_slab_probe(coords), _slab["probe"]):
+    if _slab["d_coords"].device != dev:
         return None
+    if _slab["sums"][1] is None or (engine.host_checksum(coords), _elements_checksum(elements)) != _slab["sums"]:
+        return None                                    # edited in place since slabmaker_fitting returned them
     if len(_slab["uniq"]) > engine._lib.GX_MAX_SPECIES:
         return None
     return _slab["d_coords"], _slab["d_codes"], _slab["uniq"], _slab["counts"]
@@ -127,6 +139,7 @@ def voxelgrid_device(coords, elements, table_of, r_voxel_size, q_voxel_size, max
     if max_q_diag > 2 * np.pi / r_voxel_size:
         raise Exception('Max_q is non-physical for given voxel size')
     grid_size = int(np.ceil(2 * np.pi / (q_voxel_size * r_voxel_size)))
+    engine.check_grid_size(grid_size)                     # before anything is uploaded or sorted
     if resident is not None:
         coords, enc = resident[0], resident[1:]           # device slab from slabmaker_fitting
     else:
@@ -166,12 +179,8 @@ def voxelgrid_device(coords, elements, table_of, r_voxel_size, q_voxel_size, max
     tr.lap("engine")
     eng.run(parallel.shard(np.asarray(phis, dtype=np.float64), rank, world))
     tr.lap("slices")
-    if world > 1:
-        parallel.all_reduce_sum([eng.vsum, eng.count2])
-    tr.lap("all-reduce")
-    iq_dev, axis = engine.finalize_voxels(eng.vsum, None, eng.count2, eng.row_hist, q_axis, max_q, dev,
-                                          window=window, crop=crop, f0=f0)
-    tr.lap("finalise")
+    iq_dev, axis = parallel.combine_and_finalize(eng, q_axis, max_q, dev, window=window, crop=crop, f0=f0)
+    tr.lap("combine + finalise")
     return iq_dev, axis, eng, world
 
 
@@ -193,6 +202,7 @@ def voxelgridmaker_fitting(coords, elements, r_voxel_size, q_voxel_size, max_q, 
     tr.lap("result to host")
     tr.done()
     _resident["host"], _resident["device"] = iq, iq_dev
+    _resident["sum"] = engine.device_checksum(iq_dev, widen_f32=True)
     out = (iq, axis.copy(), axis.copy(), axis.copy())
     return out + (eng,) if return_state else out
 
@@ -251,8 +261,10 @@ def detectormaker_fitting(iq, qx, qy, qz, num_pixels, max_q, angle_init_vals, an
     assert np.abs(1 - np.sum(phi_weights)) < 0.01, 'phi weights must sum to 1'
     assert np.abs(1 - np.sum(theta_weights)) < 0.01, 'theta weights must sum to 1'
 
-    grid = _resident["device"] if (iq is _resident["host"] and _resident["device"] is not None
-                                   and _resident["device"].device == dev) else iq
+    grid = iq
+    if (iq is _resident["host"] and _resident["device"] is not None and _resident["device"].device == dev
+            and engine.host_checksum(iq) == _resident["sum"]):
+        grid = _resident["device"]                     # same array, same content: skip the upload
     det = engine.DetectorEngine(grid, qx, qy, qz, device=dev)
     tr.lap("voxel grid")
     R, w = engine.orientation_tables(engine.grid_corners(gx, gy, gz), psis, psi_weights, phis, phi_weights,

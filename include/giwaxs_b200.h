@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define GX_ABI_VERSION 3   /* 3: gx_voxel_shell_scale, unweighted gx_voxel_finalize, epilogue finish == 2 */
+#define GX_ABI_VERSION 4   /* 4: gx_fused_args.phases, gx_comm_*, sharded finalise, device-side orientation model */
 
 #define GX_OK 0
 #define GX_ERR_INVALID (-1)     /* bad argument                              */
@@ -83,6 +83,14 @@ int gx_atoms_sort_rows(const double *d_coords, int64_t A, double z_min, double r
 int gx_species_histogram(const uint32_t *d_codepoints, int width, int64_t A, uint32_t *d_hist, void *stream);
 int gx_species_codes(const uint32_t *d_codepoints, int width, int64_t A, const uint8_t *d_lut,
                      uint8_t *d_codes, void *stream);
+
+/* Wrap-around sum of the 64-bit words of d_data [n]; widen_f32 != 0: d_data is
+ * fp32 and each value is widened to fp64 first (the checksum of the float64
+ * host copy a driver returns).  Lets voxelgridmaker_fitting -> detectormaker_fitting
+ * and slabmaker_fitting -> voxelgridmaker_fitting reuse the device copy of an
+ * array only while the caller's host array still has the same content
+ * (the reference always reads the host array: comparison.py:673,790).         */
+int gx_checksum64(const void *d_data, int64_t n, int widen_f32, uint64_t *d_out, void *stream);
 
 /* min and max over all atoms of y' = fma(y, cos, x*sin) for n_phi rotations.
  * d_yrange [n_phi][2].                   (utilities.py:303-317, vg.py:323) */
@@ -255,7 +263,8 @@ typedef struct gx_fused_args {
     float *d_sum;
     uint32_t *d_count2;
     double r, pedestal_re, pedestal_im, avg_f_re, avg_f_im;
-    int32_t n_species, n_phi, N, KC, q_num, row_lo, row_hi, fill_bkg, smooth_sigma, pad;
+    int32_t n_species, n_phi, N, KC, q_num, row_lo, row_hi, fill_bkg, smooth_sigma;
+    int32_t phases;              /* 0 or 3: both launches; 1: row kernel only; 2: column kernel only (per-kernel timing) */
     gx_float2 table[GX_MAX_SPECIES];   /* host copy of d_table (kernel-parameter operands) */
 } gx_fused_args;
 int gx_slices_fused(const gx_fused_args *h_args, void *stream);

@@ -13,6 +13,12 @@ Cases
   detector     stage B on the graphite262 voxel grid: 64^2 and 65^2 detectors
   twostep      two seeded clusters through the reference's generate_voxel_grid_low_mem (aff_num_qs 1
                and 3, N=210 -> Bluestein) and the old_modules/voxelgridmaker.py crop/average/f0 loop
+  named        BASELINE.json configs[0..2] on their NAMED input files at the configured sizes, a few probe
+               slices each through the unmodified reference (compact: the count grid as its exact rank-1
+               factors, the sums / iq on a subset of the hit (qy, qx) columns):
+                 config1_graphite_medium  r 0.3, q 0.02 (template values) -> N = 1048 (Bluestein), q_num 285
+                 config2_silicon_medium   r 0.3, q 0.01 -> N = 2095 (largest Bluestein), q_num 569, + 512^2 stage B
+                 config3_graphite_large   N = 1024, fill_bkg, smooth 25
   pm6          config_templates/simulate_GIWAXS_config.txt end to end (N=1048, 892 slices,
                2880 orientations x 500^2) + the reference's own golden det_sum.npy
 """
@@ -187,6 +193,79 @@ def pm6():
     np.save(os.path.join(OUT, "pm6_det_sum_ref.npy"), gold)
 
 
+def _named_case(name, xyz, r, q, max_q, fill_bkg, smooth, probes, detector_pixels=0, keep_every=4, energy=12700.0):
+    """A few slices of a named input file at its configured grid size through the unmodified reference
+    (rotate_project_fft_coords -> process_file2 on fresh accumulators, comparison.py:769-786 finalise)."""
+    ref = ref_shim.load()
+    coords, elements = ref.utilities.load_xyz(os.path.join(REF, "test_input_files", xyz))
+    setup = ref_shim.stage_a_setup(coords, elements, r, q, max_q, energy)
+    phis = setup["phis"][np.asarray(probes)]
+    t0 = time.time()
+    vsum, vcnt = ref_shim.run_slices_serial(coords, setup, r, fill_bkg, smooth, phis=phis)
+    iq, qx, qy, qz = ref_shim.finalize_serial(vsum, vcnt, setup["q_axis"], max_q)
+    q_num = setup["q_num"]
+    # the count grid is rank-1 (every slice shares the row table): store its exact factors, validated
+    # against the reference's full count grid right below
+    from . import giwaxs_oracle as ox
+    hx, hy, vz = ox.slice_q_axes(float(phis[0]), setup["grid_size"], r)
+    iz = ox.bin_indices(hx, hy, vz, setup["q_axis"])[4]
+    m = np.bincount(iz, minlength=q_num).astype(np.int64)
+    iz0 = int(np.argmax(m))
+    H = np.round(vcnt[:, :, iz0] / m[iz0]).astype(np.int64)
+    assert np.array_equal(vcnt, (H[:, :, None] * m[None, None, :]).astype(np.float64)), "count grid is not rank-1"
+    pairs = np.argwhere(H > 0)[::keep_every]
+    lo, hi = ref_shim_crop(setup["q_axis"], max_q)
+    inside = np.all((pairs >= lo) & (pairs < hi), axis=1)
+    out = dict(xyz=np.array(xyz), coords=coords, elements=np.asarray(elements), r=r, q=q, max_q=max_q, fill_bkg=fill_bkg, smooth=smooth, energy=energy,
+               grid_size=setup["grid_size"], q_num=q_num, q_axis=setup["q_axis"], probe_phis=phis,
+               n_phis_reference=len(setup["phis"]), H=H.astype(np.uint16), m=m.astype(np.uint16),
+               pairs=pairs.astype(np.int32), vsum_pairs=vsum[pairs[:, 0], pairs[:, 1], :].astype(np.float32),
+               vsum_max=vsum.max(), crop=np.array([lo, hi]), iq_pairs=(pairs[inside] - lo).astype(np.int32),
+               iq_values=iq[pairs[inside, 0] - lo, pairs[inside, 1] - lo, :].astype(np.float32), iq_max=iq.max())
+    if detector_pixels:
+        P = detector_pixels
+        psis, dphis, thetas = np.linspace(75, 90, 3), np.linspace(0, 179, 4), np.array([0.0])
+        det, h, v = ref_shim.detectormaker_serial(iq, qx, qy, qz, P, max_q, (90.0, 90.0, 90.0), ("psi", "phi", "psi"),
+                                                  psis, np.ones(3) / 3, dphis, np.ones(4) / 4, thetas, np.ones(1))
+        out.update(det_P=P, det_psis=psis, det_phis=dphis, det_thetas=thetas, det=det.astype(np.float32),
+                   det_max=det.max())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("%s: N=%d q_num=%d probes=%s pairs=%d (%.1fs)" % (name, setup["grid_size"], q_num, list(probes),
+                                                              len(pairs), time.time() - t0))
+
+
+def ref_shim_crop(axis, max_q):
+    """Index range downselect_voxelgrid keeps (voxelgrids.py:36-46), from the reference function itself."""
+    ref = ref_shim.load()
+    _, kept, _, _ = ref.voxelgrids.downselect_voxelgrid(_Zero3(len(axis)), axis, axis, axis, max_q)
+    lo = int(np.where(axis == kept[0])[0][0])
+    return lo, lo + len(kept)
+
+
+class _Zero3:
+    """Stand-in for a q_num^3 grid that downselect_voxelgrid only slices (saves 1.5 GB)."""
+
+    def __init__(self, n):
+        self.shape = (n, n, n)
+
+    def __getitem__(self, key):
+        return self
+
+
+def named():
+    r = 0.3
+    _named_case("config1_graphite_medium", "graphite_medium.xyz", r, 0.02, 2.0, True, 25, [0, 223, 446, 700],
+                keep_every=3)
+    # the template's smooth = 25 pixels is wider than this 45-pixel cluster (the blend mask is all zero and the
+    # slice is the bare pedestal): the same file and grid with smooth = 3 lets the atoms through
+    _named_case("config1b_graphite_medium_smooth3", "graphite_medium.xyz", r, 0.02, 2.0, True, 3, [0, 223, 446, 700],
+                keep_every=3)
+    _named_case("config2_silicon_medium", "silicon_medium.xyz", r, 0.01, 2.0, False, 0, [0, 600, 1337],
+                detector_pixels=512, keep_every=8)
+    _named_case("config3_graphite_large", "graphite_large.xyz", r, 2 * np.pi / (r * 1023.5), 2.0, True, 25,
+                [0, 145, 435, 869], keep_every=3)
+
+
 def write_xyz(path, coords, elements):
     """XYZ text that load_xyz parses back to the very same doubles."""
     with open(path, "w") as fh:
@@ -228,7 +307,7 @@ def twostep():
 
 def main(argv):
     os.makedirs(OUT, exist_ok=True)
-    todo = argv or ["graphite262", "silicon256", "clipped128", "detector", "twostep", "pm6"]
+    todo = argv or ["graphite262", "silicon256", "clipped128", "detector", "twostep", "named", "pm6"]
     if "twostep" in todo:
         twostep()
     iq = q = None
@@ -243,6 +322,8 @@ def main(argv):
             g = np.load(os.path.join(OUT, "graphite262.npz"))
             iq, q = g["iq"], g["q_crop"]
         detector(iq, q)
+    if "named" in todo:
+        named()
     if "pm6" in todo:
         pm6()
 

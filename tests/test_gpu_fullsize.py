@@ -290,3 +290,84 @@ def test_wide_q_window_uses_the_full_last_pass():
     assert np.array_equal(a, b) and a.sum() > 0
     fs, ss = fused.vsum, staged.vsum
     assert float((fs - ss).abs().max()) <= 1e-5 * float(ss.max())
+
+
+NAMED_CASES = ["config1_graphite_medium", "config1b_graphite_medium_smooth3", "config2_silicon_medium",
+               "config3_graphite_large"]
+
+
+@pytest.mark.parametrize("name", NAMED_CASES)
+def test_named_config_files_against_reference_fixture(golden, name):
+    """BASELINE configs[0..2] on their NAMED input files at the configured sizes - graphite_medium.xyz with the
+    template values (N = 1048, Bluestein), silicon_medium.xyz at q = 0.01 (N = 2095, q_num 569) with a 512^2
+    stage B, graphite_large.xyz at N = 1024 with fill_bkg and smooth 25 - through the public drivers, against
+    fixtures produced by the UNMODIFIED reference (oracle/make_golden.py `named`).  Counts bit-exact, sums,
+    iq and detector image within 1e-4 of the reference maximum (and, stricter than the north-star bar, the
+    voxels away from the DC column within 1e-4 of THEIR maximum)."""
+    g = golden(name + ".npz")
+    r, q, max_q = float(g["r"]), float(g["q"]), float(g["max_q"])
+    iq, qx, qy, qz, eng = comparison.voxelgridmaker_fitting(
+        g["coords"], g["elements"], r, q, max_q, float(g["energy"]), fill_bkg=bool(g["fill_bkg"]),
+        smooth=int(g["smooth"]), phis=g["probe_phis"], return_state=True)
+    assert eng.N == int(g["grid_size"]) and len(eng.q_axis) == int(g["q_num"])
+    lo, hi = (int(v) for v in g["crop"])
+    assert eng.window == (lo, hi)
+    V = hi - lo
+    H, m = g["H"].astype(np.int64), g["m"].astype(np.int64)
+    assert np.array_equal(eng.count2.cpu().numpy().astype(np.int64).reshape(V, V), H[lo:hi, lo:hi])
+    assert np.array_equal(eng.row_hist.cpu().numpy().astype(np.int64), m[lo:hi])
+    p = g["pairs"]
+    inside = np.all((p >= lo) & (p < hi), axis=1)
+    pw = p[inside] - lo
+    want = g["vsum_pairs"][inside][:, lo:hi].astype(np.float64)
+    got = eng.sums()[pw[:, 0], pw[:, 1], :].astype(np.float64)
+    assert np.abs(got - want).max() <= 1e-4 * float(g["vsum_max"])
+    col_max = want.max(axis=1)
+    off = col_max < 0.5 * col_max.max()                  # every stored column but the one through q = 0
+    if off.any() and want[off].max() > 0:
+        assert np.abs(got[off] - want[off]).max() <= 1e-4 * want[off].max()
+    ip = g["iq_pairs"]
+    assert np.array_equal(qx, g["q_axis"][lo:hi])
+    assert np.abs(iq[ip[:, 0], ip[:, 1], :] - g["iq_values"]).max() <= 1e-4 * float(g["iq_max"])
+    if "det" in g.files:
+        psis, phis, thetas = g["det_psis"], g["det_phis"], g["det_thetas"]
+        det, _, _ = comparison.detectormaker_fitting(iq, qx, qy, qz, int(g["det_P"]), max_q, (90.0, 90.0, 90.0),
+                                                     ("psi", "phi", "psi"), psis, None, phis, None, thetas, None)
+        assert np.abs(det - g["det"]).max() <= 1e-4 * float(g["det_max"])
+
+
+def test_row_with_more_than_65535_atoms_takes_the_chunked_counters():
+    """A thin-z crystalline slab: one z pixel row holds > 65535 atoms, so the 16-bit species counters of the
+    fused row kernel are flushed in chunks (gx_fused.cu, `!single` branch).  Fused == staged == oracle."""
+    rng = np.random.default_rng(3)
+    n = 150_000
+    coords = np.empty((n, 3))
+    coords[:, 0] = rng.random(n) * 30.0
+    coords[:, 1] = rng.random(n) * 24.0
+    coords[:, 2] = rng.random(n) * 0.55                     # two pixel rows at r = 0.3: ~82 k and ~68 k atoms
+    coords[0, 2], coords[1, 2] = 0.0, 36.0                  # z extent of the slab (a third, sparse row)
+    elements = rng.choice(np.array(["C", "H", "S"]), size=n, p=[0.6, 0.3, 0.1])
+    r, max_q = 0.3, 1.5
+    q = synth.pow2_q_voxel(r, 256)
+    f = ox.f_values_for(elements, table=synth.fixed_f1f2)
+    setup = ox.stage_a_setup(coords, f, r, q, max_q)
+    phis = setup["phis"][[0, 17, 50]]
+    rows = np.bincount(((coords[:, 2] - coords[:, 2].min()) // r).astype(int))
+    assert rows.max() > 65535
+    iq, qx, qy, qz, eng = comparison.voxelgridmaker_fitting(coords, elements, r, q, max_q, 12700.0, fill_bkg=False,
+                                                            smooth=0, phis=phis, return_state=True)
+    o_iq, _, _, _, o_sum, o_cnt, _ = ox.voxelgridmaker(coords, f, r, q, max_q, False, 0, phis=phis)
+    lo, hi = eng.window
+    assert np.array_equal(eng.counts(), o_cnt.astype(np.int64)[lo:hi, lo:hi, lo:hi])
+    assert np.abs(eng.sums() - o_sum[lo:hi, lo:hi, lo:hi]).max() <= 1e-4 * o_sum.max()
+    assert np.abs(iq - o_iq).max() <= 1e-4 * o_iq.max()
+    staged = engine.SliceEngine(None, r, eng.q_axis, eng.N, eng.avg_voxel_f, eng.x_bound, eng.y_bound, False, 0,
+                                atoms=eng.atoms, window=eng.window)
+    staged.run(phis, staged=True)
+    assert np.array_equal(staged.counts(), eng.counts())
+    assert np.abs(staged.sums() - eng.sums()).max() <= 1e-5 * o_sum.max()
+    # with background + blend too (the chunked path applies (d, my) after the last chunk)
+    iq2, *_ = comparison.voxelgridmaker_fitting(coords, elements, r, q, max_q, 12700.0, fill_bkg=True, smooth=3,
+                                                phis=phis)
+    o_iq2 = ox.voxelgridmaker(coords, f, r, q, max_q, True, 3, phis=phis)[0]
+    assert np.abs(iq2 - o_iq2).max() <= 1e-4 * o_iq2.max()

@@ -363,6 +363,27 @@ def test_slabmaker_fitting_bit_exact_and_resident_handoff(tmp_path, cell, kind):
         c = comparison.voxelgridmaker_fitting(coords2, el2, r, q, max_q, 12700.0, fill_bkg=True, smooth=2)
         d = comparison.voxelgridmaker_fitting(coords2.copy(), el2.copy(), r, q, max_q, 12700.0, fill_bkg=True, smooth=2)
         assert c[0].shape == d[0].shape and np.abs(c[0] - d[0]).max() <= 1e-6 * d[0].max()
+        # partial edits - a few coordinates, a few element symbols - are seen too (whole-array checksums)
+        coords3, el3 = comparison.slabmaker_fitting(path, *size, *cell)
+        coords3[len(coords3) // 3:len(coords3) // 3 + 5, 1] += 0.8
+        swap = np.flatnonzero(el3 != "S")[7:12]
+        el3[swap] = "S"
+        e3 = comparison.voxelgridmaker_fitting(coords3, el3, r, q, max_q, 12700.0, fill_bkg=True, smooth=2)
+        g3 = comparison.voxelgridmaker_fitting(coords3.copy(), el3.copy(), r, q, max_q, 12700.0, fill_bkg=True, smooth=2)
+        assert np.abs(e3[0] - g3[0]).max() <= 1e-6 * g3[0].max()
+        assert np.abs(e3[0] - a[0]).max() > 1e-6 * a[0].max()           # and the edit changes the grid at all
+        # the voxel grid handed to detectormaker_fitting: edited in place -> the host array is read
+        det_args = (48, max_q, (90.0, 90.0, 90.0), ("psi", "phi", "psi"), np.linspace(70, 90, 3), None,
+                    np.linspace(0, 120, 4), None, np.array([0.0]), None)
+        iq, qx, qy, qz = a
+        img0 = comparison.detectormaker_fitting(iq, qx, qy, qz, *det_args)[0]          # resident copy
+        img0b = comparison.detectormaker_fitting(iq.copy(), qx, qy, qz, *det_args)[0]  # uploaded
+        assert np.abs(img0 - img0b).max() <= 1e-6 * img0b.max()
+        iq[iq.shape[0] // 2 - 3:iq.shape[0] // 2 + 3] *= 0.25                             # a mask over a few planes
+        img1 = comparison.detectormaker_fitting(iq, qx, qy, qz, *det_args)[0]
+        img1b = comparison.detectormaker_fitting(iq.copy(), qx, qy, qz, *det_args)[0]
+        assert np.abs(img1 - img1b).max() <= 1e-6 * img1b.max()
+        assert np.abs(img1 - img0).max() > 1e-3 * img0.max()
     finally:
         utilities.set_f1f2_provider(previous)
 

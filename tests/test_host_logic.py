@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libgiwaxs_b200.so does not export %s" % name
     assert declared == set(_lib.exported_symbols())
-    assert _lib.cdll().gx_abi_version() == 3
+    assert _lib.cdll().gx_abi_version() == _lib.ABI_VERSION
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="a GPU is present")

@@ -133,3 +133,37 @@ def test_two_step_matches_reference_fixture(golden):
     assert ox.most_common_element(s0[1]) == str(g["element"])
     two, tax, _, _ = ox.two_step_voxelgrid([s0, s1], r, q, max_q, 1, energy, **kw)
     assert np.array_equal(tax, g["two_step_axis"]) and np.array_equal(two, g["two_step_iq"])
+
+
+NAMED_CASES = ["config1_graphite_medium", "config1b_graphite_medium_smooth3", "config2_silicon_medium",
+               "config3_graphite_large"]
+
+
+@pytest.mark.parametrize("name", NAMED_CASES)
+def test_named_config_probe_slices_match_reference_fixture(golden, name):
+    """BASELINE configs[0..2] on their named input files at the configured grid sizes (N = 1048, 2095, 1024):
+    the oracle reproduces the unmodified reference's accumulators for the probe slices - the count grid
+    through its exact rank-1 factors, the sums on the stored (qy, qx) columns (stored as fp32)."""
+    g = golden(name + ".npz")
+    coords, elements = g["coords"], g["elements"]
+    f = ox.f_values_for(elements)
+    iq, qx, _, _, vsum, vcnt, setup = ox.voxelgridmaker(
+        coords, f, float(g["r"]), float(g["q"]), float(g["max_q"]), bool(g["fill_bkg"]), int(g["smooth"]),
+        phis=g["probe_phis"], threads=4)
+    assert setup["grid_size"] == int(g["grid_size"]) and setup["q_num"] == int(g["q_num"])
+    assert len(setup["phis"]) == int(g["n_phis_reference"])
+    H, m = g["H"].astype(np.float64), g["m"].astype(np.float64)
+    assert np.array_equal(vcnt, H[:, :, None] * m[None, None, :])
+    p = g["pairs"]
+    assert np.array_equal(vsum[p[:, 0], p[:, 1], :].astype(np.float32), g["vsum_pairs"])
+    lo, hi = g["crop"]
+    assert ox.crop_range(setup["q_axis"], float(g["max_q"])) == (int(lo), int(hi))
+    ip = g["iq_pairs"]
+    assert np.array_equal(iq[ip[:, 0], ip[:, 1], :].astype(np.float32), g["iq_values"])
+    if "det" in g.files:
+        P = int(g["det_P"])
+        psis, phis, thetas = g["det_psis"], g["det_phis"], g["det_thetas"]
+        det, _, _ = ox.detectormaker(iq, qx, qx, qx, P, float(g["max_q"]), (90.0, 90.0, 90.0), ("psi", "phi", "psi"),
+                                     psis, np.ones(len(psis)) / len(psis), phis, np.ones(len(phis)) / len(phis),
+                                     thetas, np.ones(len(thetas)) / len(thetas), threads=4)
+        assert np.array_equal(det.astype(np.float32), g["det"])
