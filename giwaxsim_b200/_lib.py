@@ -42,8 +42,8 @@ class FusedArgs(ctypes.Structure):
                  "d_work", "d_sum", "d_count2")] + \
                [(n, ctypes.c_double) for n in ("r", "pedestal_re", "pedestal_im", "avg_f_re", "avg_f_im")] + \
                [(n, ctypes.c_int32) for n in ("n_species", "n_phi", "N", "KC", "q_num", "row_lo", "row_hi",
-                                              "fill_bkg", "smooth_sigma", "phases")] + \
-               [("table", ctypes.c_float * (2 * GX_MAX_SPECIES))]
+                                              "fill_bkg", "smooth_sigma", "phases", "max_row_atoms", "pad")] + \
+               [("max_abs_f_im", ctypes.c_double), ("table_f64", ctypes.c_double * (2 * GX_MAX_SPECIES))]
 
 
 class SlabArgs(ctypes.Structure):
@@ -84,11 +84,12 @@ _PROTOTYPES = {
     "gx_axis_row_index": (_i, [_p, _i, _d, _d, _d, _i, _p, _p]),
     "gx_bin_slices": (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p]),
     "gx_row_histogram": (_i, [_p, _i, _i, _p, _p]),
-    "gx_voxel_finalize": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _d, _p, _p]),
+    "gx_voxel_finalize": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _d, _i64, _i64, _p, _p]),
     "gx_voxel_shell_scale": (_i, [_p, _i, _p, _d, _d, _d, _p]),
     "gx_slice_col_range": (_i, [_p, _i, _i, _p, _p]),
     "gx_window_indices": (_i, [_p, _i64, _i, _i, _i, _i, _p]),
     "gx_slices_fused": (_i, [_p, _p]),
+    "gx_fused_wants_zeroed_work": (_i, [_i, _i]),
     "gx_slab_tiles": (_i64, [_p]),
     "gx_slab_minmax": (_i, [_p, _p, _p]),
     "gx_slab_count": (_i, [_p, _p, _p, _p, _p, _p, _p, _p]),
@@ -110,7 +111,7 @@ _PROTOTYPES = {
     "gx_detector_epilogue": (_i, [_p, _i, _i, _i, _i, _p, _p]),
 }
 
-_UNCHECKED = {"gx_abi_version", "gx_last_error", "gx_fft_plan_bytes", "gx_fast_record_bytes",
+_UNCHECKED = {"gx_fused_wants_zeroed_work", "gx_abi_version", "gx_last_error", "gx_fft_plan_bytes", "gx_fast_record_bytes",
               "gx_affine_record_bytes", "gx_affine_plan_doubles", "gx_slab_tiles"}
 
 _cdll = None

@@ -149,52 +149,92 @@ extern "C" int gx_bin_slices(const float *d_iq2d, int batch, int rows, int cols,
 struct Aff { double a[9]; double Z; };
 
 // exp(-b k (qx^2+qy^2+qz^2)) = e_b(qx) e_b(qy) e_b(qz): the four Gaussians of the Cromer-Mann sum are
-// tabulated per axis value (4 x V fp64 exps in shared memory) instead of evaluated per voxel
-// (4 x V^3 fp64 exps made this kernel compute-bound at 0.6 TB/s); products differ from the
-// reference's single exp by a few fp64 ulps, far below the fp32 result.
-__global__ void __launch_bounds__(256)
+// tabulated per axis value (4 x V exps evaluated in fp64, once per block) instead of per voxel.
+// The kernel is a stream: 4 B read + 4 B written per voxel, so the per-voxel arithmetic is fp32 on
+// fp64-prepared factors (table entries, 1/count per column and per row): the weight
+// ((sum a_t e_t + c)/Z)^2 and the quotient carry a few fp32 ulps (~3e-7 relative; the result is
+// fp32 and the bar is 1e-4 of the maximum).  The first version did two fp64 divisions and eight
+// fp64 multiply-adds per voxel and ran at 0.96 TB/s (522 us for 403^3); this one is bound by HBM.
+// One warp per (iy, ix) column, lanes along iz (contiguous addresses).  [col_begin, col_end) selects
+// a slab of columns, so that N ranks can finalise 1/N of the grid each (reduce-scatter design).
+#define FIN_THREADS 256
+__global__ void __launch_bounds__(FIN_THREADS)
 voxel_finalize_kernel(const float *__restrict__ sum, const uint32_t *__restrict__ count3,
                       const uint32_t *__restrict__ count2, const uint32_t *__restrict__ m,
-                      int q_num, int lo, int V, const double *__restrict__ axis, Aff aff, int weighted, float *iq)
+                      int q_num, int lo, int V, const double *__restrict__ axis, Aff aff, int weighted,
+                      int col_begin, int col_end, float *iq)
 {
-    extern __shared__ double s_e[];                 // [4][V]
+    extern __shared__ float4 s_e[];                 // [V] (e_0..e_3)(q_i) then [V] floats 1/m
+    float *s_rm = reinterpret_cast<float *>(s_e + V);
     const double k = 1.0 / (16.0 * 3.14159265358979323846 * 3.14159265358979323846);
-    for (int t = threadIdx.x; t < 4 * V; t += blockDim.x) {
-        const int term = t / V, i = t - term * V;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) {
         const double q = axis[i + lo];
-        s_e[t] = exp(-aff.a[2 * term + 1] * (q * q) * k);
+        const double q2k = (q * q) * k;
+        s_e[i] = weighted ? make_float4((float)exp(-aff.a[1] * q2k), (float)exp(-aff.a[3] * q2k),
+                                        (float)exp(-aff.a[5] * q2k), (float)exp(-aff.a[7] * q2k))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t mi = m ? m[i + lo] : 1u;
+        s_rm[i] = mi ? (float)(1.0 / (double)mi) : 0.f;
     }
     __syncthreads();
-    // one (iy, ix) column of V voxels per loop trip: no 64-bit divisions per voxel, contiguous iz
-    const int columns = V * V;
-    for (int col = blockIdx.x; col < columns; col += gridDim.x) {
+    const float a0 = (float)(aff.a[0] / aff.Z), a1 = (float)(aff.a[2] / aff.Z), a2 = (float)(aff.a[4] / aff.Z),
+                a3 = (float)(aff.a[6] / aff.Z), c = (float)(aff.a[8] / aff.Z);
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int col = col_begin + blockIdx.x * wpb + (threadIdx.x >> 5); col < col_end; col += gridDim.x * wpb) {
         const int iy = col / V, ix = col - iy * V;
         const size_t yx = (size_t)(iy + lo) * q_num + (ix + lo);
-        const double cyx = count3 ? 0.0 : (double)count2[yx];
-        double exy[4];
-#pragma unroll
-        for (int term = 0; term < 4; ++term) exy[term] = s_e[term * V + ix] * s_e[term * V + iy];
-        for (int iz = threadIdx.x; iz < V; iz += blockDim.x) {
-            const size_t v = yx * q_num + (iz + lo);
-            const double cnt = count3 ? (double)count3[v] : cyx * (double)m[iz + lo];
-            float out = 0.f;
-            if (cnt != 0.0 && !weighted) {
-                out = (float)((double)sum[v] / cnt);        // generate_voxel_grid_low_mem: no f0 weighting
-            } else if (cnt != 0.0) {
-                double f = aff.a[8];
-#pragma unroll
-                for (int term = 0; term < 4; ++term) f += aff.a[2 * term] * (exy[term] * s_e[term * V + iz]);
-                f /= aff.Z;
-                out = (float)(((double)sum[v] / cnt) * f * f);
+        const float *src = sum + yx * q_num + lo;
+        float *dst = iq + (size_t)col * V;
+        if (count3) {
+            // explicit 3-D counts (worker API / small grids): exact quotient, weight in fp32
+            const uint32_t *c3 = count3 + yx * q_num + lo;
+            const float4 ex = s_e[ix], ey = s_e[iy];
+            for (int iz = lane; iz < V; iz += 32) {
+                const uint32_t cnt = c3[iz];
+                float out = 0.f;
+                if (cnt) {
+                    const double qv = (double)src[iz] / (double)cnt;
+                    if (weighted) {
+                        const float4 ez = s_e[iz];
+                        const float f = fmaf(a0, ex.x * ey.x * ez.x, fmaf(a1, ex.y * ey.y * ez.y,
+                                        fmaf(a2, ex.z * ey.z * ez.z, fmaf(a3, ex.w * ey.w * ez.w, c))));
+                        out = (float)(qv * (double)f * (double)f);
+                    } else {
+                        out = (float)qv;
+                    }
+                }
+                dst[iz] = out;
             }
-            iq[(size_t)col * V + iz] = out;
+            continue;
+        }
+        const uint32_t cyx = count2[yx];
+        if (cyx == 0u) {
+            for (int iz = lane; iz < V; iz += 32) dst[iz] = 0.f;
+            continue;
+        }
+        if (!weighted) {
+            // generate_voxel_grid_low_mem: plain sum/count, correctly rounded
+            for (int iz = lane; iz < V; iz += 32) {
+                const uint32_t mi = m[iz + lo];
+                dst[iz] = mi ? (float)((double)src[iz] / ((double)cyx * (double)mi)) : 0.f;
+            }
+            continue;
+        }
+        const float rc = (float)(1.0 / (double)cyx);
+        const float4 ex = s_e[ix], ey = s_e[iy];
+        const float e0 = a0 * (ex.x * ey.x), e1 = a1 * (ex.y * ey.y), e2 = a2 * (ex.z * ey.z), e3 = a3 * (ex.w * ey.w);
+        for (int iz = lane; iz < V; iz += 32) {
+            const float4 ez = s_e[iz];
+            const float f = fmaf(e0, ez.x, fmaf(e1, ez.y, fmaf(e2, ez.z, fmaf(e3, ez.w, c))));
+            dst[iz] = (src[iz] * rc) * s_rm[iz] * (f * f);
         }
     }
 }
 
 extern "C" int gx_voxel_finalize(const float *d_sum, const uint32_t *d_count3, const uint32_t *d_count2,
                                  const uint32_t *d_m, int q_num, int lo, int hi, const double *d_axis,
-                                 const double *h_aff9, double Z, float *d_iq, void *stream)
+                                 const double *h_aff9, double Z, int64_t col_begin, int64_t col_end,
+                                 float *d_iq, void *stream)
 {
     GX_REQUIRE(d_sum && d_axis && d_iq, "NULL pointer");
     GX_REQUIRE(d_count3 || (d_count2 && d_m), "count grids missing");
@@ -203,18 +243,23 @@ extern "C" int gx_voxel_finalize(const float *d_sum, const uint32_t *d_count3, c
     for (int i = 0; i < 9; ++i) aff.a[i] = h_aff9 ? h_aff9[i] : 0.0;
     aff.Z = h_aff9 ? Z : 1.0;
     const int V = hi - lo;
-    const size_t n = (size_t)V * V * V;
-    size_t blocks = (n + 255) / 256;
-    if (blocks > (size_t)GX_SM_COUNT * 16) blocks = (size_t)GX_SM_COUNT * 16;
-    const size_t smem = (size_t)4 * V * sizeof(double);
+    const int64_t columns = (int64_t)V * V;
+    if (col_end < 0) col_end = columns;                       // whole grid
+    GX_REQUIRE(col_begin >= 0 && col_begin <= col_end && col_end <= columns && columns < (int64_t)1 << 31,
+               "bad column range");
+    if (col_begin == col_end) return GX_OK;
+    const size_t smem = (size_t)V * (sizeof(float4) + sizeof(float));
     if (smem > 200 * 1024) {
         gx_set_error("gx_voxel_finalize: cropped grid side %d too large", V);
         return GX_ERR_UNSUPPORTED;
     }
     GX_CUDA(cudaFuncSetAttribute(voxel_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (blocks > (size_t)GX_SM_COUNT * 8) blocks = (size_t)GX_SM_COUNT * 8;
-    voxel_finalize_kernel<<<(int)blocks, 256, smem, gx_stream(stream)>>>(d_sum, d_count3, d_count2, d_m, q_num,
-                                                                        lo, V, d_axis, aff, h_aff9 != nullptr, d_iq);
+    const int wpb = FIN_THREADS / 32;
+    int64_t blocks = (col_end - col_begin + wpb - 1) / wpb;
+    if (blocks > (int64_t)GX_SM_COUNT * 8) blocks = (int64_t)GX_SM_COUNT * 8;
+    voxel_finalize_kernel<<<(int)blocks, FIN_THREADS, smem, gx_stream(stream)>>>(
+        d_sum, d_count3, d_count2, d_m, q_num, lo, V, d_axis, aff, h_aff9 != nullptr, (int)col_begin, (int)col_end,
+        d_iq);
     return gx_check_launch("gx_voxel_finalize");
 }
 

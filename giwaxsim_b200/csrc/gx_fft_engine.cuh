@@ -229,7 +229,7 @@ template <> struct GxDft<16> {
 // 38 complex additions + 7 real-by-complex multiply-adds for X[0], X[15] (76 flops instead of the
 // ~170 of the full radix-16 butterfly, 2 stores instead of 16); `wide` adds X[1] and X[14].
 // Results go to the slots the full pass would use (base + k2); the other slots keep stale data.
-GX_HD void gx_dft16_lowband(const float2 *v, bool wide, float2 *sb)
+GX_HD void gx_dft16_lowband_vals(const float2 *v, bool wide, float2 &x0, float2 &x15, float2 &x1, float2 &x14)
 {
     const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
     const float h = 0.70710678118654752440f;
@@ -237,22 +237,34 @@ GX_HD void gx_dft16_lowband(const float2 *v, bool wide, float2 *sb)
 #pragma unroll
     for (int n = 1; n < 8; ++n) { p[n] = gx_cadd(v[n], v[16 - n]); m[n] = gx_csub(v[n], v[16 - n]); }
     const float2 e = gx_cadd(v[0], v[8]), o = gx_csub(v[0], v[8]);
-    const float2 x0 = gx_cadd(gx_cadd(gx_cadd(e, p[4]), gx_cadd(p[1], p[7])),
-                              gx_cadd(gx_cadd(p[2], p[6]), gx_cadd(p[3], p[5])));
+    x0 = gx_cadd(gx_cadd(gx_cadd(e, p[4]), gx_cadd(p[1], p[7])),
+                 gx_cadd(gx_cadd(p[2], p[6]), gx_cadd(p[3], p[5])));
     const float2 d17 = gx_csub(p[1], p[7]), d26 = gx_csub(p[2], p[6]), d35 = gx_csub(p[3], p[5]);
     const float2 A = gx_caxpy(s1, d35, gx_caxpy(h, d26, gx_caxpy(c1, d17, o)));
     const float2 a17 = gx_cadd(m[1], m[7]), a26 = gx_cadd(m[2], m[6]), a35 = gx_cadd(m[3], m[5]);
     const float2 B = gx_caxpy(c1, a35, gx_caxpy(h, a26, gx_caxpy(s1, a17, m[4])));
-    sb[gx_phys(0)] = x0;
-    sb[gx_phys(15)] = make_float2(A.x - B.y, A.y + B.x);            // A + iB
+    x15 = make_float2(A.x - B.y, A.y + B.x);                        // A + iB
+    x1 = x14 = make_float2(0.f, 0.f);
     if (wide) {
-        sb[gx_phys(1)] = make_float2(A.x + B.y, A.y - B.x);         // A - iB
+        x1 = make_float2(A.x + B.y, A.y - B.x);                     // A - iB
         const float2 s17 = gx_cadd(p[1], p[7]), s35 = gx_cadd(p[3], p[5]);
         const float2 t = gx_csub(s17, s35), u = gx_csub(e, p[4]);
         const float2 A2 = gx_caxpy(h, t, u);
         const float2 w = gx_csub(gx_cadd(m[1], m[3]), gx_cadd(m[5], m[7])), g = gx_csub(m[2], m[6]);
         const float2 B2 = gx_caxpy(h, w, g);
-        sb[gx_phys(14)] = make_float2(A2.x - B2.y, A2.y + B2.x);    // A2 + iB2
+        x14 = make_float2(A2.x - B2.y, A2.y + B2.x);                // A2 + iB2
+    }
+}
+
+GX_HD void gx_dft16_lowband(const float2 *v, bool wide, float2 *sb)
+{
+    float2 x0, x15, x1, x14;
+    gx_dft16_lowband_vals(v, wide, x0, x15, x1, x14);
+    sb[gx_phys(0)] = x0;
+    sb[gx_phys(15)] = x15;
+    if (wide) {
+        sb[gx_phys(1)] = x1;
+        sb[gx_phys(14)] = x14;
     }
 }
 
@@ -311,6 +323,49 @@ GX_HD void gx_apply_twiddles(float2 *v, const float2 *twt)
             v[15 % R] = gx_cmul(v[15 % R], gx_cmul(w7, w8));
         }
     }
+}
+
+// ---- 4096 = 16 boxes x 256: the split transform of the TMA-fed column kernel -------------
+// z = 16 u + c: sample z lives in box c = z mod 16 at row u = z / 16 (slot 256 c + u of the work buffer).
+//   alpha + beta : Y_c[k'] = sum_u x[16 u + c] W_256^{u k'}   two radix-16 DIF passes INSIDE one box;
+//                  Y_c[k_a + 16 k_b] ends at padded slot 256 c + 16 k_a + k_b of the column buffer
+//   gamma        : X[k' + 256 m] = sum_c (W_4096^{c k'} Y_c[k']) W_16^{c m}   radix-16 DIT ACROSS the boxes
+// The kernel and the host emulation (tests/host_emul) share these functions.
+GX_HD int gx_split_slot(int z) { return (z & 15) * 256 + (z >> 4); }
+
+// alpha for butterfly t (0..15) of box c: src[n * src_stride] = row t + 16 n of the dense box,
+// sb = column buffer + gx_phys(256 c + t); tw1 = twiddle table of pass 1 of the 4096 schedule (W_256^{t k})
+template <int TWP>
+GX_HD void gx_split_alpha(const float2 *src, int src_stride, float2 *sb, const float2 *tw1, int t)
+{
+    float2 v[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) v[n] = src[n * src_stride];
+    GxDft<16>::run(v);
+    gx_apply_twiddles<16, 16, TWP>(v, tw1 + t);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sb[gx_phys(16 * k)] = v[k];
+}
+
+// beta for block blk of box c, in place: sb = column buffer + gx_phys(256 c + 16 blk)
+GX_HD void gx_split_beta(float2 *sb)
+{
+    float2 v[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) v[n] = sb[n];
+    GxDft<16>::run(v);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sb[k] = v[k];
+}
+
+// inputs of the gamma butterfly of k' (twiddled): col = column buffer, tw0 = table of pass 0 (W_4096^{t k})
+template <int TWP>
+GX_HD void gx_split_gamma_inputs(const float2 *col, const float2 *tw0, int kp, float2 *v)
+{
+    const float2 *sb = col + gx_phys(16 * (kp & 15) + (kp >> 4));
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = sb[273 * c];        // gx_phys(256 c + s) = 273 c + gx_phys(s) for s < 256
+    gx_apply_twiddles<16, 256, TWP>(v, tw0 + kp);
 }
 
 // ---- one pass over NBUF independent buffers of length M --------------------

@@ -21,6 +21,7 @@
 // CTAs resident at any moment work on the same few z-rows for all rotations of
 // the batch and the row's atoms are fetched from HBM once and re-read from L2.
 #include <stdlib.h>
+#include <cuda.h>
 #include "gx_project.cuh"
 #include "gx_fft_engine.cuh"
 
@@ -49,12 +50,46 @@ __constant__ double c_sn[GX_CONST_BATCH], c_cs[GX_CONST_BATCH], c_yrange[2 * GX_
 __constant__ int32_t c_bbox[4 * GX_CONST_BATCH], c_colrange[2 * GX_CONST_BATCH];
 __constant__ int32_t c_row_start[GX_CONST_ROWS + 2];
 
+// The constant tables belong to one launch at a time.  Launches of one device that come from DIFFERENT
+// streams are ordered through an event: the stream that staged the tables last records it after its row
+// kernel, and a launch from another stream waits for it before overwriting them (round 1 only documented
+// "one stream per device"; two engines on two streams silently corrupted each other).
+#include <mutex>
+static std::mutex g_const_mutex;
+static cudaStream_t g_const_stream[64];
+static cudaEvent_t g_const_event[64];
+static bool g_const_used[64];
+
+static int const_tables_acquire(cudaStream_t st)
+{
+    int dev = 0;
+    GX_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return GX_OK;
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    if (g_const_used[dev] && g_const_stream[dev] != st) GX_CUDA(cudaStreamWaitEvent(st, g_const_event[dev], 0));
+    return GX_OK;
+}
+
+static int const_tables_release(cudaStream_t st)
+{
+    int dev = 0;
+    GX_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return GX_OK;
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    if (!g_const_event[dev]) GX_CUDA(cudaEventCreateWithFlags(&g_const_event[dev], cudaEventDisableTiming));
+    GX_CUDA(cudaEventRecord(g_const_event[dev], st));
+    g_const_stream[dev] = st;
+    g_const_used[dev] = true;
+    return GX_OK;
+}
+
 struct FusedArgs {
     ProjArgs proj;
     const float2 *dmy;         // [n_phi][N] (num_missing - max_voxels, my): base = dmy.x * avg_f
     float af_re, af_im;
-    float2 ftab[GX_MAX_SPECIES];   // species f-values in the parameter (constant) bank: FFMA operands
-                                   // straight from c[][] cost neither registers nor shared-memory loads
+    int4 ffx[GX_MAX_SPECIES];      // species f-values split for the integer accumulators (see scatter_fixed)
+    float fx_scale_re, fx_scale_im;    // 2^k_re, 2^k_im (generic per-atom f path converts on the fly)
+    float fx_inv_re, fx_inv_im;        // 2^-k_re, 2^-k_im
     GxFftLayout lay;
     const float2 *plan;
     const int32_t *col;        // [n_phi][N] packed iy*q_num+ix or -1
@@ -69,6 +104,7 @@ struct FusedArgs {
     float dc_re, dc_im;        // pedestal * N^2
     int n_phi;
     int use_const;             // row-kernel scalars are in the constant tables
+    int chunk_atoms;           // atoms one pass of the integer accumulators may take (31-bit headroom)
 };
 
 __device__ __forceinline__ void active_band(const ProjArgs &a, int p, int &za, int &zb)
@@ -81,77 +117,129 @@ __device__ __forceinline__ void active_band(const ProjArgs &a, int p, int &za, i
 }
 
 // ------------------------------------------------------------------ F1 ----
-// Single-chunk rows (<= 65535 atoms, i.e. always except for huge crystalline rows): the pixels of
-// this thread's first butterfly are produced in one go from the species counters,
-//     v = (sum_w n0 f0 + n1 f1 + d * avg_f) * mz * my,
-// pixel-outer / plane-inner so that every counter load is independent of every other (the
-// plane-outer accumulation into px serialised on the LDS latency and spilled px under the
-// 64-register cap).  px arrives holding the prefetched (d, my) of each pixel and leaves holding v.
-// NSP > 0: number of species known at compile time (planes = (NSP + 1) / 2, f-values constant-bank
-//          operands, and the unused upper half of the last plane of an odd count costs nothing);
-// NSP == 0: any number of planes, f-values re-read from shared memory.
-// EXACT: N == S0 * R0 (power-of-two grid, no Bluestein padding) and NB0 * NT == S0: every pixel index is
-// in range, so clamps, range selects and the butterfly-count test disappear and all counter loads
-// become one base register plus immediates.
-template <int NSP, int NB0, int R0, int S0, int NT, bool EXACT>
-__device__ __forceinline__ void flush_finish(float2 (&px)[NB0][R0], const uint32_t *words, int NP,
-                                             const float2 *s_table, const float2 (&f)[GX_MAX_SPECIES], int npair,
-                                             int tid, int N, float af_re, float af_im, float mzv)
+// Integer row accumulators.  Each atom adds its scattering factor f = Z + f' + i f'' to its pixel with
+// three native shared-memory integer atomics (ATOMS.ADD; fp32 shared atomics are CAS loops on sm_100a
+// and would make the sum depend on atom order):
+//     plane 0  += Zr          Zr = round(Re f)            exact integer part
+//     plane 1  += Fr          Fr = round((Re f - Zr) 2^k_re)   |Re f - Zr| <= 0.5
+//     plane 2  += Fi          Fi = round(Im f 2^k_im)
+// k_re, k_im are the largest exponents for which a chunk of `max chunk atoms` atoms cannot overflow 31
+// bits even if all of them fall into one pixel (gx_slices_fused; 2740 atoms per row at the headline
+// size: k_re = 20, i.e. f' resolved to 4.8e-7 - the fp32 spacing of f itself is 4.8e-7 at f = 6).
+// Integer sums commute, so the row is independent of atom order (the reference's np.add.at is a
+// sequential fp64 sum; its threaded accumulators race).  The per-pixel completion is then
+//     v = ((Zr + Fr 2^-k_re) + d avg_f.re,  Fi 2^-k_im + d avg_f.im) * mz * my
+// - three loads and three conversions per pixel whatever the number of species.  (Round 1 counted atoms
+// per species in 16-bit fields and formed sum_s n_s f_s per pixel: 27 instructions per pixel with five
+// species, 24 % of the kernel's instructions; this flush is 12.)
+template <int U, bool TAIL, bool SPECIES>
+__device__ __forceinline__ void scatter_fixed_batch(const ProjArgs &a, const int4 *s_ffx, float sc_re, float sc_im,
+                                                    int i0, int end, int nt, double s, double c, double shift,
+                                                    double r, double inv_r, int32_t *acc, int NP)
+{
+    const int N = a.N, last = end - 1;
+    double x[U], y[U];
+    unsigned sp[U];
+    float2 fv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int i = TAIL ? min(i0 + u * nt, last) : i0 + u * nt;
+        x[u] = ld_stream_f64(a.xs + i);
+        y[u] = ld_stream_f64(a.ys + i);
+        if (SPECIES) sp[u] = ld_stream_u8(a.species + i);
+        else fv[u] = __ldg(a.f + i);
+    }
+    int q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) q[u] = atom_y_pixel_int(x[u], y[u], s, c, shift, r, inv_r);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const bool ok = (!TAIL || i0 + u * nt < end) && ((unsigned)q[u] < (unsigned)N);
+        int4 F;
+        if (SPECIES) {
+            F = s_ffx[sp[u]];
+        } else {
+            const float zr = rintf(fv[u].x);
+            F = make_int4(__float2int_rn(zr), __float2int_rn((fv[u].x - zr) * sc_re), __float2int_rn(fv[u].y * sc_im), 0);
+        }
+        // no branch around an atom: an atom outside the grid adds zeros to pixel 0
+        const int word = ok ? q[u] : 0;
+        atomicAdd(acc + word, ok ? F.x : 0);
+        atomicAdd(acc + NP + word, ok ? F.y : 0);
+        atomicAdd(acc + 2 * NP + word, ok ? F.z : 0);
+    }
+}
+
+// atoms [beg, end) of one z-row: whole batches of 4 x blockDim atoms, then 2, 1 and a per-thread tail
+// (no arithmetic for atoms that do not exist)
+template <bool SPECIES>
+__device__ __forceinline__ void scatter_fixed(const ProjArgs &a, const int4 *s_ffx, float sc_re, float sc_im,
+                                              int beg, int end, double s, double c, double shift, int32_t *acc, int NP)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double r = a.r, inv_r = 1.0 / a.r;
+    int i0 = beg + tid;
+    int left = end - beg;
+    for (; left >= 4 * nt; left -= 4 * nt, i0 += 4 * nt)
+        scatter_fixed_batch<4, false, SPECIES>(a, s_ffx, sc_re, sc_im, i0, end, nt, s, c, shift, r, inv_r, acc, NP);
+    if (left >= 2 * nt) {
+        scatter_fixed_batch<2, false, SPECIES>(a, s_ffx, sc_re, sc_im, i0, end, nt, s, c, shift, r, inv_r, acc, NP);
+        left -= 2 * nt; i0 += 2 * nt;
+    }
+    if (left >= nt) {
+        scatter_fixed_batch<1, false, SPECIES>(a, s_ffx, sc_re, sc_im, i0, end, nt, s, c, shift, r, inv_r, acc, NP);
+        left -= nt; i0 += nt;
+    }
+    if (i0 < end) scatter_fixed_batch<1, false, SPECIES>(a, s_ffx, sc_re, sc_im, i0, end, nt, s, c, shift, r, inv_r, acc, NP);
+}
+
+// Pixels of this thread's first butterflies from the accumulators.  FINISH: px arrives holding the
+// prefetched (d, my) of each pixel and leaves holding the completed value; else the atom sums are added to px
+// (rows counted in several chunks).  EXACT: N == S0 * R0 and NB0 * NT == S0 (power-of-two grid, no Bluestein
+// padding): every pixel index is in range, all loads are one base register plus immediates.
+template <int NB0, int R0, int S0, int NT, bool EXACT, bool FINISH>
+__device__ __forceinline__ void flush_fixed(float2 (&px)[NB0][R0], const int32_t *acc, int NP, int tid, int N,
+                                            float inv_re, float inv_im, float af_re, float af_im, float mzv)
 {
 #pragma unroll
     for (int i = 0; i < NB0; ++i) {
         const int t = tid + i * NT;
         if (!EXACT && t >= S0) {
+            if (FINISH) {
 #pragma unroll
-            for (int n = 0; n < R0; ++n) px[i][n] = make_float2(0.f, 0.f);
+                for (int n = 0; n < R0; ++n) px[i][n] = make_float2(0.f, 0.f);
+            }
             continue;
         }
-        // no branch per pixel (a pixel beyond N reads a clamped address and is zeroed by a select):
-        // the R0 x planes counter loads are then free to be issued back to back
 #pragma unroll
         for (int n = 0; n < R0; ++n) {
             const int y = t + S0 * n;
             const int yy = EXACT ? y : min(y, N - 1);
-            float sx = 0.f, sy = 0.f;
-            if (NSP > 0) {
-#pragma unroll
-                for (int w = 0; w < (NSP + 1) / 2; ++w) {
-                    // counts -> fp32 through the 2^23 mantissa trick (PRMT + FADD, no I2F)
-                    const uint32_t cnt = words[w * NP + yy];
-                    const float n0 = __uint_as_float(__byte_perm(cnt, 0x4B000000u, 0x7610)) - 8388608.f;
-                    sx = fmaf(n0, f[2 * w].x, sx);
-                    sy = fmaf(n0, f[2 * w].y, sy);
-                    if (2 * w + 1 < NSP) {
-                        const float n1 = __uint_as_float(__byte_perm(cnt, 0x4B000000u, 0x7632)) - 8388608.f;
-                        sx = fmaf(n1, f[2 * w + 1].x, sx);
-                        sy = fmaf(n1, f[2 * w + 1].y, sy);
-                    }
-                }
-            } else {
-                for (int w = 0; w < npair; ++w) {
-                    const uint32_t cnt = words[w * NP + yy];
-                    const float2 f0 = s_table[2 * w], f1 = s_table[2 * w + 1];
-                    const float n0 = __uint_as_float(0x4B000000u | (cnt & 0xffffu)) - 8388608.f;
-                    const float n1 = __uint_as_float(__byte_perm(cnt, 0x4B000000u, 0x7632)) - 8388608.f;
-                    sx = fmaf(n1, f1.x, fmaf(n0, f0.x, sx));
-                    sy = fmaf(n1, f1.y, fmaf(n0, f0.y, sy));
-                }
+            const float zr = (float)acc[yy];
+            const float fr = (float)acc[NP + yy];
+            const float fi = (float)acc[2 * NP + yy];
+            const float sx = fmaf(fr, inv_re, zr), sy = fi * inv_im;
+            if (FINISH) {
+                const float2 dm = px[i][n];
+                const float m = (EXACT || y < N) ? mzv * dm.y : 0.f;
+                px[i][n] = make_float2(fmaf(dm.x, af_re, sx) * m, fmaf(dm.x, af_im, sy) * m);
+            } else if (EXACT || y < N) {
+                px[i][n].x += sx;
+                px[i][n].y += sy;
             }
-            const float2 dm = px[i][n];
-            const float m = (EXACT || y < N) ? mzv * dm.y : 0.f;
-            px[i][n] = make_float2(fmaf(dm.x, af_re, sx) * m, fmaf(dm.x, af_im, sy) * m);
         }
     }
 }
 
 // Pixel ownership follows the first FFT pass: butterfly t of pass 0 combines the
 // pixels t + S0*n (n < R0), so the thread that runs butterfly t also gathers the
-// species counts of exactly those pixels, completes them in registers and feeds
+// accumulators of exactly those pixels, completes them in registers and feeds
 // them straight into its radix-R0 butterfly: the finished row is never written
 // to shared memory in natural order and never read back by pass 0.
-// NSP: number of species fixed at compile time (1..6; the flush is then fully
-// unrolled with the f-values as constant-bank operands), 0 = any number (generic loop).
-template <int L, bool SPECIES, bool BLUE, int NSP>
+// SPECIES: atoms carry a species code (f from the 16-entry table) / a per-atom complex64 f.
+// ROWPERM: row z is written to slot 256 (z mod 16) + z / 16 of the work buffer, the order the
+// TMA-fed column kernel consumes (16 chunks of 256 rows, each a 256-point sub-transform).
+template <int L, bool SPECIES, bool BLUE, bool ROWPERM>
 __global__ void __launch_bounds__(PROJ_THREADS, (L >= 13) ? 2 : GX_F1_MINBLOCKS)
 slice_rows_fused(FusedArgs fa)
 {
@@ -162,8 +250,8 @@ slice_rows_fused(FusedArgs fa)
     constexpr int NB0 = (S0 + NT - 1) / NT;                // pass-0 butterflies per thread
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *buf = reinterpret_cast<float2 *>(smem_raw);
-    uint32_t *words = reinterpret_cast<uint32_t *>(smem_raw);   // aliases buf (used strictly before it)
-    __shared__ float2 s_table[GX_MAX_SPECIES];
+    int32_t *acc = reinterpret_cast<int32_t *>(smem_raw);     // aliases buf (used strictly before it)
+    __shared__ int4 s_ffx[GX_MAX_SPECIES];
     const ProjArgs &a = fa.proj;
     const int p = blockIdx.x, z = blockIdx.y;
     const int N = BLUE ? a.N : M;                          // power-of-two grids are transformed at their own length
@@ -190,105 +278,57 @@ slice_rows_fused(FusedArgs fa)
     else if (a.sigma > 0) { za = 0; zb = N - 1; }
     else { za = z_min; zb = z_max; }
     if (z < za || z > zb) return;
+    jhi = min(jhi, jlo + fa.KC);                           // the work buffer holds KC columns per row
     if (jhi <= jlo) return;
 
-    const int NP = (N + 3) & ~3;                           // counter plane stride (words)
+    const int NP = (N + 3) & ~3;                           // accumulator plane stride (words)
     const float2 *dmy = fa.dmy + (size_t)p * N;
     float2 px[NB0][R0];
     bool finished = false;                                 // px already holds the completed pixels
 
-    if (SPECIES) {
-        const bool single = end - beg <= 65535;            // 16-bit counters cannot wrap: one scatter, one flush
-        // the f-value table in shared memory is only read by the generic flush and by chunked rows
-        if ((NSP == 0 || !single) && tid < GX_MAX_SPECIES)
-            s_table[tid] = tid < a.n_species ? a.table[tid] : make_float2(0.f, 0.f);
-        const int npair = (a.n_species + 1) >> 1;
-        uint4 *words4 = reinterpret_cast<uint4 *>(smem_raw);
-        if constexpr (EXACT && NSP > 0 && (M / 4) % NT == 0) {
-            // plane count and length known at compile time: straight-line 16-byte stores, immediate offsets
+    if (SPECIES && tid < GX_MAX_SPECIES) s_ffx[tid] = fa.ffx[tid];
+    int4 *acc4 = reinterpret_cast<int4 *>(smem_raw);
+    if constexpr (EXACT && (3 * M / 4) % NT == 0) {
+        // plane length known at compile time: straight-line 16-byte stores, immediate offsets
 #pragma unroll
-            for (int k = 0; k < ((NSP + 1) / 2) * (M / 4) / NT; ++k) words4[tid + k * NT] = make_uint4(0u, 0u, 0u, 0u);
-        } else {
-            for (int y = tid; y < npair * (NP / 4); y += NT) words4[y] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        __syncthreads();
-        if (single) {
-            // (hand-pipelining the atom loads across the zeroing barrier and across batches was
-            // measured: no gain, the kernel is bound by instruction issue, not by load latency)
-            scatter_species(a, beg, end, s, c, shift, words, NP);
-            // (d, my) of this thread's pixels, requested before the barrier so that the L2 round
-            // trip overlaps the wait for the slowest warp
-#pragma unroll
-            for (int i = 0; i < NB0; ++i)
-#pragma unroll
-                for (int n = 0; n < R0; ++n) {
-                    const int t = tid + i * NT, y = t + S0 * n;
-                    px[i][n] = __ldg(dmy + (EXACT ? y : min(y, N - 1)));   // clamped: pixels beyond N are zeroed later
-                }
-            __syncthreads();
-            flush_finish<NSP, NB0, R0, S0, NT, EXACT>(px, words, NP, s_table, fa.ftab, npair, tid, N, fa.af_re, fa.af_im, mzv);
-            __syncthreads();   // every counter read is done before buf is written
-            finished = true;
-        } else {
-#pragma unroll
-            for (int i = 0; i < NB0; ++i)
-#pragma unroll
-                for (int n = 0; n < R0; ++n) px[i][n] = make_float2(0.f, 0.f);
-            // rows with more than 65535 atoms are counted in chunks
-            for (int c0 = beg; c0 < end; c0 += 65535) {
-                const int c1 = min(c0 + 65535, end);
-                scatter_species(a, c0, c1, s, c, shift, words, NP);
-                __syncthreads();
-                const bool more = c1 < end;
-                for (int w = 0; w < npair; ++w) {
-                    const float2 f0 = s_table[2 * w], f1 = s_table[2 * w + 1];
-                    uint32_t *plane = words + w * NP;
-#pragma unroll
-                    for (int i = 0; i < NB0; ++i) {
-                        const int t = tid + i * NT;
-#pragma unroll
-                        for (int n = 0; n < R0; ++n) {
-                            const int y = t + S0 * n;
-                            if (t < S0 && y < N) {
-                                const uint32_t cnt = plane[y];
-                                const float n0 = __uint_as_float(0x4B000000u | (cnt & 0xffffu)) - 8388608.f;
-                                const float n1 = __uint_as_float(__byte_perm(cnt, 0x4B000000u, 0x7632)) - 8388608.f;
-                                px[i][n].x = fmaf(n1, f1.x, fmaf(n0, f0.x, px[i][n].x));
-                                px[i][n].y = fmaf(n1, f1.y, fmaf(n0, f0.y, px[i][n].y));
-                            }
-                        }
-                    }
-                }
-                __syncthreads();   // every counter read is done before the next chunk / before buf is written
-                if (more) {
-                    for (int y = tid; y < npair * (NP / 4); y += NT) words4[y] = make_uint4(0u, 0u, 0u, 0u);
-                    __syncthreads();
-                }
-            }
-        }
+        for (int k = 0; k < (3 * M / 4) / NT; ++k) acc4[tid + k * NT] = make_int4(0, 0, 0, 0);
     } else {
-        // generic per-atom f: accumulate straight into the (padded) row buffer
-        const double r = a.r, inv_r = 1.0 / a.r;
-        for (int y = tid; y < M; y += NT) buf[gx_phys(y)] = make_float2(0.f, 0.f);
-        __syncthreads();
-        for (int i = beg + tid; i < end; i += NT) {
-            const double q = atom_y_pixel(a.xs[i], a.ys[i], s, c, shift, r, inv_r);
-            if (q < (double)N) {
-                const float2 f = a.f[i];
-                float2 *dst = &buf[gx_phys((int)q)];
-                atomicAdd(&dst->x, f.x);
-                atomicAdd(&dst->y, f.y);
-            }
-        }
-        __syncthreads();
+        for (int y = tid; y < 3 * (NP / 4); y += NT) acc4[y] = make_int4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    if (end - beg <= fa.chunk_atoms) {
+        // one scatter, one flush (every row of a non-crystalline slab)
+        scatter_fixed<SPECIES>(a, s_ffx, fa.fx_scale_re, fa.fx_scale_im, beg, end, s, c, shift, acc, NP);
+        // (d, my) of this thread's pixels, requested before the barrier so that the L2 round
+        // trip overlaps the wait for the slowest warp
 #pragma unroll
         for (int i = 0; i < NB0; ++i)
 #pragma unroll
             for (int n = 0; n < R0; ++n) {
                 const int t = tid + i * NT, y = t + S0 * n;
-                if (t < S0 && y < N) px[i][n] = buf[gx_phys(y)];
+                px[i][n] = __ldg(dmy + (EXACT ? y : min(y, N - 1)));   // clamped: pixels beyond N are zeroed later
             }
         __syncthreads();
+        flush_fixed<NB0, R0, S0, NT, EXACT, true>(px, acc, NP, tid, N, fa.fx_inv_re, fa.fx_inv_im, fa.af_re, fa.af_im, mzv);
+        __syncthreads();   // every accumulator read is done before buf is written
+        finished = true;
+    } else {
+        // rows with more atoms than one chunk may hold without overflow are summed chunk by chunk in fp32
+#pragma unroll
+        for (int i = 0; i < NB0; ++i)
+#pragma unroll
+            for (int n = 0; n < R0; ++n) px[i][n] = make_float2(0.f, 0.f);
+        for (int c0 = beg; c0 < end; c0 += fa.chunk_atoms) {
+            const int c1 = min(c0 + fa.chunk_atoms, end);
+            scatter_fixed<SPECIES>(a, s_ffx, fa.fx_scale_re, fa.fx_scale_im, c0, c1, s, c, shift, acc, NP);
+            __syncthreads();
+            flush_fixed<NB0, R0, S0, NT, EXACT, false>(px, acc, NP, tid, N, fa.fx_inv_re, fa.fx_inv_im, 0.f, 0.f, 0.f);
+            __syncthreads();   // every accumulator read is done before the next chunk / before buf is written
+            if (c1 < end) {
+                for (int y = tid; y < 3 * (NP / 4); y += NT) acc4[y] = make_int4(0, 0, 0, 0);
+                __syncthreads();
+            }
+        }
     }
 
     // complete the pixels (pedestal-free) in registers and run the first pass on them:
@@ -344,7 +384,8 @@ slice_rows_fused(FusedArgs fa)
     if (full) gx_dft_block<L, 1, 0, BLUE ? 1 : 0, true>(buf, fa.lay, fa.plan, tid, NT);
 
     // kept q-columns only; shifted column j holds unshifted coefficient j - N/2 (mod N)
-    float2 *dst = fa.work + ((size_t)p * N + z) * fa.KC;
+    const int slot = ROWPERM ? gx_split_slot(z) : z;
+    float2 *dst = fa.work + ((size_t)p * N + slot) * fa.KC;
     const int half = N / 2;
     for (int jj = tid; jj < jhi - jlo; jj += NT) {
         int k = jlo + jj - half;
@@ -427,6 +468,181 @@ slice_cols_fused(FusedArgs fa)
     }
 }
 
+// ------------------------------------------------------- F2, TMA-fed (L = 12) ----
+// Same result as slice_cols_fused for power-of-two 4096 grids, restructured around asynchronous tile
+// movement: the [n_phi N, KC] complex64 work buffer is a 2-D tensor map and a dedicated producer thread
+// streams 256-row x 4-column boxes (cp.async.bulk.tensor.2d -> UTMALDG, completion on mbarriers) through an
+// 8-slot ring while 16 consumer warps transform.  Persistent CTAs (one per SM) walk the (rotation, column
+// tile) list, so the boxes of the next tile are already landing while the current tile finishes.
+//
+// The column transform is split so that two of its three passes need only ONE box:
+//   z = 16 u + c  (F1 writes row z to slot 256 c + u: ROWPERM)
+//   Y_c[k'] = sum_u x[16 u + c] W_256^{u k'}                       256-point DIF inside box c (passes alpha, beta)
+//   X[k' + 256 m] = sum_c W_4096^{c k'} Y_c[k'] W_16^{c m}         radix-16 DIT across the boxes   (pass gamma)
+// alpha reads the dense box ([row][4 columns], 32 B per row: lanes = 4 rows x 4 columns of a half-warp are 128
+// contiguous bytes) and writes the padded per-column layout, beta is in place, gamma reads 16 values 273 slots
+// apart, forms only the outputs the voxel window keeps (m = 0, 15, sometimes 1, 14: gx_dft16_lowband) and adds
+// |X|^2 straight into the voxel sum: the transformed column is never stored, not even in shared memory.
+#define F2T_TC 4
+#define F2T_ROWS 256
+#define F2T_NBOX 16
+#define F2T_RING 8
+#define F2T_CONSUMERS 512
+#define F2T_THREADS (F2T_CONSUMERS + 32)
+#define F2T_BOX_BYTES (F2T_ROWS * F2T_TC * 8)
+#define F2T_BS 4372                     // float2 per column buffer: >= 4369 and == 4 (mod 16)
+#define F2T_SMEM (F2T_RING * F2T_BOX_BYTES + F2T_TC * F2T_BS * 8 + 2 * F2T_RING * 8)
+
+__device__ __forceinline__ uint32_t gx_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gx_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gx_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gx_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(gx_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(gx_smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(gx_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_barrier(int id, int count)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+__global__ void __launch_bounds__(F2T_THREADS, 1)
+slice_cols_tma(FusedArgs fa, const __grid_constant__ CUtensorMap tmap)
+{
+    constexpr int M = 4096, BS = F2T_BS;
+    extern __shared__ __align__(128) unsigned char smem_tma[];
+    float2 *ring = reinterpret_cast<float2 *>(smem_tma);
+    float2 *work = reinterpret_cast<float2 *>(smem_tma + F2T_RING * F2T_BOX_BYTES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_tma + F2T_RING * F2T_BOX_BYTES + F2T_TC * BS * 8);
+    uint64_t *empty = full + F2T_RING;
+    const int tid = threadIdx.x, N = M;
+    if (tid == 0) {
+        for (int i = 0; i < F2T_RING; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 2); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int tiles = fa.KC / F2T_TC;
+    const int total = fa.n_phi * tiles;
+
+    if (tid >= F2T_CONSUMERS) {
+        // ---- producer: one thread keeps the ring full, across tile boundaries
+        if (tid == F2T_CONSUMERS) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+            for (int f = blockIdx.x; f < total; f += gridDim.x) {
+                const int p = f % fa.n_phi, tile = f / fa.n_phi;
+                const int kc = min(fa.colrange[2 * p + 1] - fa.colrange[2 * p], fa.KC);
+                if (tile * F2T_TC >= kc) continue;
+                for (int c = 0; c < F2T_NBOX; ++c) {
+                    const int slot = c & (F2T_RING - 1);
+                    mbar_wait(empty + slot, ((c >> 3) & 1) ^ 1);      // n-th refill of a slot: n = 2 tile_iter + c / 8
+                    mbar_expect_tx(full + slot, F2T_BOX_BYTES);
+                    tma_load_2d(reinterpret_cast<unsigned char *>(ring) + slot * F2T_BOX_BYTES, &tmap, tile * F2T_TC,
+                                p * N + c * F2T_ROWS, full + slot);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- consumers
+    const int warp = tid >> 5, lane = tid & 31;
+    const int pair = warp >> 1;                       // boxes pair and pair + 8 of every tile; ring slot = pair
+    const int e = (warp & 1) * 32 + lane;             // 0..63 inside the pair
+    const float2 *tw0 = fa.plan + fa.lay.tw_off[0], *tw1 = fa.plan + fa.lay.tw_off[1];
+    const int half = N / 2;
+    const int klo = fa.row_lo - half, khi = fa.row_hi - half;
+    const bool lowband = klo >= -512 && khi <= 512;
+    for (int f = blockIdx.x; f < total; f += gridDim.x) {
+        const int p = f % fa.n_phi, tile = f / fa.n_phi;
+        const int jlo = fa.colrange[2 * p];
+        const int kc = min(fa.colrange[2 * p + 1] - jlo, fa.KC);
+        const int jj0 = tile * F2T_TC;
+        if (jj0 >= kc) continue;
+#pragma unroll 1
+        for (int r = 0; r < 2; ++r) {
+            const int c = pair + 8 * r;
+            // alpha: radix-16 DIF, stride 16, of the 256-point sub-transform; dense box -> padded column buffers
+            {
+                const int col = e & 3, t = e >> 2;
+                mbar_wait(full + pair, r);
+                const float2 *st = ring + pair * (F2T_ROWS * F2T_TC) + t * F2T_TC + col;
+                float2 v[16];
+#pragma unroll
+                for (int n = 0; n < 16; ++n) v[n] = st[n * 16 * F2T_TC];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + pair);          // this warp has read its half of the box
+                gx_split_alpha<GX_PASS1_TWP>(v, 1, work + col * BS + gx_phys(c * F2T_ROWS + t), tw1, t);
+            }
+            named_barrier(1 + pair, 64);
+            // beta: radix-16, stride 1, in place
+            {
+                const int blk = e & 15, col = e >> 4;
+                gx_split_beta(work + col * BS + gx_phys(c * F2T_ROWS + 16 * blk));
+            }
+        }
+        named_barrier(9, F2T_CONSUMERS);
+        // gamma: radix-16 DIT across the boxes, only the kept outputs, binned at once
+#pragma unroll 1
+        for (int g = tid; g < F2T_TC * 256; g += F2T_CONSUMERS) {
+            const int col = g >> 8, kp = g & 255;
+            if (jj0 + col >= kc) continue;
+            const int j = jlo + jj0 + col;
+            const int yx = fa.col[(size_t)p * N + j];
+            if (yx < 0) continue;
+            if (kp == 0) atomicAdd(&fa.count2[yx], 1u);
+            float2 v[16];
+            gx_split_gamma_inputs<GX_TWP>(work + col * BS, tw0, kp, v);
+            float *dst = fa.vsum + (size_t)yx * fa.q_num;
+            if (lowband) {
+                const bool w1 = kp + 256 < khi, w14 = kp - 512 >= klo;
+                float2 x0, x15, x1, x14;
+                gx_dft16_lowband_vals(v, w1 || w14, x0, x15, x1, x14);
+                if (kp == 0 && j == half) { x0.x += fa.dc_re; x0.y += fa.dc_im; }
+                int iz;
+                if (kp < khi && (iz = fa.row_index[kp + half]) >= 0) atomicAdd(dst + iz, x0.x * x0.x + x0.y * x0.y);
+                if (kp - 256 >= klo && (iz = fa.row_index[kp - 256 + half]) >= 0) atomicAdd(dst + iz, x15.x * x15.x + x15.y * x15.y);
+                if (w1 && (iz = fa.row_index[kp + 256 + half]) >= 0) atomicAdd(dst + iz, x1.x * x1.x + x1.y * x1.y);
+                if (w14 && (iz = fa.row_index[kp - 512 + half]) >= 0) atomicAdd(dst + iz, x14.x * x14.x + x14.y * x14.y);
+            } else {
+                GxDft<16>::run(v);
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const int kz = kp + 256 * m;                       // unshifted coefficient index
+                    int i = kz + half;
+                    if (i >= N) i -= N;
+                    if (i < fa.row_lo || i >= fa.row_hi) continue;
+                    const int iz = fa.row_index[i];
+                    if (iz < 0) continue;
+                    float2 x = v[m];
+                    if (kz == 0 && j == half) { x.x += fa.dc_re; x.y += fa.dc_im; }
+                    atomicAdd(dst + iz, x.x * x.x + x.y * x.y);
+                }
+            }
+        }
+        named_barrier(9, F2T_CONSUMERS);      // every read of the column buffers is done before the next tile's alpha
+    }
+}
+
 // -------------------------------------------------------------- col range ----
 __global__ void __launch_bounds__(256)
 col_range_kernel(const int32_t *__restrict__ col, int N, int32_t *range)
@@ -452,6 +668,44 @@ extern "C" int gx_slice_col_range(const int32_t *d_col, int n_phi, int N, int32_
 }
 
 // ---------------------------------------------------------------- launch ----
+typedef CUresult (*gx_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                       const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D tensor map of the [rows, KC] complex64 work buffer, box = 256 rows x 4 columns (one ring slot)
+static int work_tensor_map(CUtensorMap *map, void *work, size_t rows, int KC)
+{
+    static gx_encode_tiled_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        GX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) {
+            gx_set_error("gx_slices_fused: cuTensorMapEncodeTiled not available from this driver");
+            return GX_ERR_UNSUPPORTED;
+        }
+        encode = reinterpret_cast<gx_encode_tiled_fn>(fn);
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)KC, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)KC * 8};
+    const cuuint32_t box[2] = {F2T_TC, F2T_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, work, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        gx_set_error("gx_slices_fused: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return GX_ERR_CUDA;
+    }
+    return GX_OK;
+}
+
+// the TMA-fed column kernel covers the power-of-two 4096 grid (the headline size)
+static bool cols_tma_ok(const FusedArgs &fa, int L, bool blue)
+{
+    return L == 12 && !blue && fa.KC % 8 == 0 && (reinterpret_cast<uintptr_t>(fa.work) & 15) == 0 &&
+           !getenv("GIWAXS_B200_NO_TMA");
+}
+
 template <int L, int TC>
 static int launch_fused(const FusedArgs &fa, bool species, int phases, cudaStream_t st)
 {
@@ -461,47 +715,50 @@ static int launch_fused(const FusedArgs &fa, bool species, int phases, cudaStrea
     constexpr int BS = BS0 + ((WANT - (BS0 % 16)) + 16) % 16;
     const int N = fa.proj.N;
     const bool blue = fa.lay.bluestein != 0;
+    const bool tma = cols_tma_ok(fa, L, blue);
     size_t smem1 = (size_t)gx_phys_len(M) * sizeof(float2);
-    if (species) {
-        size_t w = (size_t)((fa.proj.n_species + 1) / 2) * ((N + 3) & ~3) * sizeof(uint32_t);
-        if (w > smem1) smem1 = w;
-    }
+    const size_t acc_bytes = (size_t)3 * ((N + 3) & ~3) * sizeof(int32_t);
+    if (acc_bytes > smem1) smem1 = acc_bytes;
     const size_t smem2 = (size_t)BS * TC * sizeof(float2);
     if (smem1 > 227 * 1024 || smem2 > 227 * 1024) {
         gx_set_error("gx_slices_fused: shared memory need (%zu / %zu B) exceeds 227 KB", smem1, smem2);
         return GX_ERR_UNSUPPORTED;
     }
     const dim3 grid1(fa.n_phi, N);
-#define GX_LAUNCH_ROWS(SP, BL, NPR)                                                                         \
+#define GX_LAUNCH_ROWS(SP, BL, RP)                                                                          \
     do {                                                                                                    \
-        GX_CUDA(cudaFuncSetAttribute(slice_rows_fused<L, SP, BL, NPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        GX_CUDA(cudaFuncSetAttribute(slice_rows_fused<L, SP, BL, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)smem1));                                                          \
-        slice_rows_fused<L, SP, BL, NPR><<<grid1, PROJ_THREADS, smem1, st>>>(fa);                          \
-    } while (0)
-    // compile-time species counts only for the large transforms (L >= 10), where F1 dominates the run
-    const int nsp = (species && L >= 10 && fa.proj.n_species >= 1 && fa.proj.n_species <= 6) ? fa.proj.n_species : 0;
-#define GX_ROWS_NSP(BL)                                                                  \
-    do {                                                                                 \
-        switch (nsp) {                                                                   \
-        case 1: GX_LAUNCH_ROWS(true, BL, (L >= 10 ? 1 : 0)); break;                      \
-        case 2: GX_LAUNCH_ROWS(true, BL, (L >= 10 ? 2 : 0)); break;                      \
-        case 3: GX_LAUNCH_ROWS(true, BL, (L >= 10 ? 3 : 0)); break;                      \
-        case 4: GX_LAUNCH_ROWS(true, BL, (L >= 10 ? 4 : 0)); break;                      \
-        case 5: GX_LAUNCH_ROWS(true, BL, (L >= 10 ? 5 : 0)); break;                      \
-        case 6: GX_LAUNCH_ROWS(true, BL, (L >= 10 ? 6 : 0)); break;                      \
-        default: GX_LAUNCH_ROWS(true, BL, 0); break;                                     \
-        }                                                                                \
+        slice_rows_fused<L, SP, BL, RP><<<grid1, PROJ_THREADS, smem1, st>>>(fa);                           \
     } while (0)
     if (phases & 1) {
-        if (species && blue) GX_ROWS_NSP(true);
-        else if (species) GX_ROWS_NSP(false);
-        else if (blue) GX_LAUNCH_ROWS(false, true, 0);
-        else GX_LAUNCH_ROWS(false, false, 0);
+        if constexpr (L == 12) {
+            if (tma) { if (species) GX_LAUNCH_ROWS(true, false, true); else GX_LAUNCH_ROWS(false, false, true); }
+        }
+        if (!tma) {
+            if (species && blue) GX_LAUNCH_ROWS(true, true, false);
+            else if (species) GX_LAUNCH_ROWS(true, false, false);
+            else if (blue) GX_LAUNCH_ROWS(false, true, false);
+            else GX_LAUNCH_ROWS(false, false, false);
+        }
         if (int e = gx_check_launch("slice_rows_fused")) return e;
     }
-#undef GX_ROWS_NSP
 #undef GX_LAUNCH_ROWS
     if (!(phases & 2)) return GX_OK;
+    if (tma) {
+        CUtensorMap map;
+        if (int e = work_tensor_map(&map, fa.work, (size_t)fa.n_phi * N, fa.KC)) return e;
+        static int sms = 0;
+        if (!sms) {
+            int dev = 0;
+            GX_CUDA(cudaGetDevice(&dev));
+            GX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        }
+        const int total = fa.n_phi * (fa.KC / F2T_TC);
+        GX_CUDA(cudaFuncSetAttribute(slice_cols_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, F2T_SMEM));
+        slice_cols_tma<<<total < sms ? total : sms, F2T_THREADS, F2T_SMEM, st>>>(fa, map);
+        return gx_check_launch("slice_cols_tma");
+    }
     int nt = TC * M / 16;
     nt = nt < 64 ? 64 : (nt > 512 ? 512 : nt);
 #if GX_F2_TILE_FAST
@@ -519,6 +776,37 @@ static int launch_fused(const FusedArgs &fa, bool species, int phases, cudaStrea
     return gx_check_launch("slice_cols_fused");
 }
 
+// Split of the species table for the integer accumulators (see scatter_fixed): the exponents are the largest
+// for which `chunk` atoms in ONE pixel cannot overflow 31 bits.
+static void fixed_point_plan(const gx_fused_args *h, FusedArgs &fa)
+{
+    double max_frac = 0.5, max_im = 1e-30;
+    for (int k = 0; k < h->n_species; ++k) {
+        const double im = h->table_f64[2 * k + 1];
+        if (fabs(im) > max_im) max_im = fabs(im);
+    }
+    if (h->n_species == 0) max_im = h->max_abs_f_im > 0.0 ? h->max_abs_f_im : 128.0;
+    int chunk = h->max_row_atoms > 0 ? h->max_row_atoms : 65535;
+    if (chunk > 65535) chunk = 65535;
+    if (chunk < 256) chunk = 256;
+    const double room = 2147483647.0 / (double)chunk;
+    int k_re = (int)floor(log2(room / max_frac)), k_im = (int)floor(log2(room / max_im));
+    if (k_re > 24) k_re = 24;
+    if (k_im > 24) k_im = 24;
+    fa.chunk_atoms = chunk;
+    fa.fx_scale_re = (float)ldexp(1.0, k_re); fa.fx_scale_im = (float)ldexp(1.0, k_im);
+    fa.fx_inv_re = (float)ldexp(1.0, -k_re); fa.fx_inv_im = (float)ldexp(1.0, -k_im);
+    for (int k = 0; k < GX_MAX_SPECIES; ++k) {
+        int4 v = make_int4(0, 0, 0, 0);
+        if (k < h->n_species) {
+            const double re = h->table_f64[2 * k], im = h->table_f64[2 * k + 1];
+            const double zr = nearbyint(re);
+            v = make_int4((int)zr, (int)nearbyint(ldexp(re - zr, k_re)), (int)nearbyint(ldexp(im, k_im)), 0);
+        }
+        fa.ffx[k] = v;
+    }
+}
+
 extern "C" int gx_slices_fused(const gx_fused_args *h, void *stream)
 {
     GX_REQUIRE(h != NULL, "NULL argument block");
@@ -526,11 +814,12 @@ extern "C" int gx_slices_fused(const gx_fused_args *h, void *stream)
                h->d_dmy && h->d_plan && h->d_col && h->d_colrange && h->d_row_index && h->d_work &&
                h->d_sum && h->d_count2, "NULL pointer");
     GX_REQUIRE(h->n_species >= 0 && h->n_species <= GX_MAX_SPECIES, "n_species out of range");
-    GX_REQUIRE(h->n_species == 0 ? h->d_f != NULL : (h->d_species != NULL && h->d_table != NULL),
-               "species/f inputs missing");
+    GX_REQUIRE(h->n_species == 0 ? h->d_f != NULL : h->d_species != NULL, "species/f inputs missing");
     GX_REQUIRE(h->d_mz, "mask vector missing");
     GX_REQUIRE(h->n_phi > 0 && h->n_phi <= 65535 && h->N >= 16 && h->KC > 0 && h->q_num > 0, "bad sizes");
     GX_REQUIRE(h->row_lo >= 0 && h->row_hi <= h->N && h->row_lo <= h->row_hi, "bad kept-row range");
+    for (int k = 0; k < h->n_species; ++k)
+        GX_REQUIRE(fabs(h->table_f64[2 * k]) < 1e6 && fabs(h->table_f64[2 * k + 1]) < 1e6, "scattering factor out of range");
     FusedArgs fa;
     ProjArgs &a = fa.proj;
     a.xs = h->d_xs; a.ys = h->d_ys; a.species = h->d_species; a.f = reinterpret_cast<const float2 *>(h->d_f);
@@ -539,8 +828,7 @@ extern "C" int gx_slices_fused(const gx_fused_args *h, void *stream)
     a.base = NULL; a.my = NULL; a.mz = h->d_mz;
     fa.dmy = reinterpret_cast<const float2 *>(h->d_dmy);
     fa.af_re = (float)h->avg_f_re; fa.af_im = (float)h->avg_f_im;
-    for (int k = 0; k < GX_MAX_SPECIES; ++k)
-        fa.ftab[k] = k < h->n_species ? make_float2(h->table[k].x, h->table[k].y) : make_float2(0.f, 0.f);
+    fixed_point_plan(h, fa);
     a.N = h->N; a.r = h->r; a.ped_re = (float)h->pedestal_re; a.ped_im = (float)h->pedestal_im;
     a.fill_bkg = h->fill_bkg; a.sigma = h->smooth_sigma;
     fa.lay = gx_fft_layout(h->N);
@@ -561,6 +849,7 @@ extern "C" int gx_slices_fused(const gx_fused_args *h, void *stream)
     cudaStream_t st = gx_stream(stream);
     fa.use_const = (h->n_phi <= GX_CONST_BATCH && h->N <= GX_CONST_ROWS && !getenv("GIWAXS_B200_NO_CONST")) ? 1 : 0;
     if (fa.use_const && (phases & 1)) {
+        if (int e = const_tables_acquire(st)) return e;
         const size_t n = (size_t)h->n_phi;
         const cudaMemcpyKind dd = cudaMemcpyDeviceToDevice;
         GX_CUDA(cudaMemcpyToSymbolAsync(c_sn, h->d_sin, n * sizeof(double), 0, dd, st));
@@ -570,18 +859,33 @@ extern "C" int gx_slices_fused(const gx_fused_args *h, void *stream)
         GX_CUDA(cudaMemcpyToSymbolAsync(c_colrange, h->d_colrange, 2 * n * sizeof(int32_t), 0, dd, st));
         GX_CUDA(cudaMemcpyToSymbolAsync(c_row_start, h->d_row_start, ((size_t)h->N + 2) * sizeof(int32_t), 0, dd, st));
     }
+    int rc;
     switch (fa.lay.L) {
-    case 4: return launch_fused<4, 8>(fa, species, phases, st);
-    case 5: return launch_fused<5, 8>(fa, species, phases, st);
-    case 6: return launch_fused<6, 8>(fa, species, phases, st);
-    case 7: return launch_fused<7, 8>(fa, species, phases, st);
-    case 8: return launch_fused<8, 8>(fa, species, phases, st);
-    case 9: return launch_fused<9, 8>(fa, species, phases, st);
-    case 10: return launch_fused<10, 8>(fa, species, phases, st);
-    case 11: return launch_fused<11, 8>(fa, species, phases, st);
-    case 12: return launch_fused<12, GX_F2_TC12>(fa, species, phases, st);
-    case 13: return launch_fused<13, 2>(fa, species, phases, st);
+    case 4: rc = launch_fused<4, 8>(fa, species, phases, st); break;
+    case 5: rc = launch_fused<5, 8>(fa, species, phases, st); break;
+    case 6: rc = launch_fused<6, 8>(fa, species, phases, st); break;
+    case 7: rc = launch_fused<7, 8>(fa, species, phases, st); break;
+    case 8: rc = launch_fused<8, 8>(fa, species, phases, st); break;
+    case 9: rc = launch_fused<9, 8>(fa, species, phases, st); break;
+    case 10: rc = launch_fused<10, 8>(fa, species, phases, st); break;
+    case 11: rc = launch_fused<11, 8>(fa, species, phases, st); break;
+    case 12: rc = launch_fused<12, GX_F2_TC12>(fa, species, phases, st); break;
+    case 13: rc = launch_fused<13, 2>(fa, species, phases, st); break;
+    default:
+        gx_set_error("gx_slices_fused: unsupported log2 size %d", fa.lay.L);
+        rc = GX_ERR_UNSUPPORTED;
     }
-    gx_set_error("gx_slices_fused: unsupported log2 size %d", fa.lay.L);
-    return GX_ERR_UNSUPPORTED;
+    if (fa.use_const && (phases & 1) && rc == GX_OK) rc = const_tables_release(st);
+    return rc;
+}
+
+// 1 when gx_slices_fused will consume the work buffer in the permuted row order of the TMA-fed column
+// kernel for this grid size / column count (the caller must then hand it a buffer whose never-written
+// rows are zero: the TMA boxes cover every row slot, also those of rows outside the atom band).
+extern "C" int gx_fused_wants_zeroed_work(int N, int KC)
+{
+    FusedArgs fa;
+    fa.KC = KC; fa.work = nullptr;
+    const GxFftLayout lay = gx_fft_layout(N);
+    return (lay.M != 0 && cols_tma_ok(fa, lay.L, lay.bluestein != 0)) ? 1 : 0;
 }

@@ -445,10 +445,13 @@ class AtomSet:
             self.n_species = len(table)
             d_species = species if isinstance(species, torch.Tensor) else _dev(species, device)
             self.species = torch.empty(self.A, dtype=torch.uint8, device=device)
-            self.table_host = np.asarray(table, dtype=np.complex128).astype(np.complex64).view(np.float32).copy()
+            self.table_c128 = np.asarray(table, dtype=np.complex128).copy()
+            self.table_host = self.table_c128.astype(np.complex64).view(np.float32).copy()
             self.table = _dev(self.table_host, device)
         else:
-            d_f = _dev(np.asarray(f_values, dtype=np.complex128).astype(np.complex64).view(np.float32), device)
+            f_host = np.asarray(f_values, dtype=np.complex128)
+            self.max_abs_f_im = float(np.abs(f_host.imag).max()) if f_host.size else 0.0
+            d_f = _dev(f_host.astype(np.complex64).view(np.float32), device)
             self.f = torch.empty(2 * self.A, dtype=torch.float32, device=device)
         self.xs = torch.empty(self.A, dtype=torch.float64, device=device)
         self.ys = torch.empty(self.A, dtype=torch.float64, device=device)
@@ -459,6 +462,15 @@ class AtomSet:
              ptr(d_species), ptr(d_f), ptr(self.xs), ptr(self.ys), ptr(self.perm),
              ptr(self.species), ptr(self.f), ptr(self.row_start), ptr(cursor), st)
         self._cand = None
+        self._max_row_atoms = None
+
+    @property
+    def max_row_atoms(self):
+        """Most atoms in one z pixel row (sizes the fixed-point scale of the fused row kernel)."""
+        if self._max_row_atoms is None:
+            rs = self.row_start[:self.N + 1]
+            self._max_row_atoms = int((rs[1:] - rs[:-1]).max().item())
+        return self._max_row_atoms
 
     def candidates(self):
         """(xs, ys, count) of the atoms that can be extreme in y' (built lazily, once)."""
@@ -695,8 +707,11 @@ class SliceEngine:
         args.pedestal_re, args.pedestal_im = self.pedestal.real, self.pedestal.imag
         args.avg_f_re, args.avg_f_im = self.avg_voxel_f.real, self.avg_voxel_f.imag
         if a.n_species:
-            for k, v in enumerate(a.table_host):
-                args.table[k] = float(v)
+            for k, v in enumerate(a.table_c128):
+                args.table_f64[2 * k], args.table_f64[2 * k + 1] = float(v.real), float(v.imag)
+        else:
+            args.max_abs_f_im = a.max_abs_f_im
+        args.max_row_atoms = a.max_row_atoms
         args.n_species, args.n_phi, args.N, args.KC, args.q_num = a.n_species, n, self.N, self.KC, self.q_out
         args.row_lo, args.row_hi = self.row_lo, self.row_hi
         args.fill_bkg, args.smooth_sigma = int(self.fill_bkg), self.sigma
@@ -719,7 +734,9 @@ class SliceEngine:
                 # equal batches (1800 rotations: 29 x 63 instead of 28 x 64 + 8): no short last launch pair
                 B = -(-len(phis) // -(-len(phis) // B))
             N = self.N
-            work = torch.empty(min(B, len(phis)) * N * self.KC * 2, dtype=torch.float32, device=self.device)
+            # rows outside the atom band are never written; the TMA-fed column kernel reads every row slot
+            alloc = torch.zeros if call("gx_fused_wants_zeroed_work", N, self.KC) else torch.empty
+            work = alloc(min(B, len(phis)) * N * self.KC * 2, dtype=torch.float32, device=self.device)
             # per-rotation tables for the whole run in one set of launches, then one
             # pair of fused launches per batch on views of them
             full = self._timed("prepare", self.prepare, phis)
@@ -836,7 +853,8 @@ def crop_range(axis, max_val):
     return int(idx[0]), int(idx[-1]) + 1
 
 
-def finalize_voxels(vsum, count3, count2, row_hist, q_axis, max_q, device, window=None, crop=True, f0=True):
+def finalize_voxels(vsum, count3, count2, row_hist, q_axis, max_q, device, window=None, crop=True, f0=True,
+                    out=None, columns=(0, -1), sync=True):
     """sum/count, crop, carbon f0 weighting -> (iq fp32 device [V,V,V], axis).
     window: the accumulators already cover only that index window (SliceEngine(window=...)).
     crop=False keeps the whole axis and f0=False skips the weighting: the plain grid
@@ -845,19 +863,20 @@ def finalize_voxels(vsum, count3, count2, row_hist, q_axis, max_q, device, windo
     lo, hi = crop_range(q_axis, max_q) if crop else (0, q_num)
     V = hi - lo
     with torch.cuda.device(device):
-        iq = torch.empty(V * V * V, dtype=torch.float32, device=device)
+        iq = out if out is not None else torch.empty(V * V * V, dtype=torch.float32, device=device)
         aff = np.asarray(CARBON_AFF, dtype=np.float64) if f0 else None
         if window is not None:
             if tuple(window) != (lo, hi):
                 raise ValueError("accumulator window %s is not the crop range %s" % (tuple(window), (lo, hi)))
             d_axis = _dev(q_axis[lo:hi], device)
             call("gx_voxel_finalize", ptr(vsum), ptr(count3), ptr(count2), ptr(row_hist), V, 0, V,
-                 ptr(d_axis), ptr(aff), CARBON_Z, ptr(iq), _stream())
+                 ptr(d_axis), ptr(aff), CARBON_Z, int(columns[0]), int(columns[1]), ptr(iq), _stream())
         else:
             d_axis = _dev(q_axis, device)
             call("gx_voxel_finalize", ptr(vsum), ptr(count3), ptr(count2), ptr(row_hist), q_num, lo, hi,
-                 ptr(d_axis), ptr(aff), CARBON_Z, ptr(iq), _stream())
-        torch.cuda.current_stream().synchronize()
+                 ptr(d_axis), ptr(aff), CARBON_Z, int(columns[0]), int(columns[1]), ptr(iq), _stream())
+        if sync:
+            torch.cuda.current_stream().synchronize()
     return iq.view(V, V, V), q_axis[lo:hi].copy()
 
 

@@ -110,7 +110,7 @@ def add_f0_q_3d(iq, qx_axis, qy_axis, qz_axis, element):
         aff = np.asarray(CROMER_MANN[element], dtype=np.float64)
         d_axis = engine._dev(qx_axis, dev)
         call("gx_voxel_finalize", ptr(d_sum), ptr(ones), None, None, V, 0, V, ptr(d_axis),
-             ptr(aff), float(ATOMIC_NUMBER[element]), ptr(out), engine._stream())
+             ptr(aff), float(ATOMIC_NUMBER[element]), 0, -1, ptr(out), engine._stream())
         return out.cpu().to(torch.float64).numpy().reshape(V, V, V)
 
 

@@ -218,10 +218,14 @@ int gx_row_histogram(const int32_t *d_row, int n, int q_num, uint32_t *d_m, void
  * count2[iy,ix]*m[iz] when d_count3 is NULL.  d_axis [q_num] fp64 voxel axis.
  * d_iq [(hi-lo)^3] fp32.     (comparison.py:769-786, vg.py:16-48,828-857)
  * h_aff9 == NULL: plain sum/count without the f0 weight, as returned by
- * generate_voxel_grid_low_mem (vg.py:633-641).                              */
+ * generate_voxel_grid_low_mem (vg.py:633-641).
+ * Only the (iy, ix) columns col_begin <= iy*V+ix < col_end of the cropped grid
+ * are written (col_end < 0: all) - N ranks finalise 1/N of the grid each after
+ * a reduce-scatter of the partial sums.                                     */
 int gx_voxel_finalize(const float *d_sum, const uint32_t *d_count3, const uint32_t *d_count2,
                       const uint32_t *d_m, int q_num, int lo, int hi, const double *d_axis,
-                      const double *h_aff9, double Z, float *d_iq, void *stream);
+                      const double *h_aff9, double Z, int64_t col_begin, int64_t col_end,
+                      float *d_iq, void *stream);
 
 /* d_iq[iy,ix,iz] *= factor where lower < sqrt(qx^2+qy^2+qz^2) <= upper, the
  * radius formed like NumPy forms it (each product, sum and the root rounded
@@ -265,9 +269,17 @@ typedef struct gx_fused_args {
     double r, pedestal_re, pedestal_im, avg_f_re, avg_f_im;
     int32_t n_species, n_phi, N, KC, q_num, row_lo, row_hi, fill_bkg, smooth_sigma;
     int32_t phases;              /* 0 or 3: both launches; 1: row kernel only; 2: column kernel only (per-kernel timing) */
-    gx_float2 table[GX_MAX_SPECIES];   /* host copy of d_table (kernel-parameter operands) */
+    int32_t max_row_atoms;       /* most atoms in one z pixel row (0: unknown -> 65535): sizes the fixed-point scale */
+    int32_t pad;
+    double max_abs_f_im;         /* n_species == 0: bound on |Im f| over the atoms (0: unknown -> 128) */
+    double table_f64[2 * GX_MAX_SPECIES];   /* host copy of the species f-values, (re, im) pairs, full precision */
 } gx_fused_args;
 int gx_slices_fused(const gx_fused_args *h_args, void *stream);
+/* 1 when, for this grid side and kept-column bound, gx_slices_fused feeds the column
+ * transform by TMA from a work buffer in permuted row order: d_work must then have
+ * been zero-filled once before the first call of a run (rows outside the atom band
+ * are never written, and the TMA boxes read every row slot).                    */
+int gx_fused_wants_zeroed_work(int N, int KC);
 
 /* Restrict bin indices to the crop window lo <= i < hi of downselect_voxelgrid
  * (voxelgrids.py:16-48; the crop commutes with the accumulation): entries

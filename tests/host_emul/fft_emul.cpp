@@ -73,3 +73,42 @@ extern "C" int emul_dft_lowband(const float *plan, const float *in, float *out, 
     for (int k = klo; k < khi; ++k) o[k - klo] = gx_dft_result<L, 0>(s.data(), g, p, k < 0 ? k + M : k);
     return 0;
 }
+
+// The split 4096-point transform of the TMA-fed column kernel (16 boxes of 256 rows; gx_split_*):
+// rows are placed at gx_split_slot(z) as the row kernel does, every box goes through alpha and beta,
+// gamma forms all 16 outputs (full != 0) or only the kept band through gx_dft16_lowband_vals.
+// out[k - klo] for klo <= k < khi (negative k = coefficient 4096 + k).
+extern "C" int emul_dft_split(const float *plan, const float *in, float *out, int klo, int khi, int full)
+{
+    constexpr int M = 4096;
+    GxFftLayout g = gx_fft_layout(M);
+    const float2 *p = reinterpret_cast<const float2 *>(plan);
+    const float2 *x = reinterpret_cast<const float2 *>(in);
+    float2 *o = reinterpret_cast<float2 *>(out);
+    std::vector<float2> dense(M), col(gx_phys_len(M));
+    for (int z = 0; z < M; ++z) dense[gx_split_slot(z)] = x[z];
+    for (int c = 0; c < 16; ++c) {
+        for (int t = 0; t < 16; ++t)
+            gx_split_alpha<1>(dense.data() + 256 * c + t, 16, col.data() + gx_phys(256 * c + t), p + g.tw_off[1], t);
+        for (int blk = 0; blk < 16; ++blk) gx_split_beta(col.data() + gx_phys(256 * c + 16 * blk));
+    }
+    std::vector<float2> X(M, make_float2(0.f, 0.f));
+    for (int kp = 0; kp < 256; ++kp) {
+        float2 v[16];
+        gx_split_gamma_inputs<1>(col.data(), p + g.tw_off[0], kp, v);
+        if (full) {
+            GxDft<16>::run(v);
+            for (int m = 0; m < 16; ++m) X[kp + 256 * m] = v[m];
+        } else {
+            if (klo < -512 || khi > 512) return -1;
+            const bool w1 = kp + 256 < khi, w14 = kp - 512 >= klo;
+            float2 x0, x15, x1, x14;
+            gx_dft16_lowband_vals(v, w1 || w14, x0, x15, x1, x14);
+            X[kp] = x0; X[kp + 3840] = x15;
+            if (w1) X[kp + 256] = x1;
+            if (w14) X[kp + 3584] = x14;
+        }
+    }
+    for (int k = klo; k < khi; ++k) o[k - klo] = X[k < 0 ? k + M : k];
+    return 0;
+}
