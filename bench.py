@@ -75,7 +75,8 @@ def config_dict(cfg, world):
     return {"workload": "BASELINE configs[4]: synthetic random-atom slab, fill_bkg=True, smooth=25",
             "atoms": cfg["n_atoms"], "grid": cfg["grid_size"], "phi_slices": cfg["n_phi"], "q_num": 569,
             "detector_pixels": cfg["num_pixels"], "orientations": int(len(cfg["psis"])),
-            "parallelism": "phi/psi sharded over %d rank(s), all-reduce of partial grids" % world,
+            "parallelism": "phi/psi sharded over %d rank(s); partial sums reduce-scattered, finalise sharded, iq "
+                           "all-gathered (NCCL behind the C ABI)" % world,
             "l2": "inputs larger than L2 (atoms 170 MB, each slice grid 134 MB); no flush needed"}
 
 
@@ -302,6 +303,7 @@ def run_ours(args):
     def stage_a():
         eng.vsum.zero_()
         eng.count2.zero_()
+        eng.vsum_is_partial = False
         eng.run(my_phis)
         state["iq"], state["axis"] = parallel.combine_and_finalize(eng, q_axis, max_q, dev, window=window)
 
@@ -311,7 +313,7 @@ def run_ours(args):
         if len(w_sel):
             det.accumulate(gx, gy, gz, R_sel, w_sel, image=img)
         if reduce and world > 1:
-            parallel.all_reduce_sum([img])
+            parallel.all_reduce_image(img, dev)
         return engine.detector_epilogue(img, P, P, True, dev, finish=True)
 
     def stage_b():
@@ -349,9 +351,13 @@ def run_ours(args):
 
     # ---- the run of record checks itself (not timed)
     check = {}
-    vsum_l1 = eng.vsum.double().abs().sum()
     if world > 1 and getattr(eng, "vsum_is_partial", False):
+        # after the reduce-scatter only this rank's slab of columns holds totals
+        cpr, _ = parallel.padded_columns(eng.q_out, world)
+        vsum_l1 = eng.vsum_store[rank * cpr * eng.q_out:(rank + 1) * cpr * eng.q_out].double().abs().sum()
         dist.all_reduce(vsum_l1)
+    else:
+        vsum_l1 = eng.vsum.double().abs().sum()
     full_digest = digest(eng.count2, eng.row_hist, float(vsum_l1.item()), state["iq"], state["det"])
     if rank == 0:
         # (1) the count grid of the WHOLE run against the oracle's bin indices, bit for bit

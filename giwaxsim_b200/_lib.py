@@ -43,7 +43,8 @@ class FusedArgs(ctypes.Structure):
                [(n, ctypes.c_double) for n in ("r", "pedestal_re", "pedestal_im", "avg_f_re", "avg_f_im")] + \
                [(n, ctypes.c_int32) for n in ("n_species", "n_phi", "N", "KC", "q_num", "row_lo", "row_hi",
                                               "fill_bkg", "smooth_sigma", "phases", "max_row_atoms", "pad")] + \
-               [("max_abs_f_im", ctypes.c_double), ("table_f64", ctypes.c_double * (2 * GX_MAX_SPECIES))]
+               [(n, ctypes.c_double) for n in ("max_row_abs_re", "max_row_abs_im", "max_abs_f_re", "max_abs_f_im")] + \
+               [("table_f64", ctypes.c_double * (2 * GX_MAX_SPECIES))]
 
 
 class SlabArgs(ctypes.Structure):
@@ -90,6 +91,12 @@ _PROTOTYPES = {
     "gx_window_indices": (_i, [_p, _i64, _i, _i, _i, _i, _p]),
     "gx_slices_fused": (_i, [_p, _p]),
     "gx_fused_wants_zeroed_work": (_i, [_i, _i]),
+    "gx_comm_unique_id": (_i, [_p]),
+    "gx_comm_init": (_i, [_p, _i, _i, _p]),
+    "gx_comm_destroy": (_i, [_p]),
+    "gx_comm_all_reduce": (_i, [_p, _p, _i64, _i, _p]),
+    "gx_comm_reduce_scatter_f32": (_i, [_p, _p, _i64, _p]),
+    "gx_comm_all_gather_f32": (_i, [_p, _p, _i64, _p]),
     "gx_slab_tiles": (_i64, [_p]),
     "gx_slab_minmax": (_i, [_p, _p, _p]),
     "gx_slab_count": (_i, [_p, _p, _p, _p, _p, _p, _p, _p]),

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libgiwaxs_b200.so")
 SOURCES = ["gx_api.cu", "gx_atoms.cu", "gx_project.cu", "gx_fft.cu", "gx_bin.cu", "gx_detector.cu",
-           "gx_detector_affine.cu", "gx_fused.cu", "gx_slab.cu"]
+           "gx_detector_affine.cu", "gx_fused.cu", "gx_slab.cu", "gx_comm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=default", "--expt-relaxed-constexpr", "-DGX_TWP=1",
@@ -64,7 +64,7 @@ def build(force=False, verbose=False):
                 sys.stderr.write(log)
     if force or _stale(LIB, objs):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                      "-Xcompiler", "-fPIC"]
+                                                      "-Xcompiler", "-fPIC", "-ldl"]
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (p.stdout, p.stderr))

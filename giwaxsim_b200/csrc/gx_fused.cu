@@ -87,7 +87,7 @@ struct FusedArgs {
     ProjArgs proj;
     const float2 *dmy;         // [n_phi][N] (num_missing - max_voxels, my): base = dmy.x * avg_f
     float af_re, af_im;
-    int4 ffx[GX_MAX_SPECIES];      // species f-values split for the integer accumulators (see scatter_fixed)
+    int2 ffx[GX_MAX_SPECIES];      // species f-values in fixed point for the integer accumulators (see scatter_fixed)
     float fx_scale_re, fx_scale_im;    // 2^k_re, 2^k_im (generic per-atom f path converts on the fly)
     float fx_inv_re, fx_inv_im;        // 2^-k_re, 2^-k_im
     GxFftLayout lay;
@@ -118,22 +118,22 @@ __device__ __forceinline__ void active_band(const ProjArgs &a, int p, int &za, i
 
 // ------------------------------------------------------------------ F1 ----
 // Integer row accumulators.  Each atom adds its scattering factor f = Z + f' + i f'' to its pixel with
-// three native shared-memory integer atomics (ATOMS.ADD; fp32 shared atomics are CAS loops on sm_100a
+// two native shared-memory integer atomics (ATOMS.ADD; fp32 shared atomics are CAS loops on sm_100a
 // and would make the sum depend on atom order):
-//     plane 0  += Zr          Zr = round(Re f)            exact integer part
-//     plane 1  += Fr          Fr = round((Re f - Zr) 2^k_re)   |Re f - Zr| <= 0.5
-//     plane 2  += Fi          Fi = round(Im f 2^k_im)
-// k_re, k_im are the largest exponents for which a chunk of `max chunk atoms` atoms cannot overflow 31
-// bits even if all of them fall into one pixel (gx_slices_fused; 2740 atoms per row at the headline
-// size: k_re = 20, i.e. f' resolved to 4.8e-7 - the fp32 spacing of f itself is 4.8e-7 at f = 6).
+//     plane 0  += round(Re f 2^k_re)          plane 1  += round(Im f 2^k_im)
+// k_re, k_im are the largest exponents for which the atoms of one chunk cannot overflow 31 bits even if
+// all of them fall into one pixel (gx_slices_fused: from the largest sum of |Re f| over a z row; 2740
+// atoms per row at the headline size give k_re = 17, i.e. f resolved to 3.8e-6 absolute, 1e-6 relative).
 // Integer sums commute, so the row is independent of atom order (the reference's np.add.at is a
 // sequential fp64 sum; its threaded accumulators race).  The per-pixel completion is then
-//     v = ((Zr + Fr 2^-k_re) + d avg_f.re,  Fi 2^-k_im + d avg_f.im) * mz * my
-// - three loads and three conversions per pixel whatever the number of species.  (Round 1 counted atoms
+//     v = (w0 2^-k_re + d avg_f.re,  w1 2^-k_im + d avg_f.im) * mz * my
+// - two loads and two conversions per pixel whatever the number of species.  (Round 1 counted atoms
 // per species in 16-bit fields and formed sum_s n_s f_s per pixel: 27 instructions per pixel with five
-// species, 24 % of the kernel's instructions; this flush is 12.)
+// species, 24 % of the kernel's instructions.  A three-plane variant with an exact integer part - Z, f', f''
+// separately - was measured first: 12.5 % fewer instructions but 3 ATOMS per atom saturate the shared-memory
+// pipe, 62.3 vs 58.0 us per slice; profiles/r04_summary.md.)
 template <int U, bool TAIL, bool SPECIES>
-__device__ __forceinline__ void scatter_fixed_batch(const ProjArgs &a, const int4 *s_ffx, float sc_re, float sc_im,
+__device__ __forceinline__ void scatter_fixed_batch(const ProjArgs &a, const int2 *s_ffx, float sc_re, float sc_im,
                                                     int i0, int end, int nt, double s, double c, double shift,
                                                     double r, double inv_r, int32_t *acc, int NP)
 {
@@ -155,25 +155,20 @@ __device__ __forceinline__ void scatter_fixed_batch(const ProjArgs &a, const int
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const bool ok = (!TAIL || i0 + u * nt < end) && ((unsigned)q[u] < (unsigned)N);
-        int4 F;
-        if (SPECIES) {
-            F = s_ffx[sp[u]];
-        } else {
-            const float zr = rintf(fv[u].x);
-            F = make_int4(__float2int_rn(zr), __float2int_rn((fv[u].x - zr) * sc_re), __float2int_rn(fv[u].y * sc_im), 0);
-        }
-        // no branch around an atom: an atom outside the grid adds zeros to pixel 0
-        const int word = ok ? q[u] : 0;
-        atomicAdd(acc + word, ok ? F.x : 0);
-        atomicAdd(acc + NP + word, ok ? F.y : 0);
-        atomicAdd(acc + 2 * NP + word, ok ? F.z : 0);
+        int2 F;
+        if (SPECIES) F = s_ffx[sp[u]];
+        else F = make_int2(__float2int_rn(fv[u].x * sc_re), __float2int_rn(fv[u].y * sc_im));
+        // no branch around an atom: the atomics are predicated (an atom outside the grid, or a species
+        // with Im f == 0 such as hydrogen, issues none)
+        if (ok) atomicAdd(acc + q[u], F.x);
+        if (ok && F.y != 0) atomicAdd(acc + NP + q[u], F.y);
     }
 }
 
 // atoms [beg, end) of one z-row: whole batches of 4 x blockDim atoms, then 2, 1 and a per-thread tail
 // (no arithmetic for atoms that do not exist)
 template <bool SPECIES>
-__device__ __forceinline__ void scatter_fixed(const ProjArgs &a, const int4 *s_ffx, float sc_re, float sc_im,
+__device__ __forceinline__ void scatter_fixed(const ProjArgs &a, const int2 *s_ffx, float sc_re, float sc_im,
                                               int beg, int end, double s, double c, double shift, int32_t *acc, int NP)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -215,10 +210,7 @@ __device__ __forceinline__ void flush_fixed(float2 (&px)[NB0][R0], const int32_t
         for (int n = 0; n < R0; ++n) {
             const int y = t + S0 * n;
             const int yy = EXACT ? y : min(y, N - 1);
-            const float zr = (float)acc[yy];
-            const float fr = (float)acc[NP + yy];
-            const float fi = (float)acc[2 * NP + yy];
-            const float sx = fmaf(fr, inv_re, zr), sy = fi * inv_im;
+            const float sx = (float)acc[yy] * inv_re, sy = (float)acc[NP + yy] * inv_im;
             if (FINISH) {
                 const float2 dm = px[i][n];
                 const float m = (EXACT || y < N) ? mzv * dm.y : 0.f;
@@ -251,7 +243,7 @@ slice_rows_fused(FusedArgs fa)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *buf = reinterpret_cast<float2 *>(smem_raw);
     int32_t *acc = reinterpret_cast<int32_t *>(smem_raw);     // aliases buf (used strictly before it)
-    __shared__ int4 s_ffx[GX_MAX_SPECIES];
+    __shared__ int2 s_ffx[GX_MAX_SPECIES];
     const ProjArgs &a = fa.proj;
     const int p = blockIdx.x, z = blockIdx.y;
     const int N = BLUE ? a.N : M;                          // power-of-two grids are transformed at their own length
@@ -288,12 +280,12 @@ slice_rows_fused(FusedArgs fa)
 
     if (SPECIES && tid < GX_MAX_SPECIES) s_ffx[tid] = fa.ffx[tid];
     int4 *acc4 = reinterpret_cast<int4 *>(smem_raw);
-    if constexpr (EXACT && (3 * M / 4) % NT == 0) {
+    if constexpr (EXACT && (2 * M / 4) % NT == 0) {
         // plane length known at compile time: straight-line 16-byte stores, immediate offsets
 #pragma unroll
-        for (int k = 0; k < (3 * M / 4) / NT; ++k) acc4[tid + k * NT] = make_int4(0, 0, 0, 0);
+        for (int k = 0; k < (2 * M / 4) / NT; ++k) acc4[tid + k * NT] = make_int4(0, 0, 0, 0);
     } else {
-        for (int y = tid; y < 3 * (NP / 4); y += NT) acc4[y] = make_int4(0, 0, 0, 0);
+        for (int y = tid; y < 2 * (NP / 4); y += NT) acc4[y] = make_int4(0, 0, 0, 0);
     }
     __syncthreads();
     if (end - beg <= fa.chunk_atoms) {
@@ -325,7 +317,7 @@ slice_rows_fused(FusedArgs fa)
             flush_fixed<NB0, R0, S0, NT, EXACT, false>(px, acc, NP, tid, N, fa.fx_inv_re, fa.fx_inv_im, 0.f, 0.f, 0.f);
             __syncthreads();   // every accumulator read is done before the next chunk / before buf is written
             if (c1 < end) {
-                for (int y = tid; y < 3 * (NP / 4); y += NT) acc4[y] = make_int4(0, 0, 0, 0);
+                for (int y = tid; y < 2 * (NP / 4); y += NT) acc4[y] = make_int4(0, 0, 0, 0);
                 __syncthreads();
             }
         }
@@ -717,7 +709,7 @@ static int launch_fused(const FusedArgs &fa, bool species, int phases, cudaStrea
     const bool blue = fa.lay.bluestein != 0;
     const bool tma = cols_tma_ok(fa, L, blue);
     size_t smem1 = (size_t)gx_phys_len(M) * sizeof(float2);
-    const size_t acc_bytes = (size_t)3 * ((N + 3) & ~3) * sizeof(int32_t);
+    const size_t acc_bytes = (size_t)2 * ((N + 3) & ~3) * sizeof(int32_t);
     if (acc_bytes > smem1) smem1 = acc_bytes;
     const size_t smem2 = (size_t)BS * TC * sizeof(float2);
     if (smem1 > 227 * 1024 || smem2 > 227 * 1024) {
@@ -776,33 +768,42 @@ static int launch_fused(const FusedArgs &fa, bool species, int phases, cudaStrea
     return gx_check_launch("slice_cols_fused");
 }
 
-// Split of the species table for the integer accumulators (see scatter_fixed): the exponents are the largest
-// for which `chunk` atoms in ONE pixel cannot overflow 31 bits.
+// Fixed-point plan of the integer accumulators (see scatter_fixed): exponents as large as 31 bits allow.
+// max_row_abs_re / max_row_abs_im: the largest sum of |Re f| / |Im f| over the atoms of one z row (a bound on
+// what a single pixel can receive).  A row whose bound would push an exponent below 14 bits is summed in
+// chunks of atoms instead.
 static void fixed_point_plan(const gx_fused_args *h, FusedArgs &fa)
 {
-    double max_frac = 0.5, max_im = 1e-30;
+    double f_re = 1e-30, f_im = 1e-30;                          // largest |Re f|, |Im f| of one atom
     for (int k = 0; k < h->n_species; ++k) {
-        const double im = h->table_f64[2 * k + 1];
-        if (fabs(im) > max_im) max_im = fabs(im);
+        f_re = fmax(f_re, fabs(h->table_f64[2 * k]));
+        f_im = fmax(f_im, fabs(h->table_f64[2 * k + 1]));
     }
-    if (h->n_species == 0) max_im = h->max_abs_f_im > 0.0 ? h->max_abs_f_im : 128.0;
-    int chunk = h->max_row_atoms > 0 ? h->max_row_atoms : 65535;
-    if (chunk > 65535) chunk = 65535;
-    if (chunk < 256) chunk = 256;
-    const double room = 2147483647.0 / (double)chunk;
-    int k_re = (int)floor(log2(room / max_frac)), k_im = (int)floor(log2(room / max_im));
+    if (h->n_species == 0) { f_re = h->max_abs_f_re > 0.0 ? h->max_abs_f_re : 128.0; f_im = h->max_abs_f_im > 0.0 ? h->max_abs_f_im : 128.0; }
+    const double rows = h->max_row_atoms > 0 ? (double)h->max_row_atoms : 65535.0;
+    // bound on one pixel's sums: the caller's per-row sums if given, else atoms x largest f
+    double b_re = h->max_row_abs_re > 0.0 ? h->max_row_abs_re : rows * f_re;
+    double b_im = h->max_row_abs_im > 0.0 ? h->max_row_abs_im : rows * f_im;
+    const double lim = 2147483647.0 * 0.999;                    // (rounding of each addend: at most 0.5 each)
+    int chunk = 0x7fffffff;
+    const double floor_scale = 16384.0;                         // never coarser than 2^-14
+    if (b_re * floor_scale + rows > lim || b_im * floor_scale + rows > lim) {
+        // too populous a row for one pass: chunk by atoms
+        double c = fmin(lim / (floor_scale * f_re + 1.0), lim / (floor_scale * f_im + 1.0));
+        chunk = c < 256.0 ? 256 : (c > 1e9 ? 1000000000 : (int)c);
+        b_re = chunk * f_re; b_im = chunk * f_im;
+    }
+    const double n_add = fmin(rows, (double)chunk);
+    int k_re = (int)floor(log2((lim - n_add) / b_re)), k_im = (int)floor(log2((lim - n_add) / b_im));
     if (k_re > 24) k_re = 24;
     if (k_im > 24) k_im = 24;
     fa.chunk_atoms = chunk;
     fa.fx_scale_re = (float)ldexp(1.0, k_re); fa.fx_scale_im = (float)ldexp(1.0, k_im);
     fa.fx_inv_re = (float)ldexp(1.0, -k_re); fa.fx_inv_im = (float)ldexp(1.0, -k_im);
     for (int k = 0; k < GX_MAX_SPECIES; ++k) {
-        int4 v = make_int4(0, 0, 0, 0);
-        if (k < h->n_species) {
-            const double re = h->table_f64[2 * k], im = h->table_f64[2 * k + 1];
-            const double zr = nearbyint(re);
-            v = make_int4((int)zr, (int)nearbyint(ldexp(re - zr, k_re)), (int)nearbyint(ldexp(im, k_im)), 0);
-        }
+        int2 v = make_int2(0, 0);
+        if (k < h->n_species)
+            v = make_int2((int)nearbyint(ldexp(h->table_f64[2 * k], k_re)), (int)nearbyint(ldexp(h->table_f64[2 * k + 1], k_im)));
         fa.ffx[k] = v;
     }
 }

@@ -450,7 +450,7 @@ class AtomSet:
             self.table = _dev(self.table_host, device)
         else:
             f_host = np.asarray(f_values, dtype=np.complex128)
-            self.max_abs_f_im = float(np.abs(f_host.imag).max()) if f_host.size else 0.0
+            self.max_abs_f = (float(np.abs(f_host.real).max()), float(np.abs(f_host.imag).max())) if f_host.size else (0.0, 0.0)
             d_f = _dev(f_host.astype(np.complex64).view(np.float32), device)
             self.f = torch.empty(2 * self.A, dtype=torch.float32, device=device)
         self.xs = torch.empty(self.A, dtype=torch.float64, device=device)
@@ -463,6 +463,7 @@ class AtomSet:
              ptr(self.species), ptr(self.f), ptr(self.row_start), ptr(cursor), st)
         self._cand = None
         self._max_row_atoms = None
+        self._max_row_abs_f = None
 
     @property
     def max_row_atoms(self):
@@ -471,6 +472,23 @@ class AtomSet:
             rs = self.row_start[:self.N + 1]
             self._max_row_atoms = int((rs[1:] - rs[:-1]).max().item())
         return self._max_row_atoms
+
+    @property
+    def max_row_abs_f(self):
+        """(max over z rows of sum |Re f|, same for |Im f|): what one pixel of a row can receive at
+        most; sizes the fixed-point scale of the fused row kernel (gx_fused_args.max_row_abs_*)."""
+        if self._max_row_abs_f is None:
+            rs = self.row_start[:self.N + 1].to(torch.int64)
+            if self.n_species:
+                t = torch.from_numpy(np.abs(np.stack([self.table_c128.real, self.table_c128.imag], axis=1))).to(self.device)
+                per_atom = t[self.species.to(torch.int64)]                       # [A, 2] float64
+            else:
+                per_atom = self.f.view(-1, 2).abs().to(torch.float64)
+            c = torch.cat([torch.zeros(1, 2, dtype=torch.float64, device=self.device), torch.cumsum(per_atom, dim=0)])
+            rows = c[rs[1:]] - c[rs[:-1]]
+            m = rows.max(dim=0).values.cpu().numpy() * (1.0 + 1e-9)
+            self._max_row_abs_f = (float(m[0]), float(m[1]))
+        return self._max_row_abs_f
 
     def candidates(self):
         """(xs, ys, count) of the atoms that can be extreme in y' (built lazily, once)."""
@@ -582,10 +600,15 @@ class SliceEngine:
                 lo, hi = self.window
                 call("gx_window_indices", ptr(self.row_index), self.N, self.q_num, lo, hi, 0, st)
                 self.q_out = hi - lo
+            self.vsum_store, self.vsum_is_partial = None, False
             if accumulators is not None:
                 self.vsum, self.count3, self.count2 = accumulators
             else:
-                self.vsum = torch.zeros(self.q_out ** 3, dtype=torch.float32, device=dev)
+                # padded to whole-column slabs per rank, so that N ranks can reduce-scatter it in place
+                from . import parallel
+                _, padded = parallel.padded_columns(self.q_out, parallel.rank_world()[1])
+                self.vsum_store = torch.zeros(padded, dtype=torch.float32, device=dev)
+                self.vsum = self.vsum_store[:self.q_out ** 3]
                 self.count3 = torch.zeros(self.q_out ** 3, dtype=torch.int32, device=dev) if count3d else None
                 self.count2 = None if count3d else torch.zeros(self.q_out ** 2, dtype=torch.int32, device=dev)
             self.row_hist = torch.zeros(self.q_out, dtype=torch.int32, device=dev)
@@ -710,8 +733,9 @@ class SliceEngine:
             for k, v in enumerate(a.table_c128):
                 args.table_f64[2 * k], args.table_f64[2 * k + 1] = float(v.real), float(v.imag)
         else:
-            args.max_abs_f_im = a.max_abs_f_im
+            args.max_abs_f_re, args.max_abs_f_im = a.max_abs_f
         args.max_row_atoms = a.max_row_atoms
+        args.max_row_abs_re, args.max_row_abs_im = a.max_row_abs_f
         args.n_species, args.n_phi, args.N, args.KC, args.q_num = a.n_species, n, self.N, self.KC, self.q_out
         args.row_lo, args.row_hi = self.row_lo, self.row_hi
         args.fill_bkg, args.smooth_sigma = int(self.fill_bkg), self.sigma
@@ -877,7 +901,7 @@ def finalize_voxels(vsum, count3, count2, row_hist, q_axis, max_q, device, windo
                  ptr(d_axis), ptr(aff), CARBON_Z, int(columns[0]), int(columns[1]), ptr(iq), _stream())
         if sync:
             torch.cuda.current_stream().synchronize()
-    return iq.view(V, V, V), q_axis[lo:hi].copy()
+    return iq[:V * V * V].view(V, V, V), q_axis[lo:hi].copy()
 
 
 def scale_shell(iq, axis, lower, upper, factor, device):

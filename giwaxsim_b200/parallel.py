@@ -42,11 +42,85 @@ def all_reduce_sum(tensors, group=None):
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
 
+_comm = {"handle": None, "key": None}
+GX_DTYPE_F32, GX_DTYPE_U32, GX_DTYPE_F64 = 0, 1, 2
+
+
+def comm(device):
+    """The library's own NCCL communicator over the ranks of the default process group (gx_comm_*,
+    include/giwaxs_b200.h): created once, its 128-byte id shipped from rank 0 through torch.distributed.
+    None for a single rank or a CPU (gloo) group - callers then use torch.distributed collectives."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return None
+    if torch.device(device).type != "cuda" or dist.get_backend() != "nccl":
+        return None
+    import ctypes
+    from ._lib import call
+    key = (dist.get_rank(), dist.get_world_size(), torch.device(device).index)
+    if _comm["handle"] is not None and _comm["key"] == key:
+        return _comm["handle"]
+    ident = np.zeros(128, dtype=np.uint8)
+    if key[0] == 0:
+        call("gx_comm_unique_id", ident.ctypes.data_as(ctypes.c_void_p))
+    t = torch.from_numpy(ident).to(device)
+    dist.broadcast(t, src=0)
+    ident = np.ascontiguousarray(t.cpu().numpy())
+    handle = ctypes.c_void_p()
+    with torch.cuda.device(device):
+        call("gx_comm_init", ident.ctypes.data_as(ctypes.c_void_p), key[0], key[1], ctypes.byref(handle))
+    _comm["handle"], _comm["key"] = handle, key
+    return handle
+
+
+def padded_columns(q_out, world):
+    """(columns per rank, elements of an accumulator padded so that `world` equal slabs of whole
+    (iy, ix) columns cover it) for the reduce-scatter / sharded finalise / all-gather of stage A."""
+    cols = q_out * q_out
+    cpr = -(-cols // max(1, world))
+    return cpr, cpr * max(1, world) * q_out
+
+
+def all_reduce_image(image, device):
+    """Sum of the fp64 partial detector images over the ranks (detector.py:298), on the launch stream."""
+    c = comm(device)
+    if c is None:
+        return all_reduce_sum([image])
+    from . import engine
+    from ._lib import call, ptr
+    with torch.cuda.device(device):
+        call("gx_comm_all_reduce", c, ptr(image), int(image.numel()), GX_DTYPE_F64, engine._stream())
+
+
 def combine_and_finalize(eng, q_axis, max_q, device, window=None, crop=True, f0=True, group=None):
     """Partial voxel sums / counts of every rank -> the finished iq grid on every rank
     (reference: the shared `+=` of voxelgrids.py:502-503 followed by comparison.py:765-786).
-    One rank: just the finalise kernel."""
+    One rank: just the finalise kernel.  N ranks on GPUs: reduce-scatter of the partial sums (each rank
+    receives the total of its slab of (iy, ix) columns), all-reduce of the 0.65 MB column counts, every
+    rank finalises ITS slab only, all-gather of iq - all four on the launch stream, no host
+    synchronisation in between (the reduce-scatter variant).  Otherwise (gloo, external
+    accumulators): all-reduce of the whole grids, then the whole finalise on every rank."""
     from . import engine
+    from ._lib import call, ptr
+    rank, world = rank_world()
+    c = comm(device) if (world > 1 and group is None) else None
+    store = getattr(eng, "vsum_store", None)
+    if c is not None and store is not None and eng.count2 is not None and window is not None and crop:
+        V = eng.q_out
+        cpr, padded = padded_columns(V, world)
+        if store.numel() >= padded:
+            with torch.cuda.device(device):
+                st = engine._stream()
+                call("gx_comm_reduce_scatter_f32", c, ptr(store), cpr * V, st)
+                call("gx_comm_all_reduce", c, ptr(eng.count2), int(eng.count2.numel()), GX_DTYPE_U32, st)
+                eng.vsum_is_partial = True          # only slab `rank` of eng.vsum holds totals now
+                iq_store = torch.empty(padded, dtype=torch.float32, device=device)
+                lo, hi = rank * cpr, min(V * V, (rank + 1) * cpr)
+                _, axis = engine.finalize_voxels(store, None, eng.count2, eng.row_hist, q_axis, max_q, device,
+                                                 window=window, crop=crop, f0=f0, out=iq_store,
+                                                 columns=(lo, max(lo, hi)), sync=False)
+                call("gx_comm_all_gather_f32", c, ptr(iq_store), cpr * V, st)
+                torch.cuda.current_stream().synchronize()
+            return iq_store[:V ** 3].view(V, V, V), axis
     all_reduce_sum([eng.vsum, eng.count2], group=group)
     return engine.finalize_voxels(eng.vsum, None, eng.count2, eng.row_hist, q_axis, max_q, device,
                                   window=window, crop=crop, f0=f0)

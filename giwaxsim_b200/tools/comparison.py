@@ -278,7 +278,7 @@ def detectormaker_fitting(iq, qx, qy, qz, num_pixels, max_q, angle_init_vals, an
         det.accumulate(gx, gy, gz, np.ascontiguousarray(R[sel]), np.ascontiguousarray(w[sel]), image=image)
     tr.lap("gather")
     if world > 1:
-        parallel.all_reduce_sum([image])
+        parallel.all_reduce_image(image, dev)
     out = engine.detector_epilogue(image, num_pixels, num_pixels, mirror, dev, finish=True)
     tr.lap("all-reduce + epilogue")
     with torch.cuda.device(dev):

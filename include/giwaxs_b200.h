@@ -269,9 +269,11 @@ typedef struct gx_fused_args {
     double r, pedestal_re, pedestal_im, avg_f_re, avg_f_im;
     int32_t n_species, n_phi, N, KC, q_num, row_lo, row_hi, fill_bkg, smooth_sigma;
     int32_t phases;              /* 0 or 3: both launches; 1: row kernel only; 2: column kernel only (per-kernel timing) */
-    int32_t max_row_atoms;       /* most atoms in one z pixel row (0: unknown -> 65535): sizes the fixed-point scale */
+    int32_t max_row_atoms;       /* most atoms in one z pixel row (0: unknown -> 65535) */
     int32_t pad;
-    double max_abs_f_im;         /* n_species == 0: bound on |Im f| over the atoms (0: unknown -> 128) */
+    double max_row_abs_re, max_row_abs_im;   /* largest sum over one z row of |Re f| / |Im f| (0: atoms x largest f):
+                                                sizes the fixed-point scale of the row accumulators */
+    double max_abs_f_re, max_abs_f_im;       /* n_species == 0: bounds on |Re f|, |Im f| of one atom (0: 128) */
     double table_f64[2 * GX_MAX_SPECIES];   /* host copy of the species f-values, (re, im) pairs, full precision */
 } gx_fused_args;
 int gx_slices_fused(const gx_fused_args *h_args, void *stream);
@@ -315,6 +317,31 @@ int gx_slab_count(const gx_slab_args *h_args, const double *h_min3, const double
 int gx_slab_write(const gx_slab_args *h_args, const double *h_min3, const double *h_lo3, const double *h_hi3,
                   const double *h_kept_min3, const int64_t *d_tile_offset, double *d_xyz_out,
                   uint8_t *d_species_out, void *stream);
+
+/* ----------------------------------------------------- multi-GPU exchange */
+/* One process per GPU; the partial voxel sums / counts of stage A and the
+ * partial detector images of stage B meet in a sum (the reference's shared
+ * accumulators: voxelgrids.py:502-503, detector.py:298).  NCCL (the libnccl.so.2
+ * already loaded in the process) is driven through these entry points, on the
+ * caller's stream, so a collective follows the kernel that produced its input
+ * without a host synchronisation.
+ *  gx_comm_unique_id : rank 0 fills 128 bytes; ship them to the other ranks
+ *                      (any out-of-band channel) and pass them to gx_comm_init
+ *  gx_comm_init      : collective over `world` ranks; the calling thread's
+ *                      current CUDA device is this rank's GPU
+ *  gx_comm_all_reduce: in-place sum; dtype GX_DTYPE_F32 / _U32 / _F64
+ *  gx_comm_reduce_scatter_f32 : d_buf [world * count_per_rank]; on return slab
+ *                      `rank` of this rank's buffer holds the sum over ranks
+ *  gx_comm_all_gather_f32     : slab `rank` of every rank -> all of d_buf on all  */
+#define GX_DTYPE_F32 0
+#define GX_DTYPE_U32 1
+#define GX_DTYPE_F64 2
+int gx_comm_unique_id(void *h_id128);
+int gx_comm_init(const void *h_id128, int rank, int world, void **out_comm);
+int gx_comm_destroy(void *comm);
+int gx_comm_all_reduce(void *comm, void *d_buf, int64_t count, int dtype, void *stream);
+int gx_comm_reduce_scatter_f32(void *comm, float *d_buf, int64_t count_per_rank, void *stream);
+int gx_comm_all_gather_f32(void *comm, float *d_buf, int64_t count_per_rank, void *stream);
 
 /* --------------------------------------------------------- detector (K4) */
 /* p <- R p for n points, R row-major 3x3, fma chain k=0,1,2.
