@@ -39,7 +39,7 @@ class FusedArgs(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in
                 ("d_xs", "d_ys", "d_species", "d_f", "d_row_start", "d_table", "d_sin", "d_cos", "d_yrange",
                  "d_bbox", "d_dmy", "d_mz", "d_plan", "d_col", "d_colrange", "d_row_index",
-                 "d_work", "d_sum", "d_count2")] + \
+                 "d_work", "d_sum", "d_count2", "d_dc")] + \
                [(n, ctypes.c_double) for n in ("r", "pedestal_re", "pedestal_im", "avg_f_re", "avg_f_im")] + \
                [(n, ctypes.c_int32) for n in ("n_species", "n_phi", "N", "KC", "q_num", "row_lo", "row_hi",
                                               "fill_bkg", "smooth_sigma", "phases", "max_row_atoms", "pad")] + \
@@ -69,6 +69,7 @@ _PROTOTYPES = {
     "gx_species_histogram": (_i, [_p, _i, _i64, _p, _p]),
     "gx_species_codes": (_i, [_p, _i, _i64, _p, _p, _p]),
     "gx_checksum64": (_i, [_p, _i64, _i, _p, _p]),
+    "gx_row_abs_f_max": (_i, [_p, _p, _p, _i, _p, _i, _p, _p]),
     "gx_slice_yrange": (_i, [_p, _p, _i64, _p, _p, _i, _p, _p]),
     "gx_extreme_atoms": (_i, [_p, _p, _i64, _p, _p, _p, _i, _p, _p]),
     "gx_hull_filter": (_i, [_p, _p, _i64, _p, _i, _d, _p, _p, _p, _i, _p]),
@@ -91,6 +92,7 @@ _PROTOTYPES = {
     "gx_window_indices": (_i, [_p, _i64, _i, _i, _i, _i, _p]),
     "gx_slices_fused": (_i, [_p, _p]),
     "gx_fused_wants_zeroed_work": (_i, [_i, _i]),
+    "gx_fold_dc": (_i, [_p, _p, _p]),
     "gx_comm_unique_id": (_i, [_p]),
     "gx_comm_init": (_i, [_p, _i, _i, _p]),
     "gx_comm_destroy": (_i, [_p]),
@@ -156,7 +158,7 @@ _LAUNCHES = {
     "gx_axis_col_index": 1, "gx_axis_row_index": 1, "gx_bin_slices": 1, "gx_row_histogram": 1,
     "gx_voxel_finalize": 1, "gx_voxel_shell_scale": 1, "gx_rotate_points": 1, "gx_detector_accumulate": 1, "gx_detector_epilogue": 1,
     "gx_detector_accumulate_fast": 1, "gx_detector_accumulate_affine": 1, "gx_grid_affine_fit": 1,
-    "gx_slices_fused": 2, "gx_species_histogram": 1, "gx_species_codes": 1, "gx_checksum64": 1, "gx_window_indices": 1, "gx_slab_minmax": 3, "gx_slab_count": 3, "gx_slab_write": 1, "gx_slice_col_range": 1, "gx_extreme_atoms": 1, "gx_hull_filter": 1,
+    "gx_slices_fused": 2, "gx_species_histogram": 1, "gx_species_codes": 1, "gx_checksum64": 1, "gx_row_abs_f_max": 2, "gx_fold_dc": 1, "gx_window_indices": 1, "gx_slab_minmax": 3, "gx_slab_count": 3, "gx_slab_write": 1, "gx_slice_col_range": 1, "gx_extreme_atoms": 1, "gx_hull_filter": 1,
 }
 _launch_count = 0
 

@@ -550,3 +550,71 @@ extern "C" int gx_checksum64(const void *d_data, int64_t n, int widen_f32, uint6
                                                                           reinterpret_cast<unsigned long long *>(d_out));
     return gx_check_launch("gx_checksum64");
 }
+
+
+// ------------------------------------------------- per-row sums of |Re f|, |Im f| ----
+// Largest sum over the atoms of one z pixel row of |Re f| and of |Im f|: what a single pixel of a row
+// can receive at most, which sizes the fixed-point scale of the fused row kernel's integer accumulators
+// (gx_fused_args.max_row_abs_re / _im).  One warp per row; atoms are sorted by row.
+__global__ void __launch_bounds__(ATOM_THREADS)
+row_abs_f_max_kernel(const uint8_t *__restrict__ species, const float2 *__restrict__ f,
+                     const int32_t *__restrict__ row_start, int N, const double *__restrict__ table_abs,
+                     int n_species, unsigned long long *out2)
+{
+    __shared__ double s_tab[2 * GX_MAX_SPECIES];
+    if (threadIdx.x < 2 * GX_MAX_SPECIES) s_tab[threadIdx.x] = (int)threadIdx.x < 2 * n_species ? table_abs[threadIdx.x] : 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    double best_re = 0.0, best_im = 0.0;
+    for (int z = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; z < N; z += warps) {
+        const int beg = row_start[z], end = row_start[z + 1];
+        double re = 0.0, im = 0.0;
+        for (int i = beg + lane; i < end; i += 32) {
+            if (species) { const int sp = species[i]; re += s_tab[2 * sp]; im += s_tab[2 * sp + 1]; }
+            else { const float2 v = f[i]; re += fabs((double)v.x); im += fabs((double)v.y); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            re += __shfl_xor_sync(0xffffffffu, re, o);
+            im += __shfl_xor_sync(0xffffffffu, im, o);
+        }
+        best_re = fmax(best_re, re);
+        best_im = fmax(best_im, im);
+    }
+    if (lane == 0) {
+        atomicMax(out2, gx_ord(best_re));
+        atomicMax(out2 + 1, gx_ord(best_im));
+    }
+}
+
+__global__ void row_abs_f_decode_kernel(unsigned long long *out2)
+{
+    if (threadIdx.x < 2) {
+        const double v = gx_unord(out2[threadIdx.x]);
+        reinterpret_cast<double *>(out2)[threadIdx.x] = v;
+    }
+}
+
+extern "C" int gx_row_abs_f_max(const uint8_t *d_species, const gx_float2 *d_f, const int32_t *d_row_start, int N,
+                                const double *h_table_abs, int n_species, double *d_out2, void *stream)
+{
+    GX_REQUIRE((d_species || d_f) && d_row_start && d_out2 && N > 0, "bad arguments");
+    GX_REQUIRE(n_species >= 0 && n_species <= GX_MAX_SPECIES && (!d_species || (h_table_abs && n_species > 0)),
+               "species table missing");
+    cudaStream_t st = gx_stream(stream);
+    double *d_tab = NULL;
+    if (d_species) {
+        GX_CUDA(cudaMallocAsync(&d_tab, 2 * GX_MAX_SPECIES * sizeof(double), st));
+        GX_CUDA(cudaMemcpyAsync(d_tab, h_table_abs, 2 * (size_t)n_species * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    unsigned long long init[2] = {gx_ord_host(0.0), gx_ord_host(0.0)};
+    GX_CUDA(cudaMemcpyAsync(d_out2, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    int blocks = (N * 32 + ATOM_THREADS - 1) / ATOM_THREADS;
+    if (blocks > GX_SM_COUNT * 8) blocks = GX_SM_COUNT * 8;
+    row_abs_f_max_kernel<<<blocks, ATOM_THREADS, 0, st>>>(d_species, reinterpret_cast<const float2 *>(d_f), d_row_start, N,
+                                                           d_tab, n_species, reinterpret_cast<unsigned long long *>(d_out2));
+    row_abs_f_decode_kernel<<<1, 32, 0, st>>>(reinterpret_cast<unsigned long long *>(d_out2));
+    if (d_tab) GX_CUDA(cudaFreeAsync(d_tab, st));
+    return gx_check_launch("gx_row_abs_f_max");
+}

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include "../../include/giwaxs_b200.h"
 
 #ifndef GX_SM_COUNT
@@ -69,4 +70,11 @@ __device__ __forceinline__ double gx_unord(unsigned long long o)
 {
     unsigned long long b = (o & 0x8000000000000000ull) ? (o & 0x7fffffffffffffffull) : ~o;
     return __longlong_as_double((long long)b);
+}
+
+static inline unsigned long long gx_ord_host(double v)
+{
+    unsigned long long b;
+    memcpy(&b, &v, 8);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }

@@ -19,7 +19,7 @@ extern "C" int64_t gx_fft_plan_bytes(int N)
     GxFftLayout g = gx_fft_layout(N);
     if (g.M == 0) {
         gx_set_error("gx_fft_plan_bytes: unsupported transform length %d "
-                     "(need 16 <= N, pow2 <= 8192 or 2N-1 <= 8192)", N);
+                     "(need 16 <= N; powers of two up to 16384, any other N up to 8192)", N);
         return GX_ERR_UNSUPPORTED;
     }
     return (int64_t)g.total * (int64_t)sizeof(float2);
@@ -214,6 +214,7 @@ extern "C" int gx_fft2_abs2_shift(const gx_float2 *d_grid, gx_float2 *d_work, fl
     case 11: return launch_fft2<11, 8>(grid, work, d_iq2d, batch, g, plan, dr, di, st);
     case 12: return launch_fft2<12, 4>(grid, work, d_iq2d, batch, g, plan, dr, di, st);
     case 13: return launch_fft2<13, 2>(grid, work, d_iq2d, batch, g, plan, dr, di, st);
+    case 14: return launch_fft2<14, 1>(grid, work, d_iq2d, batch, g, plan, dr, di, st);
     }
     gx_set_error("gx_fft2_abs2_shift: unsupported log2 size %d", g.L);
     return GX_ERR_UNSUPPORTED;

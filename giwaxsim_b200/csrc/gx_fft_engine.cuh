@@ -41,6 +41,7 @@ GX_SCHED(10, 3, 16, 16, 4, 1);
 GX_SCHED(11, 3, 16, 16, 8, 1);
 GX_SCHED(12, 3, 16, 16, 16, 1);
 GX_SCHED(13, 4, 8, 16, 16, 4);
+GX_SCHED(14, 4, 16, 16, 16, 4);
 #undef GX_SCHED
 
 // runtime view of the same table (host plan builder, tests)
@@ -50,7 +51,7 @@ static inline int gx_sched_radices(int L, int r[4])
 #define GX_CASE(L_) case L_: r[0] = GxSched<L_>::R0; r[1] = GxSched<L_>::R1; \
                              r[2] = GxSched<L_>::R2; r[3] = GxSched<L_>::R3; return GxSched<L_>::NP;
         GX_CASE(4) GX_CASE(5) GX_CASE(6) GX_CASE(7) GX_CASE(8)
-        GX_CASE(9) GX_CASE(10) GX_CASE(11) GX_CASE(12) GX_CASE(13)
+        GX_CASE(9) GX_CASE(10) GX_CASE(11) GX_CASE(12) GX_CASE(13) GX_CASE(14)
 #undef GX_CASE
     default: return 0;
     }
@@ -75,7 +76,7 @@ static inline GxFftLayout gx_fft_layout(int N)
     int M = N;
     if (!pow2) { M = 1; while (M < 2 * N - 1) M <<= 1; g.bluestein = 1; }
     int L = 0; while ((1 << L) < M) ++L;
-    if (L < 4 || L > 13) return g;
+    if (L < 4 || L > 14) return g;
     g.M = M; g.L = L;
     int r[4]; int np = gx_sched_radices(L, r);
     int off = 0, S = M;

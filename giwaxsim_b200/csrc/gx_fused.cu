@@ -102,6 +102,7 @@ struct FusedArgs {
     float *vsum;
     uint32_t *count2;
     float dc_re, dc_im;        // pedestal * N^2
+    double *dc_acc;            // [2] fp64 accumulator of the DC sample + its voxel index (NULL: straight into vsum)
     int n_phi;
     int use_const;             // row-kernel scalars are in the constant tables
     int chunk_atoms;           // atoms one pass of the integer accumulators may take (31-bit headroom)
@@ -232,7 +233,7 @@ __device__ __forceinline__ void flush_fixed(float2 (&px)[NB0][R0], const int32_t
 // ROWPERM: row z is written to slot 256 (z mod 16) + z / 16 of the work buffer, the order the
 // TMA-fed column kernel consumes (16 chunks of 256 rows, each a 256-point sub-transform).
 template <int L, bool SPECIES, bool BLUE, bool ROWPERM>
-__global__ void __launch_bounds__(PROJ_THREADS, (L >= 13) ? 2 : GX_F1_MINBLOCKS)
+__global__ void __launch_bounds__(PROJ_THREADS, (L >= 14) ? 1 : (L >= 13) ? 2 : GX_F1_MINBLOCKS)
 slice_rows_fused(FusedArgs fa)
 {
     typedef GxSched<L> Sc;
@@ -387,6 +388,16 @@ slice_rows_fused(FusedArgs fa)
 }
 
 // ------------------------------------------------------------------ F2 ----
+// The DC sample of a slice (q = 0: |sum of all f + pedestal N^2|^2, the same huge number for every rotation,
+// ~1e10 x its neighbours) is accumulated in fp64 on the side and folded into its voxel once per run
+// (gx_fold_dc): 1800 fp32 additions of it random-walked to 1.4e-6 of the maximum and made the result depend
+// on how the rotations were split over ranks.
+__device__ __forceinline__ void add_dc_sample(const FusedArgs &fa, size_t voxel, float2 v)
+{
+    atomicAdd(fa.dc_acc, (double)v.x * (double)v.x + (double)v.y * (double)v.y);
+    fa.dc_acc[1] = (double)voxel;
+}
+
 template <int L, int TC, bool BLUE>
 __global__ void __launch_bounds__(512)
 slice_cols_fused(FusedArgs fa)
@@ -455,7 +466,10 @@ slice_cols_fused(FusedArgs fa)
         int kz = i - half;
         if (kz < 0) kz += N;
         float2 v = gx_dft_result<L, BLUE ? 1 : 0>(smem + cc * BS, fa.lay, fa.plan, kz);
-        if (kz == 0 && j == half) { v.x += fa.dc_re; v.y += fa.dc_im; }
+        if (kz == 0 && j == half) {
+            v.x += fa.dc_re; v.y += fa.dc_im;
+            if (fa.dc_acc) { add_dc_sample(fa, (size_t)yx * fa.q_num + iz, v); continue; }
+        }
         atomicAdd(&fa.vsum[(size_t)yx * fa.q_num + iz], v.x * v.x + v.y * v.y);
     }
 }
@@ -609,9 +623,16 @@ slice_cols_tma(FusedArgs fa, const __grid_constant__ CUtensorMap tmap)
                 const bool w1 = kp + 256 < khi, w14 = kp - 512 >= klo;
                 float2 x0, x15, x1, x14;
                 gx_dft16_lowband_vals(v, w1 || w14, x0, x15, x1, x14);
-                if (kp == 0 && j == half) { x0.x += fa.dc_re; x0.y += fa.dc_im; }
                 int iz;
-                if (kp < khi && (iz = fa.row_index[kp + half]) >= 0) atomicAdd(dst + iz, x0.x * x0.x + x0.y * x0.y);
+                if (kp < khi && (iz = fa.row_index[kp + half]) >= 0) {
+                    if (kp == 0 && j == half) {
+                        x0.x += fa.dc_re; x0.y += fa.dc_im;
+                        if (fa.dc_acc) add_dc_sample(fa, (size_t)yx * fa.q_num + iz, x0);
+                        else atomicAdd(dst + iz, x0.x * x0.x + x0.y * x0.y);
+                    } else {
+                        atomicAdd(dst + iz, x0.x * x0.x + x0.y * x0.y);
+                    }
+                }
                 if (kp - 256 >= klo && (iz = fa.row_index[kp - 256 + half]) >= 0) atomicAdd(dst + iz, x15.x * x15.x + x15.y * x15.y);
                 if (w1 && (iz = fa.row_index[kp + 256 + half]) >= 0) atomicAdd(dst + iz, x1.x * x1.x + x1.y * x1.y);
                 if (w14 && (iz = fa.row_index[kp - 512 + half]) >= 0) atomicAdd(dst + iz, x14.x * x14.x + x14.y * x14.y);
@@ -626,7 +647,10 @@ slice_cols_tma(FusedArgs fa, const __grid_constant__ CUtensorMap tmap)
                     const int iz = fa.row_index[i];
                     if (iz < 0) continue;
                     float2 x = v[m];
-                    if (kz == 0 && j == half) { x.x += fa.dc_re; x.y += fa.dc_im; }
+                    if (kz == 0 && j == half) {
+                        x.x += fa.dc_re; x.y += fa.dc_im;
+                        if (fa.dc_acc) { add_dc_sample(fa, (size_t)yx * fa.q_num + iz, x); continue; }
+                    }
                     atomicAdd(dst + iz, x.x * x.x + x.y * x.y);
                 }
             }
@@ -838,7 +862,7 @@ extern "C" int gx_slices_fused(const gx_fused_args *h, void *stream)
     fa.col = h->d_col; fa.colrange = h->d_colrange; fa.row_index = h->d_row_index;
     fa.row_lo = h->row_lo; fa.row_hi = h->row_hi;
     fa.work = reinterpret_cast<float2 *>(h->d_work); fa.KC = h->KC; fa.q_num = h->q_num;
-    fa.vsum = h->d_sum; fa.count2 = h->d_count2;
+    fa.vsum = h->d_sum; fa.count2 = h->d_count2; fa.dc_acc = h->d_dc;
     const double n2 = (double)h->N * (double)h->N;
     const bool has_ped = h->fill_bkg || h->smooth_sigma > 0;
     fa.dc_re = has_ped ? (float)(h->pedestal_re * n2) : 0.f;
@@ -872,12 +896,29 @@ extern "C" int gx_slices_fused(const gx_fused_args *h, void *stream)
     case 11: rc = launch_fused<11, 8>(fa, species, phases, st); break;
     case 12: rc = launch_fused<12, GX_F2_TC12>(fa, species, phases, st); break;
     case 13: rc = launch_fused<13, 2>(fa, species, phases, st); break;
+    case 14: rc = launch_fused<14, 1>(fa, species, phases, st); break;
     default:
         gx_set_error("gx_slices_fused: unsupported log2 size %d", fa.lay.L);
         rc = GX_ERR_UNSUPPORTED;
     }
     if (fa.use_const && (phases & 1) && rc == GX_OK) rc = const_tables_release(st);
     return rc;
+}
+
+__global__ void fold_dc_kernel(double *dc, float *vsum)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0 && dc[0] != 0.0) {
+        vsum[(size_t)dc[1]] += (float)dc[0];
+        dc[0] = 0.0;
+    }
+}
+
+// vsum[voxel of q = 0] += the fp64 sum of the DC samples gathered in d_dc since the last fold; d_dc is reset.
+extern "C" int gx_fold_dc(double *d_dc, float *d_sum, void *stream)
+{
+    GX_REQUIRE(d_dc && d_sum, "NULL pointer");
+    fold_dc_kernel<<<1, 32, 0, gx_stream(stream)>>>(d_dc, d_sum);
+    return gx_check_launch("gx_fold_dc");
 }
 
 // 1 when gx_slices_fused will consume the work buffer in the permuted row order of the TMA-fed column

@@ -478,15 +478,14 @@ class AtomSet:
         """(max over z rows of sum |Re f|, same for |Im f|): what one pixel of a row can receive at
         most; sizes the fixed-point scale of the fused row kernel (gx_fused_args.max_row_abs_*)."""
         if self._max_row_abs_f is None:
-            rs = self.row_start[:self.N + 1].to(torch.int64)
+            out = torch.empty(2, dtype=torch.float64, device=self.device)
+            tab = None
             if self.n_species:
-                t = torch.from_numpy(np.abs(np.stack([self.table_c128.real, self.table_c128.imag], axis=1))).to(self.device)
-                per_atom = t[self.species.to(torch.int64)]                       # [A, 2] float64
-            else:
-                per_atom = self.f.view(-1, 2).abs().to(torch.float64)
-            c = torch.cat([torch.zeros(1, 2, dtype=torch.float64, device=self.device), torch.cumsum(per_atom, dim=0)])
-            rows = c[rs[1:]] - c[rs[:-1]]
-            m = rows.max(dim=0).values.cpu().numpy() * (1.0 + 1e-9)
+                tab = np.ascontiguousarray(np.abs(np.stack([self.table_c128.real, self.table_c128.imag], axis=1)))
+            with torch.cuda.device(self.device):
+                call("gx_row_abs_f_max", ptr(self.species), ptr(self.f), ptr(self.row_start), self.N, ptr(tab),
+                     self.n_species, ptr(out), _stream())
+                m = out.cpu().numpy() * (1.0 + 1e-9)
             self._max_row_abs_f = (float(m[0]), float(m[1]))
         return self._max_row_abs_f
 
@@ -611,6 +610,7 @@ class SliceEngine:
                 self.vsum = self.vsum_store[:self.q_out ** 3]
                 self.count3 = torch.zeros(self.q_out ** 3, dtype=torch.int32, device=dev) if count3d else None
                 self.count2 = None if count3d else torch.zeros(self.q_out ** 2, dtype=torch.int32, device=dev)
+            self.dc = torch.zeros(2, dtype=torch.float64, device=dev)     # fp64 side sum of the q = 0 samples
             self.row_hist = torch.zeros(self.q_out, dtype=torch.int32, device=dev)
             call("gx_row_histogram", ptr(self.row_index), self.N, self.q_out, ptr(self.row_hist), st)
             if self.sigma > 0:
@@ -724,7 +724,7 @@ class SliceEngine:
                              ("d_dmy", t["dmy"]), ("d_mz", t.get("mz")),
                              ("d_plan", self.plan.table), ("d_col", t["col"]), ("d_colrange", t["colrange"]),
                              ("d_row_index", self.row_index), ("d_work", work), ("d_sum", self.vsum),
-                             ("d_count2", self.count2)):
+                             ("d_count2", self.count2), ("d_dc", self.dc)):
             setattr(args, name, None if tensor is None else tensor.data_ptr())
         args.r = self.r
         args.pedestal_re, args.pedestal_im = self.pedestal.real, self.pedestal.imag
@@ -773,6 +773,7 @@ class SliceEngine:
                 self.fused(t, work)
                 ranges.append(t["colrange"])
                 self.slices_done += n
+            call("gx_fold_dc", ptr(self.dc), ptr(self.vsum), _stream())
             torch.cuda.current_stream().synchronize()
             self.check_bbox(full)
             cr = torch.cat(ranges).cpu().numpy().reshape(-1, 2)

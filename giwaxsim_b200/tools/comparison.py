@@ -242,6 +242,25 @@ def _detector_base_device(num_pixels, max_q, angle_init_vals, angle_init_axs, de
     return gx, gy, gz, h, v
 
 
+class _ContentCheck:
+    """Whole-array checksum of a host array on a worker thread (the sum releases the GIL), so that the
+    verification of a resident device copy overlaps the GPU work that speculatively uses it."""
+
+    def __init__(self, array, expected):
+        import threading
+        self.ok = None
+
+        def work():
+            self.ok = engine.host_checksum(array) == expected
+
+        self.thread = threading.Thread(target=work, daemon=True)
+        self.thread.start()
+
+    def result(self):
+        self.thread.join()
+        return bool(self.ok)
+
+
 def detectormaker_fitting(iq, qx, qy, qz, num_pixels, max_q, angle_init_vals, angle_init_axs, psis,
                           psi_weights_path, phis, phi_weights_path, thetas, theta_weights_path, mirror=True):
     """2-D detector image summed over psi x phi x theta orientations.
@@ -261,30 +280,48 @@ def detectormaker_fitting(iq, qx, qy, qz, num_pixels, max_q, angle_init_vals, an
     assert np.abs(1 - np.sum(phi_weights)) < 0.01, 'phi weights must sum to 1'
     assert np.abs(1 - np.sum(theta_weights)) < 0.01, 'theta weights must sum to 1'
 
-    grid = iq
+    # The device copy of the grid voxelgridmaker_fitting returned is used only if the caller's array still
+    # has the content it was handed out with.  The checksum of the host array (0.5 GB at the headline size)
+    # runs on a worker thread while the GPU already works on the resident copy; a mismatch (the array was
+    # edited in place: the reference reads the host array, comparison.py:790) discards that result and the
+    # host array is uploaded instead.
+    check = None
     if (iq is _resident["host"] and _resident["device"] is not None and _resident["device"].device == dev
-            and engine.host_checksum(iq) == _resident["sum"]):
-        grid = _resident["device"]                     # same array, same content: skip the upload
-    det = engine.DetectorEngine(grid, qx, qy, qz, device=dev)
-    tr.lap("voxel grid")
-    R, w = engine.orientation_tables(engine.grid_corners(gx, gy, gz), psis, psi_weights, phis, phi_weights,
-                                     thetas, theta_weights)
-    tr.lap("orientation tables")
+            and _resident["sum"] is not None):
+        check = _ContentCheck(iq, _resident["sum"])
     rank, world = parallel.rank_world()
-    sel = parallel.shard(np.arange(len(w)), rank, world)
-    with torch.cuda.device(dev):
-        image = torch.zeros(num_pixels * num_pixels, dtype=torch.float64, device=dev)
-    if len(sel):
-        det.accumulate(gx, gy, gz, np.ascontiguousarray(R[sel]), np.ascontiguousarray(w[sel]), image=image)
-    tr.lap("gather")
-    if world > 1:
-        parallel.all_reduce_image(image, dev)
-    out = engine.detector_epilogue(image, num_pixels, num_pixels, mirror, dev, finish=True)
-    tr.lap("all-reduce + epilogue")
-    with torch.cuda.device(dev):
-        # the image was summed in fp64 on the device; fp32 carries it across PCIe at half the bytes
-        # (2^-24 relative, far inside the 1e-4 bar) and is widened into the float64 array the caller gets
-        res = engine.to_host_f64(out.to(torch.float32), replicated=world > 1)
-    tr.lap("result to host")
+    R = w = None
+    for grid in ((_resident["device"], iq) if check is not None else (iq,)):
+        det = engine.DetectorEngine(grid, qx, qy, qz, device=dev)
+        tr.lap("voxel grid")
+        if R is None:
+            R, w = engine.orientation_tables(engine.grid_corners(gx, gy, gz), psis, psi_weights, phis, phi_weights,
+                                             thetas, theta_weights)
+            tr.lap("orientation tables")
+        sel = parallel.shard(np.arange(len(w)), rank, world)
+        with torch.cuda.device(dev):
+            image = torch.zeros(num_pixels * num_pixels, dtype=torch.float64, device=dev)
+        if len(sel):
+            det.accumulate(gx, gy, gz, np.ascontiguousarray(R[sel]), np.ascontiguousarray(w[sel]), image=image)
+        tr.lap("gather")
+        if world > 1:
+            parallel.all_reduce_image(image, dev)
+        out = engine.detector_epilogue(image, num_pixels, num_pixels, mirror, dev, finish=True)
+        tr.lap("all-reduce + epilogue")
+        with torch.cuda.device(dev):
+            # the image was summed in fp64 on the device; fp32 carries it across PCIe at half the bytes
+            # (2^-24 relative, far inside the 1e-4 bar) and is widened into the float64 array the caller gets
+            res = engine.to_host_f64(out.to(torch.float32), replicated=world > 1)
+        tr.lap("result to host")
+        if check is None or grid is iq:
+            break
+        same = check.result()
+        if world > 1:
+            flag = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)   # ranks take the same path
+            same = bool(flag.item())
+        tr.lap("content check")
+        if same:
+            break
     tr.done()
     return res, det_h.copy(), det_v.copy()

@@ -92,6 +92,13 @@ int gx_species_codes(const uint32_t *d_codepoints, int width, int64_t A, const u
  * (the reference always reads the host array: comparison.py:673,790).         */
 int gx_checksum64(const void *d_data, int64_t n, int widen_f32, uint64_t *d_out, void *stream);
 
+/* d_out2 = {max over z rows of sum |Re f|, max over z rows of sum |Im f|} of the atoms
+ * sorted by gx_atoms_sort_rows (species codes + h_table_abs [n_species][2] = |Re f_s|,
+ * |Im f_s|, or per-atom d_f): the most a single pixel of a row can receive, which sizes
+ * the fixed-point scale of gx_slices_fused (gx_fused_args.max_row_abs_re / _im).      */
+int gx_row_abs_f_max(const uint8_t *d_species, const gx_float2 *d_f, const int32_t *d_row_start, int N,
+                     const double *h_table_abs, int n_species, double *d_out2, void *stream);
+
 /* min and max over all atoms of y' = fma(y, cos, x*sin) for n_phi rotations.
  * d_yrange [n_phi][2].                   (utilities.py:303-317, vg.py:323) */
 int gx_slice_yrange(const double *d_xs, const double *d_ys, int64_t A,
@@ -266,6 +273,8 @@ typedef struct gx_fused_args {
     gx_float2 *d_work;
     float *d_sum;
     uint32_t *d_count2;
+    double *d_dc;               /* [2] zero-initialised, or NULL: fp64 side accumulator of the q = 0 sample of every
+                                   slice (+ its voxel index); fold it into d_sum with gx_fold_dc after the last batch */
     double r, pedestal_re, pedestal_im, avg_f_re, avg_f_im;
     int32_t n_species, n_phi, N, KC, q_num, row_lo, row_hi, fill_bkg, smooth_sigma;
     int32_t phases;              /* 0 or 3: both launches; 1: row kernel only; 2: column kernel only (per-kernel timing) */
@@ -277,6 +286,7 @@ typedef struct gx_fused_args {
     double table_f64[2 * GX_MAX_SPECIES];   /* host copy of the species f-values, (re, im) pairs, full precision */
 } gx_fused_args;
 int gx_slices_fused(const gx_fused_args *h_args, void *stream);
+int gx_fold_dc(double *d_dc, float *d_sum, void *stream);
 /* 1 when, for this grid side and kept-column bound, gx_slices_fused feeds the column
  * transform by TMA from a work buffer in permuted row order: d_work must then have
  * been zero-filled once before the first call of a run (rows outside the atom band

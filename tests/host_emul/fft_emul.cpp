@@ -40,6 +40,7 @@ extern "C" int emul_dft(int N, const float *plan, const float *in, float *out)
     case 11: run<11>(g, p, i, o); break;
     case 12: run<12>(g, p, i, o); break;
     case 13: run<13>(g, p, i, o); break;
+    case 14: run<14>(g, p, i, o); break;
     default: return -2;
     }
     return 0;
@@ -51,7 +52,7 @@ extern "C" int emul_offsets_ok()
 {
     return gx_fft_offsets_ok<4>() & gx_fft_offsets_ok<5>() & gx_fft_offsets_ok<6>() & gx_fft_offsets_ok<7>() &
            gx_fft_offsets_ok<8>() & gx_fft_offsets_ok<9>() & gx_fft_offsets_ok<10>() & gx_fft_offsets_ok<11>() &
-           gx_fft_offsets_ok<12>() & gx_fft_offsets_ok<13>();
+           gx_fft_offsets_ok<12>() & gx_fft_offsets_ok<13>() & gx_fft_offsets_ok<14>();
 }
 
 // 4096-point transform with the band-limited last pass (gx_fft_lastpass16_lowband): passes 0 and 1

@@ -371,3 +371,25 @@ def test_row_with_more_than_65535_atoms_takes_the_chunked_counters():
                                                 phis=phis)
     o_iq2 = ox.voxelgridmaker(coords, f, r, q, max_q, True, 3, phis=phis)[0]
     assert np.abs(iq2 - o_iq2).max() <= 1e-4 * o_iq2.max()
+
+
+def test_grid_size_4189_needs_the_16384_point_bluestein_against_oracle():
+    """r = 0.15, q = 0.01 -> grid_size = ceil(2 pi / (q r)) = 4189 (SURVEY hard part 2: config 5 at r = 0.15):
+    not a power of two and above 4096, so rows and columns go through the 16384-point chirp-z transform
+    (round 1 refused every non-power-of-two size above 4096).  One slice against the oracle."""
+    r, q, max_q = 0.15, 0.01, 2.0
+    coords, el = synth.random_slab(40_000, (200.0, 120.0, 180.0), seed=9)
+    f = ox.f_values_for(el, table=synth.fixed_f1f2)
+    setup = ox.stage_a_setup(coords, f, r, q, max_q)
+    assert setup["grid_size"] == 4189
+    phi = np.array([setup["phis"][321]])
+    iq, qx, qy, qz, eng = comparison.voxelgridmaker_fitting(coords, el, r, q, max_q, 12700.0, fill_bkg=True, smooth=7,
+                                                            phis=phi, return_state=True)
+    q3 = (setup["q_num"],) * 3
+    vsum, vcnt = np.zeros(q3), np.zeros(q3)
+    ox.run_slice(vsum, vcnt, coords, setup, r, float(phi[0]), True, 7)
+    lo, hi = eng.window
+    assert np.array_equal(eng.counts(), vcnt.astype(np.int64)[lo:hi, lo:hi, lo:hi])
+    assert np.abs(eng.sums() - vsum[lo:hi, lo:hi, lo:hi]).max() <= 1e-4 * vsum.max()
+    o_iq = ox.finalize_voxelgrid(vsum, vcnt, setup["q_axis"], max_q)[0]
+    assert np.abs(iq - o_iq).max() <= 1e-4 * o_iq.max()

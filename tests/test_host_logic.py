@@ -40,7 +40,8 @@ def test_product_fails_loudly_without_gpu():
 
 
 def test_unsupported_fft_size_is_an_error():
-    assert _lib.cdll().gx_fft_plan_bytes(5000) == _lib.GX_ERR_UNSUPPORTED
+    assert _lib.cdll().gx_fft_plan_bytes(8193) == _lib.GX_ERR_UNSUPPORTED      # non-pow2 above 8192
+    assert _lib.cdll().gx_fft_plan_bytes(32768) == _lib.GX_ERR_UNSUPPORTED
     assert "unsupported" in _lib.last_error()
     assert _lib.cdll().gx_fft_plan_bytes(8) == _lib.GX_ERR_UNSUPPORTED
 
@@ -53,7 +54,8 @@ def fft_emul(tmp_path_factory):
     return ctypes.CDLL(so)
 
 
-@pytest.mark.parametrize("N", [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 17, 131, 262, 524, 1048, 2095, 4095])
+@pytest.mark.parametrize("N", [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 17, 131, 262, 524, 1048, 2095, 4095,
+                               4189, 8192 - 3])
 def test_fft_engine_host_build_matches_numpy(fft_emul, N):
     nbytes = _lib.cdll().gx_fft_plan_bytes(N)
     assert nbytes >= 0          # N = 16 is a single radix-16 pass: empty table
