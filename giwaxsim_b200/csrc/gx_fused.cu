@@ -102,7 +102,7 @@ struct FusedArgs {
     float *vsum;
     uint32_t *count2;
     float dc_re, dc_im;        // pedestal * N^2
-    double *dc_acc;            // [2] fp64 accumulator of the DC sample + its voxel index (NULL: straight into vsum)
+    double *dc_acc;            // [2 GX_DC_SLOTS] fp64 sums of the DC samples + their voxel keys (NULL: straight into vsum)
     int n_phi;
     int use_const;             // row-kernel scalars are in the constant tables
     int chunk_atoms;           // atoms one pass of the integer accumulators may take (31-bit headroom)
@@ -197,6 +197,10 @@ template <int NB0, int R0, int S0, int NT, bool EXACT, bool FINISH>
 __device__ __forceinline__ void flush_fixed(float2 (&px)[NB0][R0], const int32_t *acc, int NP, int tid, int N,
                                             float inv_re, float inv_im, float af_re, float af_im, float mzv)
 {
+    // FINISH: v = ((w0 + d af_re 2^k_re) m 2^-k_re, (w1 + d af_im 2^k_im) m 2^-k_im) - the scales ride on the
+    // background coefficient and on the mask, so a pixel costs two conversions, two FFMA and three FMUL
+    const float bg_re = af_re / inv_re, bg_im = af_im / inv_im;       // exact: the scales are powers of two
+    const float mz_re = mzv * inv_re, mz_im = mzv * inv_im;
 #pragma unroll
     for (int i = 0; i < NB0; ++i) {
         const int t = tid + i * NT;
@@ -211,14 +215,14 @@ __device__ __forceinline__ void flush_fixed(float2 (&px)[NB0][R0], const int32_t
         for (int n = 0; n < R0; ++n) {
             const int y = t + S0 * n;
             const int yy = EXACT ? y : min(y, N - 1);
-            const float sx = (float)acc[yy] * inv_re, sy = (float)acc[NP + yy] * inv_im;
+            const float w0 = (float)acc[yy], w1 = (float)acc[NP + yy];
             if (FINISH) {
                 const float2 dm = px[i][n];
-                const float m = (EXACT || y < N) ? mzv * dm.y : 0.f;
-                px[i][n] = make_float2(fmaf(dm.x, af_re, sx) * m, fmaf(dm.x, af_im, sy) * m);
+                const float my = (EXACT || y < N) ? dm.y : 0.f;
+                px[i][n] = make_float2(fmaf(dm.x, bg_re, w0) * (mz_re * my), fmaf(dm.x, bg_im, w1) * (mz_im * my));
             } else if (EXACT || y < N) {
-                px[i][n].x += sx;
-                px[i][n].y += sy;
+                px[i][n].x = fmaf(w0, inv_re, px[i][n].x);
+                px[i][n].y = fmaf(w1, inv_im, px[i][n].y);
             }
         }
     }
@@ -388,14 +392,24 @@ slice_rows_fused(FusedArgs fa)
 }
 
 // ------------------------------------------------------------------ F2 ----
-// The DC sample of a slice (q = 0: |sum of all f + pedestal N^2|^2, the same huge number for every rotation,
-// ~1e10 x its neighbours) is accumulated in fp64 on the side and folded into its voxel once per run
-// (gx_fold_dc): 1800 fp32 additions of it random-walked to 1.4e-6 of the maximum and made the result depend
-// on how the rotations were split over ranks.
+// The DC sample of a slice (the coefficient k = 0 of column N/2: |sum of all f + pedestal N^2|^2, the same
+// huge number for every rotation, ~1e10 x its neighbours) is accumulated in fp64 on the side and folded into
+// the voxel grid once per run (gx_fold_dc): 1800 fp32 additions of it random-walked to 1.4e-6 of the maximum
+// and made the result depend on how the rotations were split over ranks.  Column N/2 of the symmetric
+// linspace axis sits half a step off q = 0 on a side that depends on the rotation, so the samples fall into
+// up to four neighbouring voxels: the side table has GX_DC_SLOTS (key = voxel + 1, fp64 sum) entries,
+// claimed with a compare-and-swap; a full table falls back to the fp32 grid.
+#define GX_DC_SLOTS 8
 __device__ __forceinline__ void add_dc_sample(const FusedArgs &fa, size_t voxel, float2 v)
 {
-    atomicAdd(fa.dc_acc, (double)v.x * (double)v.x + (double)v.y * (double)v.y);
-    fa.dc_acc[1] = (double)voxel;
+    const double val = (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(fa.dc_acc + GX_DC_SLOTS);
+    const unsigned long long key = (unsigned long long)voxel + 1ull;
+    for (int s = 0; s < GX_DC_SLOTS; ++s) {
+        const unsigned long long prev = atomicCAS(keys + s, 0ull, key);
+        if (prev == 0ull || prev == key) { atomicAdd(fa.dc_acc + s, val); return; }
+    }
+    atomicAdd(fa.vsum + voxel, (float)val);
 }
 
 template <int L, int TC, bool BLUE>
@@ -907,13 +921,20 @@ extern "C" int gx_slices_fused(const gx_fused_args *h, void *stream)
 
 __global__ void fold_dc_kernel(double *dc, float *vsum)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0 && dc[0] != 0.0) {
-        vsum[(size_t)dc[1]] += (float)dc[0];
-        dc[0] = 0.0;
+    const int s = threadIdx.x;
+    if (blockIdx.x == 0 && s < GX_DC_SLOTS) {
+        unsigned long long *keys = reinterpret_cast<unsigned long long *>(dc + GX_DC_SLOTS);
+        const unsigned long long key = keys[s];
+        if (key != 0ull) {
+            atomicAdd(vsum + (size_t)(key - 1ull), (float)dc[s]);
+            dc[s] = 0.0;
+            keys[s] = 0ull;
+        }
     }
 }
 
-// vsum[voxel of q = 0] += the fp64 sum of the DC samples gathered in d_dc since the last fold; d_dc is reset.
+// d_sum[voxel] += the fp64 sums of the DC samples gathered in d_dc (16 x 8 bytes, zero-initialised) since the
+// last fold; d_dc is reset.
 extern "C" int gx_fold_dc(double *d_dc, float *d_sum, void *stream)
 {
     GX_REQUIRE(d_dc && d_sum, "NULL pointer");

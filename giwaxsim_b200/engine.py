@@ -71,6 +71,7 @@ def _pinned_staging(nbytes):
 
 
 PIPELINED_DOWNLOAD_MIN_BYTES = 64 << 20
+SHARED_RESULT_MIN_BYTES = 128 << 20        # float64 bytes above which N ranks of a node share one host conversion
 PIPELINED_DOWNLOAD_CHUNKS = 8
 _host_pool = []        # [{"buf": flat float64 CPU tensor, "live": weakref to the array handed out}]
 _HOST_POOL_MAX = 4
@@ -110,7 +111,9 @@ def to_host_f64(t, out=None, replicated=False):
     t = t.contiguous()
     if replicated and out is None:
         from . import parallel
-        shared = parallel.shared_result_f64(t, lambda dev_slice, view: to_host_f64(dev_slice, out=view))
+        # (small results - the 33 MB detector image - are cheaper to convert per rank than to share)
+        shared = parallel.shared_result_f64(t, lambda dev_slice, view: to_host_f64(dev_slice, out=view),
+                                            min_bytes=SHARED_RESULT_MIN_BYTES)
         if shared is not None:
             return shared
     nbytes = t.numel() * t.element_size()
@@ -610,7 +613,7 @@ class SliceEngine:
                 self.vsum = self.vsum_store[:self.q_out ** 3]
                 self.count3 = torch.zeros(self.q_out ** 3, dtype=torch.int32, device=dev) if count3d else None
                 self.count2 = None if count3d else torch.zeros(self.q_out ** 2, dtype=torch.int32, device=dev)
-            self.dc = torch.zeros(2, dtype=torch.float64, device=dev)     # fp64 side sum of the q = 0 samples
+            self.dc = torch.zeros(16, dtype=torch.float64, device=dev)    # fp64 side sums of the DC samples (gx_fold_dc)
             self.row_hist = torch.zeros(self.q_out, dtype=torch.int32, device=dev)
             call("gx_row_histogram", ptr(self.row_index), self.N, self.q_out, ptr(self.row_hist), st)
             if self.sigma > 0:

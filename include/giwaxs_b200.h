@@ -273,8 +273,8 @@ typedef struct gx_fused_args {
     gx_float2 *d_work;
     float *d_sum;
     uint32_t *d_count2;
-    double *d_dc;               /* [2] zero-initialised, or NULL: fp64 side accumulator of the q = 0 sample of every
-                                   slice (+ its voxel index); fold it into d_sum with gx_fold_dc after the last batch */
+    double *d_dc;               /* [16] zero-initialised, or NULL: fp64 side sums of the k = 0 sample of the centre column of
+                                   every slice (8 sums + 8 voxel keys); fold into d_sum with gx_fold_dc after the last batch */
     double r, pedestal_re, pedestal_im, avg_f_re, avg_f_im;
     int32_t n_species, n_phi, N, KC, q_num, row_lo, row_hi, fill_bkg, smooth_sigma;
     int32_t phases;              /* 0 or 3: both launches; 1: row kernel only; 2: column kernel only (per-kernel timing) */
