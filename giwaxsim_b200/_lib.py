@@ -93,6 +93,10 @@ _PROTOTYPES = {
     "gx_slices_fused": (_i, [_p, _p]),
     "gx_fused_wants_zeroed_work": (_i, [_i, _i]),
     "gx_fold_dc": (_i, [_p, _p, _p]),
+    "gx_polar_warp": (_i, [_p, _i, _i, _d, _d, _d, _i, _i, _d, _p, _p]),
+    "gx_polar_unwarp": (_i, [_p, _i, _i, _d, _d, _d, _i, _i, _d, _p, _p]),
+    "gx_gather_columns": (_i, [_p, _i, _i, _p, _i, _p, _p, _p]),
+    "gx_masked_fit_sums": (_i, [_p, _p, _p, _i64, _p, _p]),
     "gx_comm_unique_id": (_i, [_p]),
     "gx_comm_init": (_i, [_p, _i, _i, _p]),
     "gx_comm_destroy": (_i, [_p]),
@@ -158,7 +162,7 @@ _LAUNCHES = {
     "gx_axis_col_index": 1, "gx_axis_row_index": 1, "gx_bin_slices": 1, "gx_row_histogram": 1,
     "gx_voxel_finalize": 1, "gx_voxel_shell_scale": 1, "gx_rotate_points": 1, "gx_detector_accumulate": 1, "gx_detector_epilogue": 1,
     "gx_detector_accumulate_fast": 1, "gx_detector_accumulate_affine": 1, "gx_grid_affine_fit": 1,
-    "gx_slices_fused": 2, "gx_species_histogram": 1, "gx_species_codes": 1, "gx_checksum64": 1, "gx_row_abs_f_max": 2, "gx_fold_dc": 1, "gx_window_indices": 1, "gx_slab_minmax": 3, "gx_slab_count": 3, "gx_slab_write": 1, "gx_slice_col_range": 1, "gx_extreme_atoms": 1, "gx_hull_filter": 1,
+    "gx_slices_fused": 2, "gx_species_histogram": 1, "gx_species_codes": 1, "gx_checksum64": 1, "gx_row_abs_f_max": 3, "gx_fold_dc": 1, "gx_polar_warp": 1, "gx_polar_unwarp": 1, "gx_gather_columns": 1, "gx_masked_fit_sums": 1, "gx_window_indices": 1, "gx_slab_minmax": 3, "gx_slab_count": 3, "gx_slab_write": 1, "gx_slice_col_range": 1, "gx_extreme_atoms": 1, "gx_hull_filter": 1,
 }
 _launch_count = 0
 

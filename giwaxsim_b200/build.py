@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libgiwaxs_b200.so")
 SOURCES = ["gx_api.cu", "gx_atoms.cu", "gx_project.cu", "gx_fft.cu", "gx_bin.cu", "gx_detector.cu",
-           "gx_detector_affine.cu", "gx_fused.cu", "gx_slab.cu", "gx_comm.cu"]
+           "gx_detector_affine.cu", "gx_fused.cu", "gx_slab.cu", "gx_comm.cu", "gx_compare.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=default", "--expt-relaxed-constexpr", "-DGX_TWP=1",

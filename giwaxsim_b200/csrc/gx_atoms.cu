@@ -553,16 +553,18 @@ extern "C" int gx_checksum64(const void *d_data, int64_t n, int widen_f32, uint6
 
 
 // ------------------------------------------------- per-row sums of |Re f|, |Im f| ----
+struct AbsTable { double v[2 * GX_MAX_SPECIES]; };      // kernel-parameter copy of the host table
+
 // Largest sum over the atoms of one z pixel row of |Re f| and of |Im f|: what a single pixel of a row
 // can receive at most, which sizes the fixed-point scale of the fused row kernel's integer accumulators
 // (gx_fused_args.max_row_abs_re / _im).  One warp per row; atoms are sorted by row.
 __global__ void __launch_bounds__(ATOM_THREADS)
 row_abs_f_max_kernel(const uint8_t *__restrict__ species, const float2 *__restrict__ f,
-                     const int32_t *__restrict__ row_start, int N, const double *__restrict__ table_abs,
+                     const int32_t *__restrict__ row_start, int N, AbsTable table_abs,
                      int n_species, unsigned long long *out2)
 {
     __shared__ double s_tab[2 * GX_MAX_SPECIES];
-    if (threadIdx.x < 2 * GX_MAX_SPECIES) s_tab[threadIdx.x] = (int)threadIdx.x < 2 * n_species ? table_abs[threadIdx.x] : 0.0;
+    if (threadIdx.x < 2 * GX_MAX_SPECIES) s_tab[threadIdx.x] = (int)threadIdx.x < 2 * n_species ? table_abs.v[threadIdx.x] : 0.0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -588,6 +590,11 @@ row_abs_f_max_kernel(const uint8_t *__restrict__ species, const float2 *__restri
     }
 }
 
+__global__ void row_abs_f_init_kernel(unsigned long long *out2)
+{
+    if (threadIdx.x < 2) out2[threadIdx.x] = gx_ord(0.0);
+}
+
 __global__ void row_abs_f_decode_kernel(unsigned long long *out2)
 {
     if (threadIdx.x < 2) {
@@ -603,18 +610,15 @@ extern "C" int gx_row_abs_f_max(const uint8_t *d_species, const gx_float2 *d_f, 
     GX_REQUIRE(n_species >= 0 && n_species <= GX_MAX_SPECIES && (!d_species || (h_table_abs && n_species > 0)),
                "species table missing");
     cudaStream_t st = gx_stream(stream);
-    double *d_tab = NULL;
-    if (d_species) {
-        GX_CUDA(cudaMallocAsync(&d_tab, 2 * GX_MAX_SPECIES * sizeof(double), st));
-        GX_CUDA(cudaMemcpyAsync(d_tab, h_table_abs, 2 * (size_t)n_species * sizeof(double), cudaMemcpyHostToDevice, st));
-    }
-    unsigned long long init[2] = {gx_ord_host(0.0), gx_ord_host(0.0)};
-    GX_CUDA(cudaMemcpyAsync(d_out2, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    AbsTable tab;
+    memset(&tab, 0, sizeof(tab));
+    if (d_species)
+        for (int k = 0; k < 2 * n_species; ++k) tab.v[k] = h_table_abs[k];
+    row_abs_f_init_kernel<<<1, 32, 0, st>>>(reinterpret_cast<unsigned long long *>(d_out2));
     int blocks = (N * 32 + ATOM_THREADS - 1) / ATOM_THREADS;
     if (blocks > GX_SM_COUNT * 8) blocks = GX_SM_COUNT * 8;
     row_abs_f_max_kernel<<<blocks, ATOM_THREADS, 0, st>>>(d_species, reinterpret_cast<const float2 *>(d_f), d_row_start, N,
-                                                           d_tab, n_species, reinterpret_cast<unsigned long long *>(d_out2));
+                                                           tab, n_species, reinterpret_cast<unsigned long long *>(d_out2));
     row_abs_f_decode_kernel<<<1, 32, 0, st>>>(reinterpret_cast<unsigned long long *>(d_out2));
-    if (d_tab) GX_CUDA(cudaFreeAsync(d_tab, st));
     return gx_check_launch("gx_row_abs_f_max");
 }

@@ -325,3 +325,192 @@ def detectormaker_fitting(iq, qx, qy, qz, num_pixels, max_q, angle_init_vals, an
             break
     tr.done()
     return res, det_h.copy(), det_v.copy()
+
+
+# ---------------------------------------------------------------------------
+# post-hoc comparison transforms (second half): what evaluate_fit / the fit loop
+# apply to the finished detector image (comparison.py:161-191, 469-592, 873-912)
+# ---------------------------------------------------------------------------
+def trim_sim_data(sim_det_ints, det_h, det_v, exp_qxy, exp_qz):
+    """Image and axes restricted to the q range of the experimental data (comparison.py:161-191)."""
+    h_mask = (det_h >= np.min(exp_qxy)) & (det_h <= np.max(exp_qxy))
+    v_mask = (det_v >= np.min(exp_qz)) & (det_v <= np.max(exp_qz))
+    return sim_det_ints[v_mask, :][:, h_mask], det_h[h_mask], det_v[v_mask]
+
+
+def _f64_device(a, dev):
+    if isinstance(a, torch.Tensor):
+        return a.to(dev, torch.float64).contiguous()
+    return engine._dev(np.ascontiguousarray(a, dtype=np.float64), dev)
+
+
+def _polar_warp_device(d_img, o, r, shape, cont, dev):
+    out = torch.empty(shape, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        engine.call("gx_polar_warp", engine.ptr(d_img), int(d_img.shape[0]), int(d_img.shape[1]), float(o[0]),
+                    float(o[1]), float(r), int(shape[0]), int(shape[1]), float(cont), engine.ptr(out), engine._stream())
+    return out
+
+
+def linear_polar(img, o=None, r=None, output=None, order=1, cont=0):
+    """Cartesian image -> polar image, rows = angle, columns = radius (comparison.py:469-499),
+    sampled on the device like scipy's map_coordinates(order=1, cval=cont)."""
+    if order != 1:
+        raise ValueError("only order=1 (the value every caller of the reference uses) is implemented")
+    img = np.asarray(img)
+    o = np.array(img.shape[:2]) / 2 - 0.5 if o is None else np.array(o)
+    if r is None:
+        r = np.sqrt((np.array(img.shape[:2]) ** 2).sum()) / 2
+    if output is None:
+        shape = (int(round(r * 2 * np.pi)), int(round(r)))
+    elif isinstance(output, tuple):
+        shape = output
+    else:
+        shape = output.shape
+    dev = engine.resolve_device()
+    res = _polar_warp_device(_f64_device(img, dev), o, r, shape, cont, dev).cpu().numpy().astype(img.dtype, copy=False)
+    if output is not None and not isinstance(output, tuple):
+        output[...] = res
+        return output
+    return res
+
+
+def _polar_unwarp_device(d_polar, o, r, shape, cont, dev):
+    out = torch.empty(shape, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        engine.call("gx_polar_unwarp", engine.ptr(d_polar), int(d_polar.shape[0]), int(d_polar.shape[1]), float(r),
+                    float(o[0]), float(o[1]), int(shape[0]), int(shape[1]), float(cont), engine.ptr(out),
+                    engine._stream())
+    return out
+
+
+def polar_linear(img, o=None, r=None, output=None, order=1, cont=0):
+    """Polar image -> Cartesian image (comparison.py:501-539)."""
+    if order != 1:
+        raise ValueError("only order=1 (the value every caller of the reference uses) is implemented")
+    img = np.asarray(img)
+    if r is None:
+        r = img.shape[1]
+    if output is None:
+        shape = (int(r * 2), int(r * 2))
+    elif isinstance(output, tuple):
+        shape = output
+    else:
+        shape = output.shape
+    o = np.array(shape) / 2 - 0.5 if o is None else np.array(o)
+    dev = engine.resolve_device()
+    res = _polar_unwarp_device(_f64_device(img, dev), o, r, shape, cont, dev).cpu().numpy().astype(img.dtype, copy=False)
+    if output is not None and not isinstance(output, tuple):
+        output[...] = res
+        return output
+    return res
+
+
+def pad_column_map(n_cols, r_axis, pad_width, pad_range):
+    """Source column of every column of add_pad's output (comparison.py:541-564): the reference
+    duplicates pad_width_pixels columns spread over pad_range with np.insert and trims as many from
+    the end; the same inserts applied to the column numbers give the gather map."""
+    pad_range_min, pad_range_max = pad_range
+    widths = np.diff(r_axis)
+    widths_trim = widths[widths > 0]
+    pixel_width = np.mean(widths_trim)
+    pad_width_pixels = int(np.round(pad_width / pixel_width))
+    cols = np.arange(n_cols)
+    if pad_width_pixels == 0:
+        return cols
+    pad_start_idx = int(np.argmin(np.abs(r_axis - pad_range_min)))
+    pad_end_idx = int(np.argmin(np.abs(r_axis - pad_range_max)))
+    spacing = int((pad_end_idx - pad_start_idx - 1) / pad_width_pixels - 1)
+    assert spacing >= 0, 'pad_range is too small for desired pad_width'
+    for i in range(pad_width_pixels):
+        pad_idx = pad_start_idx + 2 * i + spacing * i
+        cols = np.insert(cols, pad_idx + 1, cols[pad_idx])
+    return cols[:-pad_width_pixels]
+
+
+def add_pad(polar_image, r_axis, pad_width, pad_range):
+    """Stretch the polar image between pad_range by duplicating columns (comparison.py:541-564)."""
+    cols = pad_column_map(polar_image.shape[1], r_axis, pad_width, pad_range)
+    return polar_image[:, cols]
+
+
+def _shift_peak_device(d_image, det_h, det_v, pad_width_qspace, pad_range_qspace, dev):
+    """shift_peak with the image on the device (fp64 tensor in, fp64 tensor out)."""
+    det_h, det_v = np.asarray(det_h, dtype=np.float64), np.asarray(det_v, dtype=np.float64)
+    row, col = (int(v) for v in d_image.shape)
+    radius = float(np.sqrt(row ** 2 + col ** 2))
+    centre = (int(np.argmin(np.abs(det_v))), int(np.argmin(np.abs(det_h))))
+    shape = (int(round(radius * 2 * np.pi)), int(round(radius)))
+    polar = _polar_warp_device(d_image, centre, radius, shape, 0.0, dev)
+    # r_axis = first row (angle 0) of the warped |q| image
+    xx, yy = np.meshgrid(det_h, det_v)
+    d_r = engine._dev(np.hypot(xx, yy), dev)
+    r_axis = _polar_warp_device(d_r, centre, radius, (1, shape[1]), 0.0, dev).cpu().numpy()[0]
+    cols = pad_column_map(shape[1], r_axis, pad_width_qspace, pad_range_qspace)
+    d_map = engine._dev(np.ascontiguousarray(cols, dtype=np.int32), dev)
+    padded = torch.empty_like(polar)
+    with torch.cuda.device(dev):
+        engine.call("gx_gather_columns", engine.ptr(polar), shape[0], shape[1], engine.ptr(d_map), shape[1],
+                    engine.ptr(polar), engine.ptr(padded), engine._stream())
+    return _polar_unwarp_device(padded, centre, shape[1], (row, col), 0.0, dev)
+
+
+def shift_peak(image, det_h, det_v, pad_width_qspace, pad_range_qspace):
+    """Radial stretch of the image between pad_range (pi-pi peak position correction):
+    polar warp -> add_pad -> zero mask -> inverse warp (comparison.py:566-592), on the device."""
+    dev = engine.resolve_device()
+    out = _shift_peak_device(_f64_device(np.asarray(image), dev), det_h, det_v, pad_width_qspace,
+                             pad_range_qspace, dev)
+    return out.cpu().numpy()
+
+
+def _scale_offset_device(d_sim, d_ref, d_mask, dev):
+    sums = torch.empty(5, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        engine.call("gx_masked_fit_sums", engine.ptr(d_sim), engine.ptr(d_ref), engine.ptr(d_mask),
+                    int(d_sim.numel()), engine.ptr(sums), engine._stream())
+    n, sx, sy, sxx, sxy = (float(v) for v in sums.cpu().numpy())
+    det = n * sxx - sx * sx
+    if n < 2 or det == 0.0:
+        raise np.linalg.LinAlgError("scale/offset fit is singular")
+    scale = (n * sxy - sx * sy) / det
+    return scale, (sy - scale * sx) / n
+
+
+def optimize_scale_offset(sim_map, rebin_map, rebin_mask):
+    """Least-squares scale and offset of sim_map against rebin_map over the pixels with
+    rebin_mask == 0 (comparison.py:873-882; closed form of the two-parameter lstsq)."""
+    dev = engine.resolve_device()
+    return _scale_offset_device(_f64_device(np.asarray(sim_map), dev), _f64_device(np.asarray(rebin_map), dev),
+                                _f64_device(np.asarray(rebin_mask), dev), dev)
+
+
+def evaluate_fit(best_params, fixed_slab_params, fixed_voxelgrid_params, fixed_detectormaker_params,
+                 fixed_exp_params):
+    """Simulated, scaled and masked detector image of a slab size against the re-binned experiment
+    (comparison.py:884-912): slab -> voxel grid -> detector image -> trim -> shift_peak -> scale/offset.
+    The warps and the fit sums run on the device; returns (rebin_map, sim_comp_map, diff_map)."""
+    x_size, y_size, z_size = best_params
+    input_filepath, a, b, c, alpha, beta, gamma = fixed_slab_params
+    r_voxel_size, q_voxel_size, max_q, energy, fill_bkg, smooth = fixed_voxelgrid_params
+    (num_pixels, angle_init_vals, angle_init_axs, psis, psi_weights_path, phis, phi_weights_path, thetas,
+     theta_weights_path) = fixed_detectormaker_params
+    rebin_map, rebin_mask, exp_qxy, exp_qz, pad_width, pad_range = fixed_exp_params
+    coords_slab, elements_slab = slabmaker_fitting(input_filepath, x_size, y_size, z_size, a, b, c, alpha, beta, gamma)
+    iq, qx, qy, qz = voxelgridmaker_fitting(coords_slab, elements_slab, r_voxel_size, q_voxel_size, max_q, energy,
+                                            num_cpus=None, fill_bkg=fill_bkg, smooth=smooth)
+    det_sum, det_h, det_v = detectormaker_fitting(iq, qx, qy, qz, num_pixels, max_q, angle_init_vals, angle_init_axs,
+                                                  psis, psi_weights_path, phis, phi_weights_path, thetas,
+                                                  theta_weights_path, mirror=True)
+    sim_int_trim, det_h_trim, det_v_trim = trim_sim_data(det_sum, det_h, det_v, exp_qxy, exp_qz)
+    dev = engine.resolve_device()
+    d_sim = _shift_peak_device(_f64_device(sim_int_trim, dev), det_h_trim, det_v_trim, pad_width, pad_range, dev)
+    rebin_map = np.asarray(rebin_map)
+    d_ref, d_mask = _f64_device(rebin_map, dev), _f64_device(np.asarray(rebin_mask), dev)
+    scale, offset = _scale_offset_device(d_sim, d_ref, d_mask, dev)
+    # the last three element-wise steps on the (trimmed, few hundred pixels a side) host image, as the reference
+    scaled_map = scale * d_sim.cpu().numpy() + offset
+    sim_comp_map = scaled_map.copy()
+    sim_comp_map[np.asarray(rebin_mask) == 1] = 0
+    diff_map = np.where(rebin_map > 1e-10, sim_comp_map - rebin_map, 0)
+    return rebin_map, sim_comp_map, diff_map

@@ -328,6 +328,25 @@ int gx_slab_write(const gx_slab_args *h_args, const double *h_min3, const double
                   const double *h_kept_min3, const int64_t *d_tile_offset, double *d_xyz_out,
                   uint8_t *d_species_out, void *stream);
 
+/* ------------------------------- post-hoc image transforms (next row N4) */
+/* The polar warp pair of shift_peak and the masked linear fit of optimize_scale_offset
+ * (tools/comparison.py:469-592, 873-882), fp64, on the trimmed detector image.
+ * Sampling = scipy.ndimage.map_coordinates(order=1, mode='constant', cval).
+ *  gx_polar_warp   : linear_polar - d_out [out_h][out_w], radius linspace(0, r, out_w),
+ *                    angle linspace(0, 2 pi, out_h) about (o_row, o_col)
+ *  gx_polar_unwarp : polar_linear - d_out [out_h][out_w] from d_polar [ph][pw], radius r
+ *  gx_gather_columns : d_out[i][j] = d_src[i][d_map[j]], zeroed where d_zero_ref[i][j] == 0
+ *                    (add_pad's column duplication + the zero mask; d_zero_ref may be NULL)
+ *  gx_masked_fit_sums: d_out5 = {n, sum x, sum y, sum x^2, sum x y} over mask == 0           */
+int gx_polar_warp(const double *d_img, int rows, int cols, double o_row, double o_col, double r,
+                  int out_h, int out_w, double cval, double *d_out, void *stream);
+int gx_polar_unwarp(const double *d_polar, int ph, int pw, double r, double o_row, double o_col,
+                    int out_h, int out_w, double cval, double *d_out, void *stream);
+int gx_gather_columns(const double *d_src, int rows, int src_cols, const int32_t *d_map, int out_cols,
+                      const double *d_zero_ref, double *d_out, void *stream);
+int gx_masked_fit_sums(const double *d_x, const double *d_y, const double *d_mask, int64_t n,
+                       double *d_out5, void *stream);
+
 /* ----------------------------------------------------- multi-GPU exchange */
 /* One process per GPU; the partial voxel sums / counts of stage A and the
  * partial detector images of stage B meet in a sum (the reference's shared

@@ -180,3 +180,39 @@ def test_randomised_pipeline_bit_exact(seed):
                                        mirror=mirror)
     db = ox.detectormaker(b[0], b[1], b[2], b[3], P, max_q, vals, axs, psis, w[0], phis, w[1], thetas, w[2], mirror=mirror)
     assert all(np.array_equal(x, y) for x, y in zip(da, db))
+
+
+def _compare_case(seed=4, P=60):
+    rng = np.random.default_rng(seed)
+    h = np.linspace(-2.0, 2.0, P)
+    v = np.linspace(-2.0, 2.0, P)
+    xx, yy = np.meshgrid(h, v)
+    img = np.exp(-((np.hypot(xx, yy) - 1.1) / 0.15) ** 2) * (1 + 0.3 * np.cos(3 * np.arctan2(yy, xx))) + 0.05 * rng.random((P, P))
+    exp_qxy, exp_qz = np.linspace(0.0, 1.8, 37), np.linspace(0.0, 1.7, 35)
+    return img, h, v, exp_qxy, exp_qz
+
+
+def test_post_hoc_transforms_bit_exact():
+    """trim_sim_data, linear_polar, polar_linear, add_pad, shift_peak, optimize_scale_offset and the tail of
+    evaluate_fit (comparison.py:161-191, 469-592, 873-912) restated in the oracle == the reference functions."""
+    ref = ref_shim.load().comparison
+    img, h, v, exp_qxy, exp_qz = _compare_case()
+    a = ref.trim_sim_data(img, h, v, exp_qxy, exp_qz)
+    b = ox.trim_sim_data(img, h, v, exp_qxy, exp_qz)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    trim, th, tv = b
+    centre = (int(np.argmin(np.abs(tv))), int(np.argmin(np.abs(th))))
+    radius = float(np.sqrt(trim.shape[0] ** 2 + trim.shape[1] ** 2))
+    pol_ref = ref.linear_polar(trim, o=centre, r=radius, output=None, order=1, cont=0)
+    pol = ox.linear_polar(trim, centre, radius)
+    assert np.array_equal(pol, pol_ref)
+    assert np.array_equal(ox.polar_linear(pol, centre, trim.shape), ref.polar_linear(pol_ref, o=centre, r=None, output=trim.shape))
+    for pad_width, pad_range in [(0.05, (0.9, 1.4)), (0.0, (0.9, 1.4)), (0.12, (0.3, 1.6))]:
+        assert np.array_equal(ox.shift_peak(trim.copy(), th, tv, pad_width, pad_range),
+                              ref.shift_peak(trim.copy(), th, tv, pad_width, pad_range))
+    rng = np.random.default_rng(8)
+    target = 3.5 * ox.shift_peak(trim.copy(), th, tv, 0.05, (0.9, 1.4)) + 0.7 + 0.01 * rng.random(trim.shape)
+    mask = (rng.random(trim.shape) < 0.2).astype(int)
+    s0, o0 = ref.optimize_scale_offset(trim, target, mask)
+    s1, o1 = ox.optimize_scale_offset(trim, target, mask)
+    assert (s0, o0) == (s1, o1)
