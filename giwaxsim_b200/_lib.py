@@ -97,6 +97,9 @@ _PROTOTYPES = {
     "gx_polar_unwarp": (_i, [_p, _i, _i, _d, _d, _d, _i, _i, _d, _p, _p]),
     "gx_gather_columns": (_i, [_p, _i, _i, _p, _i, _p, _p, _p]),
     "gx_masked_fit_sums": (_i, [_p, _p, _p, _i64, _p, _p]),
+    "gx_host_register": (_i, [_p, _i64]),
+    "gx_host_unregister": (_i, [_p]),
+    "gx_copy_to_host_async": (_i, [_p, _p, _i64, _p]),
     "gx_comm_unique_id": (_i, [_p]),
     "gx_comm_init": (_i, [_p, _i, _i, _p]),
     "gx_comm_destroy": (_i, [_p]),

@@ -61,3 +61,35 @@ extern "C" int gx_device_check(int device)
     }
     return GX_OK;
 }
+
+// ------------------------------------------------------- host boundary ----
+// Page-lock a range of host memory the caller owns (a slab of a pooled POSIX shared-memory result
+// segment) so that results can be DMA'd straight into their final place, and the asynchronous copy
+// itself.  Registration is expensive (~0.2 ms per MB): callers register pooled buffers once.
+extern "C" int gx_host_register(void *h_ptr, int64_t nbytes)
+{
+    GX_REQUIRE(h_ptr && nbytes > 0, "bad arguments");
+    cudaError_t e = cudaHostRegister(h_ptr, (size_t)nbytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return GX_OK; }
+    if (e != cudaSuccess) {
+        gx_set_error("gx_host_register: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return GX_ERR_CUDA;
+    }
+    return GX_OK;
+}
+
+extern "C" int gx_host_unregister(void *h_ptr)
+{
+    if (!h_ptr) return GX_OK;
+    cudaError_t e = cudaHostUnregister(h_ptr);
+    if (e != cudaSuccess) cudaGetLastError();
+    return GX_OK;
+}
+
+extern "C" int gx_copy_to_host_async(void *h_dst, const void *d_src, int64_t nbytes, void *stream)
+{
+    GX_REQUIRE(h_dst && d_src && nbytes >= 0, "bad arguments");
+    GX_CUDA(cudaMemcpyAsync(h_dst, d_src, (size_t)nbytes, cudaMemcpyDeviceToHost, gx_stream(stream)));
+    return GX_OK;
+}

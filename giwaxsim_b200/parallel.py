@@ -42,6 +42,9 @@ def all_reduce_sum(tensors, group=None):
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
 
+import os as _os_env
+# GIWAXS_B200_COMBINE = allreduce (default) | scatter: how N ranks combine their partial voxel sums
+COMBINE = _os_env.environ.get("GIWAXS_B200_COMBINE", "allreduce")
 _comm = {"handle": None, "key": None}
 GX_DTYPE_F32, GX_DTYPE_U32, GX_DTYPE_F64 = 0, 1, 2
 
@@ -94,16 +97,28 @@ def all_reduce_image(image, device):
 def combine_and_finalize(eng, q_axis, max_q, device, window=None, crop=True, f0=True, group=None):
     """Partial voxel sums / counts of every rank -> the finished iq grid on every rank
     (reference: the shared `+=` of voxelgrids.py:502-503 followed by comparison.py:765-786).
-    One rank: just the finalise kernel.  N ranks on GPUs: reduce-scatter of the partial sums (each rank
-    receives the total of its slab of (iy, ix) columns), all-reduce of the 0.65 MB column counts, every
-    rank finalises ITS slab only, all-gather of iq - all four on the launch stream, no host
-    synchronisation in between (the reduce-scatter variant).  Otherwise (gloo, external
-    accumulators): all-reduce of the whole grids, then the whole finalise on every rank."""
+    One rank: just the finalise kernel.  N ranks on GPUs, both variants through the library's own NCCL
+    communicator on the launch stream with no host synchronisation in between:
+      allreduce (default): all-reduce of sums and counts, whole finalise on every rank;
+      scatter (SURVEY 8(e) alternative): reduce-scatter of the sums (each rank receives the total of its
+        slab of (iy, ix) columns), all-reduce of the 0.65 MB counts, every rank finalises ITS slab only,
+        all-gather of iq.
+    Otherwise (gloo, CPU tensors): torch.distributed all-reduce, then the whole finalise."""
     from . import engine
     from ._lib import call, ptr
     rank, world = rank_world()
     c = comm(device) if (world > 1 and group is None) else None
     store = getattr(eng, "vsum_store", None)
+    if c is not None and COMBINE != "scatter" and eng.count2 is not None:
+        # all-reduce of the partial sums and counts on the launch stream, then the whole (streaming, ~0.1 ms)
+        # finalise on every rank: measured faster on NVSwitch than reduce-scatter + all-gather, whose two
+        # collectives each move (N-1)/N of the grid per rank (profiles/r04_summary.md)
+        with torch.cuda.device(device):
+            st = engine._stream()
+            call("gx_comm_all_reduce", c, ptr(eng.vsum), int(eng.vsum.numel()), GX_DTYPE_F32, st)
+            call("gx_comm_all_reduce", c, ptr(eng.count2), int(eng.count2.numel()), GX_DTYPE_U32, st)
+        return engine.finalize_voxels(eng.vsum, None, eng.count2, eng.row_hist, q_axis, max_q, device,
+                                      window=window, crop=crop, f0=f0)
     if c is not None and store is not None and eng.count2 is not None and window is not None and crop:
         V = eng.q_out
         cpr, padded = padded_columns(V, world)
@@ -127,8 +142,8 @@ def combine_and_finalize(eng, q_axis, max_q, device, window=None, crop=True, f0=
 
 
 SHARDED_UPLOAD_MIN_BYTES = 8 << 20
-STAGED_UPLOAD_MIN_BYTES = 32 << 20
-STAGED_UPLOAD_CHUNK = 32 << 20
+STAGED_UPLOAD_MIN_BYTES = 8 << 20
+STAGED_UPLOAD_CHUNK = 8 << 20         # small enough that a rank's 30 MB slice of the atom table still pipelines
 
 
 def _upload_staged(flat, device, out=None):
@@ -225,6 +240,9 @@ def _segment_free(seg):
 
 def _close_segment(seg):
     try:
+        if seg.get("pinned"):
+            from ._lib import call
+            call("gx_host_unregister", seg["pinned"][0])
         seg["w"].close()
         _os.close(seg["fd"])
     except (OSError, ValueError, BufferError):
@@ -260,6 +278,25 @@ def _new_segment(nbytes, rank, device, group):
         _os.unlink(name)
     w = _mmap.mmap(fd, nbytes, flags=_mmap.MAP_SHARED, prot=_mmap.PROT_READ | _mmap.PROT_WRITE)
     return {"nbytes": nbytes, "fd": fd, "w": w, "live": None}
+
+
+def _register_slab(seg, lo, hi):
+    """Page-lock elements [lo, hi) of the segment's shared mapping (once per segment; pooled segments are
+    reused).  False when registration is not possible - the caller then converts on the host."""
+    if seg.get("pinned") is not None:
+        return seg["pinned"][1:] == (lo, hi)
+    if seg.get("pin_failed"):
+        return False
+    import ctypes
+    from ._lib import GxError, call
+    base = ctypes.addressof(ctypes.c_char.from_buffer(seg["w"]))
+    try:
+        call("gx_host_register", ctypes.c_void_p(base + lo * 8), (hi - lo) * 8)
+    except GxError:
+        seg["pin_failed"] = True
+        return False
+    seg["pinned"] = (base + lo * 8, lo, hi)
+    return True
 
 
 def shared_result_f64(t, to_host_slice, group=None, min_bytes=16 << 20):
@@ -315,9 +352,20 @@ def shared_result_f64(t, to_host_slice, group=None, min_bytes=16 << 20):
     per = (n + world - 1) // world
     lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
     if hi > lo:
-        out = np.frombuffer(seg["w"], dtype=np.float64)
-        to_host_slice(flat[lo:hi], out[lo:hi])
-        del out
+        if t.is_cuda and _register_slab(seg, lo, hi):
+            # the slab is widened on the device and DMA'd straight into its place in the (page-locked)
+            # segment: no host-side copy or conversion, which 8 ranks would do on the same cores
+            import ctypes
+            from . import engine
+            from ._lib import call, ptr
+            wide = flat[lo:hi].to(torch.float64)
+            with torch.cuda.device(t.device):
+                call("gx_copy_to_host_async", ctypes.c_void_p(seg["pinned"][0]), ptr(wide), (hi - lo) * 8, engine._stream())
+                torch.cuda.current_stream().synchronize()
+        else:
+            out = np.frombuffer(seg["w"], dtype=np.float64)
+            to_host_slice(flat[lo:hi], out[lo:hi])
+            del out
     dist.barrier(group=group)                                      # every slab is written
     m = _mmap.mmap(seg["fd"], nbytes, flags=_mmap.MAP_PRIVATE, prot=_mmap.PROT_READ | _mmap.PROT_WRITE)
     base = np.frombuffer(m, dtype=np.float64)

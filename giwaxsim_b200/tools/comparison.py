@@ -26,6 +26,9 @@ from .utilities import ATOMIC_NUMBER, calc_real_space_abc, get_element_f1_f2_dic
 # the host array, comparison.py:790).
 _resident = {"host": None, "device": None, "sum": None}
 _TRACE = os.environ.get("GIWAXS_B200_TRACE", "0") == "1"
+# GIWAXS_B200_RESIDENT_CHECK=0: trust array identity alone when re-using the device copy of a returned array
+# (skips the whole-array content checksums; only for callers that never edit returned arrays in place)
+_CHECK_RESIDENT = os.environ.get("GIWAXS_B200_RESIDENT_CHECK", "1") != "0"
 
 
 class _Trace:
@@ -117,7 +120,8 @@ def _resident_slab(coords, elements, dev):
         return None
     if _slab["d_coords"].device != dev:
         return None
-    if _slab["sums"][1] is None or (engine.host_checksum(coords), _elements_checksum(elements)) != _slab["sums"]:
+    if _CHECK_RESIDENT and (_slab["sums"][1] is None or
+                            (engine.host_checksum(coords), _elements_checksum(elements)) != _slab["sums"]):
         return None                                    # edited in place since slabmaker_fitting returned them
     if len(_slab["uniq"]) > engine._lib.GX_MAX_SPECIES:
         return None
@@ -261,6 +265,11 @@ class _ContentCheck:
         return bool(self.ok)
 
 
+class _Trusted:
+    def result(self):
+        return True
+
+
 def detectormaker_fitting(iq, qx, qy, qz, num_pixels, max_q, angle_init_vals, angle_init_axs, psis,
                           psi_weights_path, phis, phi_weights_path, thetas, theta_weights_path, mirror=True):
     """2-D detector image summed over psi x phi x theta orientations.
@@ -288,7 +297,7 @@ def detectormaker_fitting(iq, qx, qy, qz, num_pixels, max_q, angle_init_vals, an
     check = None
     if (iq is _resident["host"] and _resident["device"] is not None and _resident["device"].device == dev
             and _resident["sum"] is not None):
-        check = _ContentCheck(iq, _resident["sum"])
+        check = _ContentCheck(iq, _resident["sum"]) if _CHECK_RESIDENT else _Trusted()
     rank, world = parallel.rank_world()
     R = w = None
     for grid in ((_resident["device"], iq) if check is not None else (iq,)):

@@ -347,6 +347,15 @@ int gx_gather_columns(const double *d_src, int rows, int src_cols, const int32_t
 int gx_masked_fit_sums(const double *d_x, const double *d_y, const double *d_mask, int64_t n,
                        double *d_out5, void *stream);
 
+/* ----------------------------------------------------------- host boundary */
+/* Results are returned as float64 host arrays (the reference's types).  With N ranks on a
+ * node the array lives in a pooled shared-memory segment mapped by every rank; each rank
+ * page-locks ITS slab once (gx_host_register) and from then on DMAs the widened slab
+ * straight into place (gx_copy_to_host_async) - no host-side copy or conversion.        */
+int gx_host_register(void *h_ptr, int64_t nbytes);
+int gx_host_unregister(void *h_ptr);
+int gx_copy_to_host_async(void *h_dst, const void *d_src, int64_t nbytes, void *stream);
+
 /* ----------------------------------------------------- multi-GPU exchange */
 /* One process per GPU; the partial voxel sums / counts of stage A and the
  * partial detector images of stage B meet in a sum (the reference's shared
