@@ -299,7 +299,52 @@ def _register_slab(seg, lo, hi):
     return True
 
 
-def shared_result_f64(t, to_host_slice, group=None, min_bytes=16 << 20):
+_cow = {}             # id(base array) -> (weakref to it, address, nbytes) of results handed out as private mappings
+
+
+def _pagemap_unmodified(addr, nbytes):
+    """True when no page of [addr, addr + nbytes) of a MAP_PRIVATE file mapping has been written through the
+    mapping: the kernel copies a page on the first write, and /proc/self/pagemap then reports it as an
+    anonymous page (bit 61 clear) instead of a file page.  None when pagemap cannot be read."""
+    page = _mmap.PAGESIZE
+    first = addr // page
+    count = (addr + nbytes + page - 1) // page - first
+    try:
+        fd = _os.open("/proc/self/pagemap", _os.O_RDONLY)
+        try:
+            raw = _os.pread(fd, count * 8, first * 8)
+        finally:
+            _os.close(fd)
+    except OSError:
+        return None
+    if len(raw) != count * 8:
+        return None
+    e = np.frombuffer(raw, dtype=np.uint64)
+    present = (e >> np.uint64(63)) & np.uint64(1)
+    swapped = (e >> np.uint64(62)) & np.uint64(1)
+    file_page = (e >> np.uint64(61)) & np.uint64(1)
+    return not bool((((present == 1) & (file_page == 0)) | (swapped == 1)).any())
+
+
+def result_unmodified(array):
+    """For an array handed out by shared_result_f64: True / False = the caller has not / has written to it
+    (tracked by the kernel's copy-on-write, about a millisecond for 0.5 GB instead of re-reading the array);
+    None = not such an array, or not decidable here - the caller falls back to a content checksum."""
+    hit = _cow.get(id(array))
+    if hit is None or hit[0]() is not array:
+        return None
+    if not array.flags.c_contiguous or array.ctypes.data != hit[1]:
+        return None
+    return _pagemap_unmodified(hit[1], hit[2])
+
+
+def _remember_cow(base, shaped):
+    for k in [k for k, v in _cow.items() if v[0]() is None]:
+        del _cow[k]
+    _cow[id(shaped)] = (_weakref.ref(shaped), base.ctypes.data, base.nbytes)
+
+
+def shared_result_f64(t, to_host_slice, group=None, min_bytes=16 << 20, single=False):
     """float64 NumPy copy of tensor `t`, which every rank holds identically after an all-reduce.
     One process per GPU on one node would otherwise pay the device->host copy and the fp32->fp64
     widening of the whole grid once PER RANK on the same host cores and memory bus.  Here rank r
@@ -309,42 +354,49 @@ def shared_result_f64(t, to_host_slice, group=None, min_bytes=16 << 20):
     pages), but the bytes are produced once per node.  Segments come from a small pool and are reused
     only when EVERY rank's previous array on that segment has been garbage collected (first touch of
     fresh tmpfs pages costs more than the conversion itself).  Returns None - the caller converts on
-    its own - for a single rank, small tensors, ranks spread over several nodes, a /dev/shm that is too
-    small, or when all pool segments are still referenced."""
-    if not (dist.is_available() and dist.is_initialized()):
+    its own - for small tensors, ranks spread over several nodes, a /dev/shm that is too small, or
+    when all pool segments are still referenced.
+    single=True: also with ONE rank (no process group needed): the result is then a private mapping
+    whose modification by the caller the kernel tracks (result_unmodified)."""
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if not multi and not single:
         return None
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    world, rank = (dist.get_world_size(group), dist.get_rank(group)) if multi else (1, 0)
     n = t.numel()
     nbytes = n * 8
-    if world == 1 or nbytes < min_bytes or not _all_local(group):
+    if nbytes < min_bytes or (multi and not _all_local(group)):
         return None
+
+    def agree(flags_list):
+        """element-wise AND over the ranks of a list of 0/1 flags"""
+        if not multi:
+            return flags_list
+        f = torch.tensor(flags_list, dtype=torch.int32, device=t.device)
+        dist.all_reduce(f, op=dist.ReduceOp.MIN, group=group)
+        return f.tolist()
+
     # agree on a segment of this size class: free on every rank (the pool evolves in lockstep on all
     # ranks, so positions match)
     segs = _pool.get(nbytes)
     if segs is None:
         if len(_pool) >= _POOL_CLASSES:
-            # drop a size class whose segments are all free everywhere (checked with the same all-reduce)
+            # drop a size class whose segments are all free everywhere
             keys = sorted(_pool)
-            idle = torch.tensor([1 if all(_segment_free(x) for x in _pool[k]) else 0 for k in keys],
-                                dtype=torch.int32, device=t.device)
-            dist.all_reduce(idle, op=dist.ReduceOp.MIN, group=group)
-            victims = [k for k, f in zip(keys, idle.tolist()) if f == 1]
+            idle = agree([1 if all(_segment_free(x) for x in _pool[k]) else 0 for k in keys])
+            victims = [k for k, f in zip(keys, idle) if f == 1]
             if not victims:
                 return None
             for x in _pool.pop(victims[0]):
                 _close_segment(x)
         segs = _pool[nbytes] = []
-    flags = torch.zeros(_POOL_MAX, dtype=torch.int32, device=t.device)
-    for i, x in enumerate(segs):
-        flags[i] = 1 if _segment_free(x) else 0
-    dist.all_reduce(flags, op=dist.ReduceOp.MIN, group=group)
+    flags = agree([1 if (i < len(segs) and _segment_free(segs[i])) else 0 for i in range(_POOL_MAX)])
     free = [i for i in range(len(segs)) if int(flags[i]) == 1]
     if free:
         seg = segs[free[0]]
     else:
         if len(segs) >= _POOL_MAX:
             return None
-        seg = _new_segment(nbytes, rank, t.device, group)
+        seg = _new_segment(nbytes, rank, t.device, group) if multi else _new_segment_local(nbytes)
         if seg is None:
             return None
         segs.append(seg)
@@ -352,7 +404,7 @@ def shared_result_f64(t, to_host_slice, group=None, min_bytes=16 << 20):
     per = (n + world - 1) // world
     lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
     if hi > lo:
-        if t.is_cuda and _register_slab(seg, lo, hi):
+        if multi and t.is_cuda and _register_slab(seg, lo, hi):
             # the slab is widened on the device and DMA'd straight into its place in the (page-locked)
             # segment: no host-side copy or conversion, which 8 ranks would do on the same cores
             import ctypes
@@ -366,8 +418,31 @@ def shared_result_f64(t, to_host_slice, group=None, min_bytes=16 << 20):
             out = np.frombuffer(seg["w"], dtype=np.float64)
             to_host_slice(flat[lo:hi], out[lo:hi])
             del out
-    dist.barrier(group=group)                                      # every slab is written
-    m = _mmap.mmap(seg["fd"], nbytes, flags=_mmap.MAP_PRIVATE, prot=_mmap.PROT_READ | _mmap.PROT_WRITE)
+    if multi:
+        dist.barrier(group=group)                                  # every slab is written
+    # MAP_POPULATE: the page tables are filled here (read-only, still copy-on-write), not by ~1e5 minor
+    # faults during the caller's first pass over the array
+    m = _mmap.mmap(seg["fd"], nbytes, flags=_mmap.MAP_PRIVATE | getattr(_mmap, "MAP_POPULATE", 0),
+                   prot=_mmap.PROT_READ | _mmap.PROT_WRITE)
     base = np.frombuffer(m, dtype=np.float64)
     seg["live"] = _weakref.ref(base)                               # views of the result keep `base` alive
-    return base.reshape(tuple(t.shape))
+    shaped = base.reshape(tuple(t.shape))
+    _remember_cow(base, shaped)
+    return shaped
+
+
+def _new_segment_local(nbytes):
+    """Single-rank flavour of _new_segment: an anonymous memory file (memfd), or an unlinked /dev/shm file."""
+    try:
+        if hasattr(_os, "memfd_create"):
+            fd = _os.memfd_create("giwaxs_b200_result")
+        else:
+            _pool_serial[0] += 1
+            name = "/dev/shm/giwaxs_b200_%d_%d" % (_os.getpid(), _pool_serial[0])
+            fd = _os.open(name, _os.O_CREAT | _os.O_TRUNC | _os.O_RDWR, 0o600)
+            _os.unlink(name)
+        _os.ftruncate(fd, nbytes)
+        w = _mmap.mmap(fd, nbytes, flags=_mmap.MAP_SHARED, prot=_mmap.PROT_READ | _mmap.PROT_WRITE)
+    except OSError:
+        return None
+    return {"nbytes": nbytes, "fd": fd, "w": w, "live": None}

@@ -247,15 +247,18 @@ def _detector_base_device(num_pixels, max_q, angle_init_vals, angle_init_axs, de
 
 
 class _ContentCheck:
-    """Whole-array checksum of a host array on a worker thread (the sum releases the GIL), so that the
-    verification of a resident device copy overlaps the GPU work that speculatively uses it."""
+    """Has the caller's host array still the content it was handed out with?  Decided on a worker thread so
+    that it overlaps the GPU work that speculatively uses the resident device copy: first by the kernel's
+    copy-on-write tracking of the result mapping (parallel.result_unmodified: ~3 ms for 0.5 GB, touches no
+    data), else by a whole-array checksum (the sum releases the GIL)."""
 
     def __init__(self, array, expected):
         import threading
         self.ok = None
 
         def work():
-            self.ok = engine.host_checksum(array) == expected
+            tracked = parallel.result_unmodified(array)
+            self.ok = tracked if tracked is not None else engine.host_checksum(array) == expected
 
         self.thread = threading.Thread(target=work, daemon=True)
         self.thread.start()
@@ -318,9 +321,8 @@ def detectormaker_fitting(iq, qx, qy, qz, num_pixels, max_q, angle_init_vals, an
         out = engine.detector_epilogue(image, num_pixels, num_pixels, mirror, dev, finish=True)
         tr.lap("all-reduce + epilogue")
         with torch.cuda.device(dev):
-            # the image was summed in fp64 on the device; fp32 carries it across PCIe at half the bytes
-            # (2^-24 relative, far inside the 1e-4 bar) and is widened into the float64 array the caller gets
-            res = engine.to_host_f64(out.to(torch.float32), replicated=world > 1)
+            # the fp64 image goes by one DMA into a pooled page-locked array (no host-side conversion)
+            res = engine.to_host_f64(out, replicated=world > 1)
         tr.lap("result to host")
         if check is None or grid is iq:
             break
