@@ -514,7 +514,9 @@ def roofline_block(cfg, eng, kernel_ms, n_slices_timed, N, peak, peak_src, clock
     kc = float(getattr(eng, "mean_kept_columns", 0.0)) or 1.12 * (eng.window[1] - eng.window[0])
     kr = eng.row_hi - eng.row_lo
     inter = 8.0 * rows_active * kc                       # kept-column intermediate, complex64
-    fused_bytes = {"rows": 17.0 * A / B + inter, "cols": inter + 8.0 * kr * kc}
+    # the TMA-fed column kernel reads every row slot of its boxes (also the zero rows outside the atom band)
+    inter_read = 8.0 * N * kc if N == 4096 else inter
+    fused_bytes = {"rows": 17.0 * A / B + inter, "cols": inter_read + 8.0 * kr * kc}
     metrics = {}
     try:
         metrics = json.load(open(os.path.join(ROOT, "profiles", "r04_kernel_metrics.json")))
@@ -524,7 +526,8 @@ def roofline_block(cfg, eng, kernel_ms, n_slices_timed, N, peak, peak_src, clock
     issue_peak = 4.0 * SM_COUNT * sm_mhz * 1e6            # warp instructions / s
     fp32_peak = 2.0 * 128 * SM_COUNT * sm_mhz * 1e6       # FLOP/s
     per = {}
-    for name, kern in (("rows", "slice_rows_fused"), ("cols", "slice_cols_fused")):
+    cols_kernel = "slice_cols_tma" if (N == 4096 and "slice_cols_tma" in metrics) else "slice_cols_fused"
+    for name, kern in (("rows", "slice_rows_fused"), ("cols", cols_kernel)):
         us = 1e3 * kernel_ms[name] / n_slices_timed
         ach = fused_bytes[name] / (us * 1e-6) / 1e9
         k = {"kernel": kern, "us_per_slice": us, "us_per_launch": us * B,
