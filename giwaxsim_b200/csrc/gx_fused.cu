@@ -1,11 +1,14 @@
 // Fused stage-A slice pipeline: the production path of voxelgridmaker_fitting.
 //
 //   F1  slice_rows_fused   one CTA per (rotation, z-row):
-//         atoms of the row -> species counters in shared memory (ATOMS.ADD) ->
-//         complex row (background, edge blend, pedestal removed) -> 1-D FFT along
-//         y in the same shared memory -> only the q-columns the voxel box keeps
-//         are written (N x Kc complex64 instead of N x N).
-//   F2  slice_cols_fused   one CTA per (rotation, TC kept columns):
+//         atoms of the row -> fixed-point integer accumulators in shared memory
+//         (ATOMS.ADD) -> complex row (background, edge blend, pedestal removed) ->
+//         1-D FFT along y in the same shared memory -> only the q-columns the voxel
+//         box keeps are written (N x Kc complex64 instead of N x N).
+//   F2  slice_cols_tma     N = 4096: persistent CTAs, column tiles streamed in by TMA
+//         (256-row x 4-column boxes through an mbarrier ring), split 16 x 256
+//         transform, only the kept outputs formed and binned at once;
+//       slice_cols_fused   other sizes: one CTA per (rotation, TC kept columns):
 //         column tile (rows of the atom band only; the rest is zero once the
 //         pedestal is removed) -> 1-D FFT along z -> |.|^2 of the kept q-rows ->
 //         fp32 RED.ADD straight into the 3-D voxel sum, u32 per-column count.

@@ -283,3 +283,43 @@ def test_to_host_f64_pipelined_chunks(monkeypatch):
         view = np.zeros((101, 67, 13))
         engine.to_host_f64(t, out=view)
         assert np.array_equal(view, out)
+
+
+def test_two_engines_on_two_streams_do_not_corrupt_each_other():
+    """gx_slices_fused stages per-rotation scalars through __constant__ tables that belong to one launch at a
+    time: launches of one device arriving on DIFFERENT streams are ordered through an event behind the row kernel
+    (round 1 only documented 'one stream per device').  Two engines with different atoms, interleaved batch by
+    batch on two streams, must give what each gives alone."""
+    dev = engine.resolve_device()
+    r, max_q = 0.25, 1.5
+    q = synth.pow2_q_voxel(r, 256)
+    jobs = []
+    for seed, box in ((4, (60.0, 35.0, 50.0)), (9, (40.0, 55.0, 45.0))):
+        coords, el = synth.random_slab(25_000, box, seed=seed)
+        codes, uniq, table = comparison.species_table(el, 12700.0)
+        atoms = engine.AtomSet(coords, r, 256, dev, species=codes, table=table)
+        N, q_num, q_axis, phis = engine.stage_a_geometry(atoms.bounds, r, q, max_q)
+        avg = np.sum(np.bincount(codes, minlength=len(table)) * np.asarray(table)) / np.prod(atoms.bounds) * r ** 3
+        make = lambda a=atoms, qa=q_axis, n=N, av=avg: engine.SliceEngine(None, r, qa, n, av, a.bounds[0], a.bounds[1],
+                                                                        True, 4, atoms=a)
+        jobs.append((make, phis[::3]))
+    alone = []
+    for make, phis in jobs:
+        e = make()
+        e.run(phis)
+        alone.append((e.counts(), e.sums().astype(np.float64)))
+    torch.cuda.synchronize()
+    engines = [make() for make, _ in jobs]
+    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    step = 7                                            # small batches: many interleaved launch pairs
+    n = max(len(p) for _, p in jobs)
+    for i0 in range(0, n, step):
+        for k, (e, (_, phis)) in enumerate(zip(engines, jobs)):
+            chunk = phis[i0:i0 + step]
+            if len(chunk):
+                with torch.cuda.stream(streams[k]):
+                    e.run(chunk)
+    torch.cuda.synchronize()
+    for e, (cnt, sums) in zip(engines, alone):
+        assert np.array_equal(e.counts(), cnt)
+        assert np.abs(e.sums() - sums).max() <= 1e-5 * sums.max()

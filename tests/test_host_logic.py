@@ -320,3 +320,40 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("BASELINE configs[4]") and d["gpu_launches"] == 0
+
+
+def test_result_mapping_tracks_in_place_edits():
+    """Large results are handed out as private copy-on-write mappings of a pooled memory file
+    (parallel.shared_result_f64(single=True)): reading leaves them 'unmodified', any write - also through a
+    view - is seen by the kernel's page tracking (parallel.result_unmodified), arrays the pool did not hand out
+    are 'unknown' (None), and a segment is recycled only when the previous array on it is gone."""
+    from giwaxsim_b200 import parallel
+    import gc
+
+    def widen(dev_slice, view):
+        view[:] = dev_slice.numpy().astype(np.float64)
+
+    t = torch.arange(300_000, dtype=torch.float32).reshape(50, 60, 100)
+    a = parallel.shared_result_f64(t, widen, min_bytes=0, single=True)
+    assert a.dtype == np.float64 and a.shape == (50, 60, 100) and a.flags.writeable
+    assert np.array_equal(a, t.numpy().astype(np.float64))
+    if parallel.result_unmodified(a) is None:
+        pytest.skip("/proc/self/pagemap not readable here")
+    assert parallel.result_unmodified(a) is True
+    assert float(a.sum()) == float(t.double().sum())                 # reading does not count
+    assert parallel.result_unmodified(a) is True
+    b = parallel.shared_result_f64(t * 2, widen, min_bytes=0, single=True)       # `a` alive -> another segment
+    assert len(parallel._pool[a.nbytes]) == 2 and a[1, 2, 3] == t[1, 2, 3].item()
+    a[49, 59, 99] += 1.0
+    assert parallel.result_unmodified(a) is False and parallel.result_unmodified(b) is True
+    view = b[10:12]
+    view[0, 0, 0] = -5.0                                                          # a write through a view
+    assert parallel.result_unmodified(b) is False
+    assert parallel.result_unmodified(np.zeros(4)) is None and parallel.result_unmodified(a[1:]) is None
+    del a, b, view
+    gc.collect()
+    import time
+    time.sleep(0.05)                                                              # (background populate threads)
+    c = parallel.shared_result_f64(t * 3, widen, min_bytes=0, single=True)       # a freed segment is reused ...
+    assert len(parallel._pool[c.nbytes]) == 2
+    assert parallel.result_unmodified(c) is True and c[2, 2, 2] == 3 * t[2, 2, 2].item()   # ... with no stale private pages
