@@ -121,6 +121,8 @@ _PROTOTYPES = {
     "gx_host_affine_orientations": (_i, [_p, _p, _i, _i, _p, _p, _i, _d, _d, _d, _d, _i, _i, _i, _p, _p]),
     "gx_detector_accumulate_affine": (_i, [_p, _i, _i, _i, _d, _d, _d, _d, _p, _p, _p, _i, _i, _p, _p, _p, _i,
                                            _p, _p, _i, _p, _p, _p]),
+    "gx_detector_accumulate_affine_brick": (_i, [_p, _p, _i, _i, _i, _i, _d, _d, _d, _d, _p, _p, _p, _i, _i, _p, _p, _p,
+                                                 _i, _p, _p, _p]),
     "gx_fast_record_bytes": (_i, []),
     "gx_host_fast_orientations": (_i, [_p, _p, _i, _d, _d, _d, _d, _p, _p]),
     "gx_host_orientation_matrices": (_i, [_p, _p, _i, _p]),
@@ -164,7 +166,7 @@ _LAUNCHES = {
     "gx_slice_vectors": 1, "gx_project_slices": 1, "gx_fft2_abs2_shift": 2, "gx_slice_col_index": 1,
     "gx_axis_col_index": 1, "gx_axis_row_index": 1, "gx_bin_slices": 1, "gx_row_histogram": 1,
     "gx_voxel_finalize": 1, "gx_voxel_shell_scale": 1, "gx_rotate_points": 1, "gx_detector_accumulate": 1, "gx_detector_epilogue": 1,
-    "gx_detector_accumulate_fast": 1, "gx_detector_accumulate_affine": 1, "gx_grid_affine_fit": 1,
+    "gx_detector_accumulate_fast": 1, "gx_detector_accumulate_affine": 1, "gx_detector_accumulate_affine_brick": 1, "gx_grid_affine_fit": 1,
     "gx_slices_fused": 2, "gx_species_histogram": 1, "gx_species_codes": 1, "gx_checksum64": 1, "gx_row_abs_f_max": 3, "gx_fold_dc": 1, "gx_polar_warp": 1, "gx_polar_unwarp": 1, "gx_gather_columns": 1, "gx_masked_fit_sums": 1, "gx_window_indices": 1, "gx_slab_minmax": 3, "gx_slab_count": 3, "gx_slab_write": 1, "gx_slice_col_range": 1, "gx_extreme_atoms": 1, "gx_hull_filter": 1,
 }
 _launch_count = 0

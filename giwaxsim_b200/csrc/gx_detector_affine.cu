@@ -33,6 +33,7 @@
 #include <math.h>
 #include <string.h>
 #include "gx_common.cuh"
+#include "gx_tma.cuh"
 
 #define GA_TW 32
 #define GA_TH 16
@@ -238,6 +239,170 @@ detector_affine_kernel(const __grid_constant__ AffLaunch L)
     }
     if (rmax2 <= L.rin2) aff_tile<false, PROBE>(L, s_rec, r0, c0, o_begin, o_end);
     else aff_tile<true, PROBE>(L, s_rec, r0, c0, o_begin, o_end);
+}
+
+// ------------------------------------------------ TMA-brick variant (A/B) ----
+// north_star's kernel (4) names "TMA-staged voxel tiles".  For a 32 x 16-pixel tile and one orientation the
+// pixels' voxel coordinates span at most 31 |u_a| + 15 |v_a| voxels along axis a (6.7 at config 5), so an
+// 8 x 8 x 8 brick of the voxel grid holds every voxel the tile can touch.  This variant streams those bricks
+// (cp.async.bulk.tensor.3d -> UTMALDG.3D, 2 KB each, mbarrier ring of GA_RING slots, thread 0 as producer) and
+// gathers from shared memory; pixels inside the error band still take the reference's fp64 chain and read
+// the grid itself, tiles that touch the box boundary run the clamped LDG path.  Measured against the LDG
+// kernel in profiles/r04_summary.md; selected with GIWAXS_B200_DETECTOR_TMA=1.
+#define GA_B 8
+#define GA_RING 8
+#define GA_BRICK (GA_B * GA_B * GA_B)
+
+struct AffBrick { int32_t bz, bx, by; uint32_t oc; };   // TMA coordinates of the brick and its flat origin
+
+__global__ void __launch_bounds__(GA_THREADS)
+detector_affine_brick_kernel(const __grid_constant__ AffLaunch L, const __grid_constant__ CUtensorMap map, uint32_t off)
+{
+    __shared__ __align__(16) AffSmem s_rec[GA_CHUNK];
+    __shared__ __align__(16) AffBrick s_brick[GA_CHUNK];
+    __shared__ __align__(128) float s_ring[GA_RING][GA_BRICK];
+    __shared__ __align__(8) uint64_t s_full[GA_RING], s_empty[GA_RING];
+    const int tiles_x = (L.cols + GA_TW - 1) / GA_TW;
+    const int tile = blockIdx.x;
+    const int r0 = (tile / tiles_x) * GA_TH, c0 = (tile % tiles_x) * GA_TW;
+    const int o_begin = blockIdx.y * L.per_split;
+    const int o_end = min(L.n_orient, o_begin + L.per_split);
+    double rmax2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double fr = (double)(r0 + ((k & 2) ? GA_TH - 1 : 0)), fc = (double)(c0 + ((k & 1) ? GA_TW - 1 : 0));
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double p = L.b_o[a] + fc * L.b_u[a] + fr * L.b_v[a];
+            s += p * p;
+        }
+        rmax2 = fmax(rmax2, s);
+    }
+    if (rmax2 > L.rin2) {                       // tile can leave the voxel box: clamped gather from the grid
+        aff_tile<true, false>(L, s_rec, r0, c0, o_begin, o_end);
+        return;
+    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < GA_RING; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, GA_THREADS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const int cx = 2 * ((warp & 1) * 8 + (lane & 7));
+    const int ry = 2 * ((warp >> 1) * 4 + (lane >> 3));
+    const int r = r0 + ry, c = c0 + cx;
+    const bool live0 = r < L.rows && c < L.cols, live1 = r < L.rows && c + 1 < L.cols;
+    const bool live2 = r + 1 < L.rows && c < L.cols, live3 = r + 1 < L.rows && c + 1 < L.cols;
+    const int64_t i0 = (int64_t)r * L.cols + c;
+    const int F = L.F;
+    const uint32_t HM = L.HM;
+    const float *iqs = L.iq_shifted;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+    unsigned g = 0;                              // running orientation number of this CTA: ring slot g % GA_RING
+
+    for (int o0 = o_begin; o0 < o_end; o0 += GA_CHUNK) {
+        const int nc = min(GA_CHUNK, o_end - o0);
+        __syncthreads();
+        if (tid < nc) {
+            const AffRecord *q = L.rec + (o0 + tid);
+            AffSmem e;
+            const double fr = (double)r0, fc = (double)c0;
+            const double t0 = __fma_rn(fr, q->v[0], __fma_rn(fc, q->u[0], q->o[0]));
+            const double t1 = __fma_rn(fr, q->v[1], __fma_rn(fc, q->u[1], q->o[1]));
+            const double t2 = __fma_rn(fr, q->v[2], __fma_rn(fc, q->u[2], q->o[2]));
+            e.tx = (uint32_t)__double2ll_rn(t0 * L.scale) + L.half;
+            e.ty = (uint32_t)__double2ll_rn(t1 * L.scale) + L.half;
+            e.tz = (uint32_t)__double2ll_rn(t2 * L.scale) + L.half;
+            e.w = q->w;
+            e.ux = q->U[0]; e.uy = q->U[1]; e.uz = q->U[2]; e.pad0 = 0;
+            e.vx = q->V[0]; e.vy = q->V[1]; e.vz = q->V[2]; e.pad1 = 0;
+            s_rec[tid] = e;
+            // lowest voxel index the tile's pixels can take along each axis: the coordinate is affine in
+            // (row, col), so its minimum sits at a corner of the tile
+            const uint32_t ex = (uint32_t)(GA_TW - 1) * (uint32_t)e.ux, fx = (uint32_t)(GA_TH - 1) * (uint32_t)e.vx;
+            const uint32_t ey = (uint32_t)(GA_TW - 1) * (uint32_t)e.uy, fy = (uint32_t)(GA_TH - 1) * (uint32_t)e.vy;
+            const uint32_t ez = (uint32_t)(GA_TW - 1) * (uint32_t)e.uz, fz = (uint32_t)(GA_TH - 1) * (uint32_t)e.vz;
+            const uint32_t mx = min(min(e.tx, e.tx + ex), min(e.tx + fx, e.tx + ex + fx)) >> F;
+            const uint32_t my = min(min(e.ty, e.ty + ey), min(e.ty + fy, e.ty + ey + fy)) >> F;
+            const uint32_t mz = min(min(e.tz, e.tz + ez), min(e.tz + fz, e.tz + ez + fz)) >> F;
+            AffBrick b;
+            b.bx = (int32_t)(mx - off); b.by = (int32_t)(my - off); b.bz = (int32_t)(mz - off);
+            b.oc = (my * GA_B + mx) * GA_B + mz;
+            s_brick[tid] = b;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // every slot is free here (all warps finished the previous chunk): start the ring
+            for (int o = 0; o < min(GA_RING - 1, nc); ++o) {
+                const unsigned gi = g + o, slot = gi % GA_RING;
+                mbar_wait(s_empty + slot, ((gi / GA_RING) & 1) ^ 1);
+                mbar_expect_tx(s_full + slot, GA_BRICK * 4);
+                tma_load_3d(s_ring[slot], &map, s_brick[o].bz, s_brick[o].bx, s_brick[o].by, s_full + slot);
+            }
+        }
+#pragma unroll 1
+        for (int o = 0; o < nc; ++o, ++g) {
+            if (tid == 0 && o + GA_RING - 1 < nc) {
+                const unsigned gi = g + GA_RING - 1, slot = gi % GA_RING;
+                mbar_wait(s_empty + slot, ((gi / GA_RING) & 1) ^ 1);
+                mbar_expect_tx(s_full + slot, GA_BRICK * 4);
+                const AffBrick b = s_brick[o + GA_RING - 1];
+                tma_load_3d(s_ring[slot], &map, b.bz, b.bx, b.by, s_full + slot);
+            }
+            const uint4 A = *reinterpret_cast<const uint4 *>(&s_rec[o].tx);
+            const uint4 B = *reinterpret_cast<const uint4 *>(&s_rec[o].ux);
+            const uint4 C = *reinterpret_cast<const uint4 *>(&s_rec[o].vx);
+            const uint32_t oc = s_brick[o].oc;
+            const float w = __uint_as_float(A.w);
+            const uint32_t x0 = A.x + (uint32_t)cx * B.x + (uint32_t)ry * C.x;
+            const uint32_t y0 = A.y + (uint32_t)cx * B.y + (uint32_t)ry * C.y;
+            const uint32_t z0 = A.z + (uint32_t)cx * B.z + (uint32_t)ry * C.z;
+            const uint32_t x1 = x0 + B.x, y1 = y0 + B.y, z1 = z0 + B.z;
+            const uint32_t x2 = x0 + C.x, y2 = y0 + C.y, z2 = z0 + C.z;
+            const uint32_t x3 = x2 + B.x, y3 = y2 + B.y, z3 = z2 + B.z;
+#define GA_LOCAL(X, Y, Z) ((((Y) >> F) * GA_B + ((X) >> F)) * GA_B + ((Z) >> F) - oc)
+            const uint32_t l0 = GA_LOCAL(x0, y0, z0), l1 = GA_LOCAL(x1, y1, z1);
+            const uint32_t l2 = GA_LOCAL(x2, y2, z2), l3 = GA_LOCAL(x3, y3, z3);
+#undef GA_LOCAL
+            const uint32_t m0 = umin3(x0 & HM, y0 & HM, z0 & HM);
+            const uint32_t m1 = umin3(x1 & HM, y1 & HM, z1 & HM);
+            const uint32_t m2 = umin3(x2 & HM, y2 & HM, z2 & HM);
+            const uint32_t m3 = umin3(x3 & HM, y3 & HM, z3 & HM);
+            const unsigned slot = g % GA_RING;
+            mbar_wait(s_full + slot, (g / GA_RING) & 1);
+            const float *brick = s_ring[slot];
+            // (a pixel of a partial tile lies outside the image: its brick index is clamped, its value unused)
+            float v0 = brick[min(l0, (uint32_t)GA_BRICK - 1)], v1 = brick[min(l1, (uint32_t)GA_BRICK - 1)];
+            float v2 = brick[min(l2, (uint32_t)GA_BRICK - 1)], v3 = brick[min(l3, (uint32_t)GA_BRICK - 1)];
+            if (min(min(m0, m1), min(m2, m3)) == 0u) {
+                // within the error bound of a voxel edge: the reference's own arithmetic decides, from the grid
+                if (m0 == 0u && live0) v0 = __ldg(iqs + aff_exact_voxel(L, i0, o0 + o));
+                if (m1 == 0u && live1) v1 = __ldg(iqs + aff_exact_voxel(L, i0 + 1, o0 + o));
+                if (m2 == 0u && live2) v2 = __ldg(iqs + aff_exact_voxel(L, i0 + L.cols, o0 + o));
+                if (m3 == 0u && live3) v3 = __ldg(iqs + aff_exact_voxel(L, i0 + L.cols + 1, o0 + o));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty + slot);
+            a0 = fmaf(w, v0, a0);
+            a1 = fmaf(w, v1, a1);
+            a2 = fmaf(w, v2, a2);
+            a3 = fmaf(w, v3, a3);
+        }
+        d0 += (double)a0; d1 += (double)a1; d2 += (double)a2; d3 += (double)a3;
+        a0 = a1 = a2 = a3 = 0.f;
+    }
+    if (L.n_split == 1) {
+        if (live0) L.image[i0] += d0;
+        if (live1) L.image[i0 + 1] += d1;
+        if (live2) L.image[i0 + L.cols] += d2;
+        if (live3) L.image[i0 + L.cols + 1] += d3;
+    } else {
+        if (live0) atomicAdd(L.image + i0, d0);
+        if (live1) atomicAdd(L.image + i0 + 1, d1);
+        if (live2) atomicAdd(L.image + i0 + L.cols, d2);
+        if (live3) atomicAdd(L.image + i0 + L.cols + 1, d3);
+    }
 }
 
 // --------------------------------------------------------- affine fit ----
@@ -504,12 +669,13 @@ extern "C" int gx_host_affine_orientations(const double *h_corners9, const doubl
     return GX_OK;
 }
 
-extern "C" int gx_detector_accumulate_affine(const float *d_iq, int Vy, int Vx, int Vz, double qx_min,
-                                             double qy_min, double qz_min, double dq, const double *d_px,
-                                             const double *d_py, const double *d_pz, int rows, int cols,
-                                             const double *h_corners9, const void *d_records, const double *d_R,
-                                             int n_orient, const double *h_plan, double *d_image, int probe,
-                                             int64_t *d_index_out, unsigned long long *d_slow_count, void *stream)
+static int affine_launch(const float *d_iq, int Vy, int Vx, int Vz, double qx_min,
+                         double qy_min, double qz_min, double dq, const double *d_px,
+                         const double *d_py, const double *d_pz, int rows, int cols,
+                         const double *h_corners9, const void *d_records, const double *d_R,
+                         int n_orient, const double *h_plan, double *d_image, int probe,
+                         int64_t *d_index_out, unsigned long long *d_slow_count, void *stream,
+                         const float *d_iq_padded, int Vz_padded)
 {
     GX_REQUIRE(d_iq && d_px && d_py && d_pz && h_corners9 && d_records && d_R && h_plan && d_image, "NULL pointer");
     GX_REQUIRE(Vy > 0 && Vx > 0 && Vz > 0 && dq > 0.0, "bad voxel grid");
@@ -554,9 +720,57 @@ extern "C" int gx_detector_accumulate_affine(const float *d_iq, int Vy, int Vx, 
     L.per_split = per;
     L.n_split = n_split;
     dim3 grid((unsigned)tiles, (unsigned)n_split);
+    if (d_iq_padded) {
+        // TMA-brick variant: 3-D tensor map of the grid padded to a 16-byte row pitch, box 8 x 8 x 8
+        GX_REQUIRE(Vz_padded >= Vz && Vz_padded % 4 == 0 && !(d_index_out && probe >= 0) && !d_slow_count,
+                   "brick variant: padded pitch must be a multiple of 4 floats; no probe / slow count");
+        gx_encode_tiled_fn encode = gx_tensor_map_encoder();
+        if (!encode) return GX_ERR_UNSUPPORTED;
+        CUtensorMap map;
+        const cuuint64_t dims[3] = {(cuuint64_t)Vz, (cuuint64_t)Vx, (cuuint64_t)Vy};
+        const cuuint64_t strides[2] = {(cuuint64_t)Vz_padded * 4, (cuuint64_t)Vz_padded * 4 * (cuuint64_t)Vx};
+        const cuuint32_t box[3] = {GA_B, GA_B, GA_B};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(d_iq_padded), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            gx_set_error("gx_detector_accumulate_affine_brick: cuTensorMapEncodeTiled failed (%d)", (int)r);
+            return GX_ERR_CUDA;
+        }
+        detector_affine_brick_kernel<<<grid, GA_THREADS, 0, gx_stream(stream)>>>(L, map, off);
+        return gx_check_launch("gx_detector_accumulate_affine_brick");
+    }
     if (d_index_out && probe >= 0)
         detector_affine_kernel<true><<<grid, GA_THREADS, 0, gx_stream(stream)>>>(L);
     else
         detector_affine_kernel<false><<<grid, GA_THREADS, 0, gx_stream(stream)>>>(L);
     return gx_check_launch("gx_detector_accumulate_affine");
+}
+
+extern "C" int gx_detector_accumulate_affine(const float *d_iq, int Vy, int Vx, int Vz, double qx_min,
+                                             double qy_min, double qz_min, double dq, const double *d_px,
+                                             const double *d_py, const double *d_pz, int rows, int cols,
+                                             const double *h_corners9, const void *d_records, const double *d_R,
+                                             int n_orient, const double *h_plan, double *d_image, int probe,
+                                             int64_t *d_index_out, unsigned long long *d_slow_count, void *stream)
+{
+    return affine_launch(d_iq, Vy, Vx, Vz, qx_min, qy_min, qz_min, dq, d_px, d_py, d_pz, rows, cols, h_corners9,
+                         d_records, d_R, n_orient, h_plan, d_image, probe, d_index_out, d_slow_count, stream, NULL, 0);
+}
+
+// Same result through the TMA-brick variant of the gather (see detector_affine_brick_kernel): d_iq_padded is a
+// copy of the grid with rows of Vz_padded floats (a multiple of 4: tensor-map strides are multiples of 16
+// bytes).  The caller must have checked that every tile's voxel span fits the 8 x 8 x 8 brick:
+// (31 |U_a| + 15 |V_a|) / 2^F < 7 for every orientation record and axis.
+extern "C" int gx_detector_accumulate_affine_brick(const float *d_iq, const float *d_iq_padded, int Vz_padded, int Vy,
+                                                   int Vx, int Vz, double qx_min, double qy_min, double qz_min, double dq,
+                                                   const double *d_px, const double *d_py, const double *d_pz, int rows,
+                                                   int cols, const double *h_corners9, const void *d_records,
+                                                   const double *d_R, int n_orient, const double *h_plan, double *d_image,
+                                                   void *stream)
+{
+    GX_REQUIRE(d_iq_padded != NULL, "padded grid missing");
+    return affine_launch(d_iq, Vy, Vx, Vz, qx_min, qy_min, qz_min, dq, d_px, d_py, d_pz, rows, cols, h_corners9,
+                         d_records, d_R, n_orient, h_plan, d_image, -1, NULL, NULL, stream, d_iq_padded, Vz_padded);
 }

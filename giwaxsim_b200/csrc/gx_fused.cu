@@ -27,6 +27,7 @@
 #include <cuda.h>
 #include "gx_project.cuh"
 #include "gx_fft_engine.cuh"
+#include "gx_tma.cuh"
 
 #ifndef GX_F2_TC12
 #define GX_F2_TC12 4        // columns per F2 CTA at N = 4096 (2 -> 3 CTAs/SM was measured: 1 % slower)
@@ -516,39 +517,6 @@ slice_cols_fused(FusedArgs fa)
 #define F2T_BS 4372                     // float2 per column buffer: >= 4369 and == 4 (mod 16)
 #define F2T_SMEM (F2T_RING * F2T_BOX_BYTES + F2T_TC * F2T_BS * 8 + 2 * F2T_RING * 8)
 
-__device__ __forceinline__ uint32_t gx_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gx_smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gx_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gx_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(gx_smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(gx_smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(gx_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void named_barrier(int id, int count)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-
 __global__ void __launch_bounds__(F2T_THREADS, 1)
 slice_cols_tma(FusedArgs fa, const __grid_constant__ CUtensorMap tmap)
 {
@@ -701,24 +669,11 @@ extern "C" int gx_slice_col_range(const int32_t *d_col, int n_phi, int N, int32_
 }
 
 // ---------------------------------------------------------------- launch ----
-typedef CUresult (*gx_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                       const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 // 2-D tensor map of the [rows, KC] complex64 work buffer, box = 256 rows x 4 columns (one ring slot)
 static int work_tensor_map(CUtensorMap *map, void *work, size_t rows, int KC)
 {
-    static gx_encode_tiled_fn encode = nullptr;
-    if (!encode) {
-        void *fn = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        GX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
-        if (!fn || q != cudaDriverEntryPointSuccess) {
-            gx_set_error("gx_slices_fused: cuTensorMapEncodeTiled not available from this driver");
-            return GX_ERR_UNSUPPORTED;
-        }
-        encode = reinterpret_cast<gx_encode_tiled_fn>(fn);
-    }
+    gx_encode_tiled_fn encode = gx_tensor_map_encoder();
+    if (!encode) return GX_ERR_UNSUPPORTED;
     const cuuint64_t dims[2] = {(cuuint64_t)KC, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)KC * 8};
     const cuuint32_t box[2] = {F2T_TC, F2T_ROWS};

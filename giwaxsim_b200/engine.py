@@ -31,6 +31,9 @@ USE_ALL_ATOMS_FOR_RANGE = os.environ.get("GIWAXS_B200_FULL_RANGE", "0") == "1"
 # GIWAXS_B200_EXACT_DETECTOR=1 runs the all-fp64 detector kernel instead of the
 # fp32-filtered one (both give identical voxel indices).
 EXACT_DETECTOR_ONLY = os.environ.get("GIWAXS_B200_EXACT_DETECTOR", "0") == "1"
+# GIWAXS_B200_DETECTOR_TMA=1 feeds the affine detector gather with TMA-staged 8^3 voxel bricks instead of
+# L1-cached loads (A/B variant of the same kernel; identical result, measured slower - DESIGN.md 4.4).
+DETECTOR_TMA = os.environ.get("GIWAXS_B200_DETECTOR_TMA", "0") == "1"
 
 _checked_devices = set()
 
@@ -1049,6 +1052,24 @@ class DetectorEngine:
     def affine_plan_host(self, corners, dev3, rows, cols, R, w):
         return affine_plan_host(self.shape, self.mins, self.dq, corners, dev3, rows, cols, R, w)
 
+    def padded_grid(self):
+        """Copy of the voxel grid with rows padded to a multiple of 4 floats (tensor-map strides are
+        multiples of 16 bytes), built once per engine for the TMA-brick variant of the gather."""
+        if getattr(self, "_padded", None) is None:
+            Vy, Vx, Vz = self.shape
+            pad = torch.zeros((Vy, Vx, (Vz + 3) // 4 * 4), dtype=torch.float32, device=self.device)
+            pad[:, :, :Vz] = self.iq
+            self._padded = pad
+        return self._padded
+
+    @staticmethod
+    def _brick_fits(rec, plan):
+        """Every 32 x 16-pixel tile spans fewer than 7 voxels along every axis for every orientation record
+        (the 8^3 brick then holds every voxel the tile can touch)."""
+        r = np.frombuffer(rec, dtype=AFFINE_RECORD)
+        span = (AFFINE_TILE[1] - 1) * np.abs(r["U"].astype(np.float64)) + (AFFINE_TILE[0] - 1) * np.abs(r["V"].astype(np.float64))
+        return bool(span.max() / 2.0 ** float(plan[0]) < 7.0)
+
     def accumulate(self, det_x, det_y, det_z, R, w, image=None, probe=-1, exact_only=None, count_slow=False,
                    kernel=None):
         """image[P,P] (fp64, device) += sum_o w_o * iq[voxel(R_o p)].
@@ -1077,7 +1098,7 @@ class DetectorEngine:
             slow = torch.zeros(1, dtype=torch.int64, device=dev) if count_slow else None
             self.last_slow_fraction = None
 
-            if kernel in (None, "affine") and len(shape) == 2 and shape[0] > 1 and shape[1] > 1:
+            if kernel in (None, "affine", "affine_tma") and len(shape) == 2 and shape[0] > 1 and shape[1] > 1:
                 # The host model of a chunk of orientations is built while the GPU works on the
                 # previous chunk (launches are asynchronous): a short first chunk gets the device
                 # busy at once, later chunks are sized so that their host time stays hidden.
@@ -1091,9 +1112,9 @@ class DetectorEngine:
                     plan = self.affine_plan(px, py, pz, Rc, wc)
                     # edge-locked: a coordinate that is constant over the detector, sits on a voxel edge
                     # and could not be modelled -> every pixel would take the exact path anyway
-                    ok = plan is not None and (kernel == "affine" or plan[2][6] <= 0.5 * (b1 - b0))
+                    ok = plan is not None and (kernel in ("affine", "affine_tma") or plan[2][6] <= 0.5 * (b1 - b0))
                     if not ok:
-                        if kernel == "affine":
+                        if kernel in ("affine", "affine_tma"):
                             raise _lib.GxError(_lib.GX_ERR_UNSUPPORTED, "detector grid is not affine in (row, col)")
                         if not launched:
                             break                          # generic kernels below take the whole set
@@ -1106,6 +1127,14 @@ class DetectorEngine:
                     corners, rec, pl = plan
                     d_rec = _dev(rec, dev)
                     pr = probe - b0 if b0 <= probe < b1 else -1
+                    if (DETECTOR_TMA or kernel == "affine_tma") and pr < 0 and not count_slow and self._brick_fits(rec, pl):
+                        pad = self.padded_grid()
+                        call("gx_detector_accumulate_affine_brick", ptr(self.iq), ptr(pad), int(pad.shape[2]), Vy, Vx, Vz,
+                             self.mins[0], self.mins[1], self.mins[2], self.dq, ptr(px), ptr(py), ptr(pz), shape[0],
+                             shape[1], ptr(corners), ptr(d_rec), ptr(d_R[b0:b1]), b1 - b0, ptr(pl), ptr(image), _stream())
+                        launched = True
+                        self.last_kernel, self.last_plan = "affine_tma", pl
+                        continue
                     call("gx_detector_accumulate_affine", ptr(self.iq), Vy, Vx, Vz, self.mins[0], self.mins[1],
                          self.mins[2], self.dq, ptr(px), ptr(py), ptr(pz), shape[0], shape[1], ptr(corners),
                          ptr(d_rec), ptr(d_R[b0:b1]), b1 - b0, ptr(pl), ptr(image), int(pr),

@@ -347,6 +347,20 @@ int gx_gather_columns(const double *d_src, int rows, int src_cols, const int32_t
 int gx_masked_fit_sums(const double *d_x, const double *d_y, const double *d_mask, int64_t n,
                        double *d_out5, void *stream);
 
+/* The same accumulation as gx_detector_accumulate_affine with the gather fed by TMA: for every
+ * (32 x 16-pixel tile, orientation) the 8 x 8 x 8 brick of voxels the tile can touch is
+ * streamed into shared memory (cp.async.bulk.tensor.3d, mbarrier ring) and the pixels read
+ * it there.  d_iq_padded: copy of d_iq with rows of Vz_padded floats (multiple of 4: tensor
+ * map strides are multiples of 16 bytes).  Precondition (caller): (31 |U_a| + 15 |V_a|) / 2^F
+ * < 7 for every record and axis, so that a tile's voxel span fits the brick.  A/B variant of
+ * north_star's kernel (4); see DESIGN.md section 4.4 for the measured comparison.         */
+int gx_detector_accumulate_affine_brick(const float *d_iq, const float *d_iq_padded, int Vz_padded, int Vy,
+                                        int Vx, int Vz, double qx_min, double qy_min, double qz_min, double dq,
+                                        const double *d_px, const double *d_py, const double *d_pz, int rows,
+                                        int cols, const double *h_corners9, const void *d_records,
+                                        const double *d_R, int n_orient, const double *h_plan, double *d_image,
+                                        void *stream);
+
 /* ----------------------------------------------------------- host boundary */
 /* Results are returned as float64 host arrays (the reference's types).  With N ranks on a
  * node the array lives in a pooled shared-memory segment mapped by every rank; each rank

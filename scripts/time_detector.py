@@ -23,7 +23,7 @@ det = engine.DetectorEngine(iq, q, q, q)
 ref = None
 for k in kernels:
     img = torch.zeros(P * P, dtype=torch.float64, device=dev)
-    det.accumulate(gx, gy, gz, R, w, image=img, kernel=k, count_slow=(k != "exact"))
+    det.accumulate(gx, gy, gz, R, w, image=img, kernel=k, count_slow=(k in ("filtered", "affine")))
     slow = det.last_slow_fraction
     if ref is None:
         ref = img.clone()

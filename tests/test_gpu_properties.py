@@ -323,3 +323,25 @@ def test_two_engines_on_two_streams_do_not_corrupt_each_other():
     for e, (cnt, sums) in zip(engines, alone):
         assert np.array_equal(e.counts(), cnt)
         assert np.abs(e.sums() - sums).max() <= 1e-5 * sums.max()
+
+
+def test_tma_brick_detector_variant_is_identical_to_the_ldg_kernel():
+    """The TMA-brick variant of the affine detector gather (8^3 voxel bricks streamed by cp.async.bulk.tensor.3d
+    through an mbarrier ring; north_star kernel (4)) reads the same voxels in the same order as the L1-fed
+    kernel: images must be identical, also for a partial-tile size and orientations that make tiles touch the
+    box boundary (those tiles run the clamped path)."""
+    dev = engine.resolve_device()
+    rng = np.random.default_rng(3)
+    V = 121
+    iq = torch.from_numpy(rng.random((V, V, V)).astype(np.float32) * 1e5).to(dev)
+    q = np.linspace(-2.02, 2.02, V)
+    for P, max_q in ((300, 2.0), (517, 1.1)):
+        gx, gy, gz, _, _ = comparison.detector_base_device(P, max_q, (90.0, 90.0, 90.0), ("psi", "phi", "psi"), dev)
+        psis, phis, thetas = np.linspace(0, 89, 9), np.linspace(0, 170, 5), np.array([0.0, 3.0])
+        ones = lambda a: np.ones_like(a) / len(a)
+        R, w = engine.orientation_tables(engine.grid_corners(gx, gy, gz), psis, ones(psis), phis, ones(phis), thetas, ones(thetas))
+        det = engine.DetectorEngine(iq, q, q, q, device=dev)
+        a, _ = det.accumulate(gx, gy, gz, R, w, kernel="affine")
+        b, _ = det.accumulate(gx, gy, gz, R, w, kernel="affine_tma")
+        assert det.last_kernel == "affine_tma"
+        assert torch.equal(a, b)
