@@ -420,36 +420,17 @@ def shared_result_f64(t, to_host_slice, group=None, min_bytes=16 << 20, single=F
             del out
     if multi:
         dist.barrier(group=group)                                  # every slab is written
+    # The mapping is NOT pre-populated: the usual next step (detectormaker_fitting on the resident device copy)
+    # never touches the host array, and a caller that does read it takes ordinary minor faults (~10 ms for a
+    # first pass over 0.5 GB).  Measured alternatives: MADV_POPULATE_READ costs 13 ms of kernel time per call and
+    # its page tables another ~8 ms to tear down when the array is freed; MAP_POPULATE faults a private writable
+    # mapping with write intent, i.e. copies every page and makes the array look modified.
     m = _mmap.mmap(seg["fd"], nbytes, flags=_mmap.MAP_PRIVATE, prot=_mmap.PROT_READ | _mmap.PROT_WRITE)
     base = np.frombuffer(m, dtype=np.float64)
     seg["live"] = _weakref.ref(base)                               # views of the result keep `base` alive
     shaped = base.reshape(tuple(t.shape))
     _remember_cow(base, shaped)
-    _populate_in_background(base)
     return shaped
-
-
-def _populate_in_background(base):
-    """Fill the page tables of a fresh result mapping with READ faults (MADV_POPULATE_READ, Linux 5.14+) on a
-    worker thread: 13 ms of kernel work for 0.5 GB that would otherwise be ~1e5 minor faults in the caller's
-    first pass over the array - and that the usual next step (detectormaker_fitting on the resident device
-    copy) never needs at all.  Read faults keep the pages copy-on-write.  (MAP_POPULATE is not an option: on a
-    private writable mapping it faults with write intent, copies every page and makes the array look modified.)
-    The thread holds a reference to the array, so the mapping cannot go away under the call."""
-    import ctypes
-    import threading
-    try:
-        libc = ctypes.CDLL(None, use_errno=True)
-        madvise = libc.madvise
-    except (OSError, AttributeError):
-        return
-    madvise.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
-    madvise.restype = ctypes.c_int
-
-    def work(arr=base):
-        madvise(ctypes.c_void_p(arr.ctypes.data), arr.nbytes, 22)     # ctypes releases the GIL for the call
-
-    threading.Thread(target=work, daemon=True).start()
 
 
 def _new_segment_local(nbytes):

@@ -335,7 +335,7 @@ def test_tma_brick_detector_variant_is_identical_to_the_ldg_kernel():
     V = 121
     iq = torch.from_numpy(rng.random((V, V, V)).astype(np.float32) * 1e5).to(dev)
     q = np.linspace(-2.02, 2.02, V)
-    for P, max_q in ((300, 2.0), (517, 1.1)):
+    for P, max_q in ((900, 2.0), (517, 1.1)):      # fine enough pixels for a tile to span < 7 voxels
         gx, gy, gz, _, _ = comparison.detector_base_device(P, max_q, (90.0, 90.0, 90.0), ("psi", "phi", "psi"), dev)
         psis, phis, thetas = np.linspace(0, 89, 9), np.linspace(0, 170, 5), np.array([0.0, 3.0])
         ones = lambda a: np.ones_like(a) / len(a)

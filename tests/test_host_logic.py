@@ -352,8 +352,6 @@ def test_result_mapping_tracks_in_place_edits():
     assert parallel.result_unmodified(np.zeros(4)) is None and parallel.result_unmodified(a[1:]) is None
     del a, b, view
     gc.collect()
-    import time
-    time.sleep(0.05)                                                              # (background populate threads)
     c = parallel.shared_result_f64(t * 3, widen, min_bytes=0, single=True)       # a freed segment is reused ...
     assert len(parallel._pool[c.nbytes]) == 2
     assert parallel.result_unmodified(c) is True and c[2, 2, 2] == 3 * t[2, 2, 2].item()   # ... with no stale private pages
