@@ -244,14 +244,19 @@ detector_affine_kernel(const __grid_constant__ AffLaunch L)
 // ------------------------------------------------ TMA-brick variant (A/B) ----
 // north_star's kernel (4) names "TMA-staged voxel tiles".  For a 32 x 16-pixel tile and one orientation the
 // pixels' voxel coordinates span at most 31 |u_a| + 15 |v_a| voxels along axis a (6.7 at config 5), so an
-// 8 x 8 x 8 brick of the voxel grid holds every voxel the tile can touch.  This variant streams those bricks
-// (cp.async.bulk.tensor.3d -> UTMALDG.3D, 2 KB each, mbarrier ring of GA_RING slots, thread 0 as producer) and
-// gathers from shared memory; pixels inside the error band still take the reference's fp64 chain and read
-// the grid itself, tiles that touch the box boundary run the clamped LDG path.  Measured against the LDG
-// kernel in profiles/r04_summary.md; selected with GIWAXS_B200_DETECTOR_TMA=1.
+// 8 (y) x 8 (x) x 12 (z) brick of the voxel grid holds every voxel the tile can touch: the z origin is rounded
+// down to a multiple of 4 voxels because the innermost start coordinate of a tensor-map box must be 16-byte
+// aligned (an unaligned start raises "illegal instruction": found the hard way, tilted orientations only).
+// This variant streams those bricks (cp.async.bulk.tensor.3d -> UTMALDG.3D, 3 KB each, mbarrier ring of
+// GA_RING slots, thread 0 as producer) and gathers from shared memory; pixels inside the error band still take
+// the reference's fp64 chain and read the grid itself, tiles that touch the box boundary run the clamped LDG
+// path.  Result identical to the LDG kernel; measured 45 % SLOWER (1.91 vs 1.26 - 1.36 ms per 360 orientations at
+// config 5, profiles/r04_summary.md): the LDG gather lives on L1 hits and is bound by instruction issue, and
+// the ring adds waits and arrivals to exactly that resource.  Kept as an A/B switch: GIWAXS_B200_DETECTOR_TMA=1.
 #define GA_B 8
+#define GA_BZ 12                 // innermost (z) extent: the box starts at a multiple of 4 voxels (16 bytes)
 #define GA_RING 8
-#define GA_BRICK (GA_B * GA_B * GA_B)
+#define GA_BRICK (GA_B * GA_B * GA_BZ)
 
 struct AffBrick { int32_t bz, bx, by; uint32_t oc; };   // TMA coordinates of the brick and its flat origin
 
@@ -327,8 +332,9 @@ detector_affine_brick_kernel(const __grid_constant__ AffLaunch L, const __grid_c
             const uint32_t my = min(min(e.ty, e.ty + ey), min(e.ty + fy, e.ty + ey + fy)) >> F;
             const uint32_t mz = min(min(e.tz, e.tz + ez), min(e.tz + fz, e.tz + ez + fz)) >> F;
             AffBrick b;
-            b.bx = (int32_t)(mx - off); b.by = (int32_t)(my - off); b.bz = (int32_t)(mz - off);
-            b.oc = (my * GA_B + mx) * GA_B + mz;
+            const uint32_t mz4 = mz - ((mz - off) & 3u);       // z origin rounded down to 4 voxels past the grid start
+            b.bx = (int32_t)(mx - off); b.by = (int32_t)(my - off); b.bz = (int32_t)(mz4 - off);
+            b.oc = (my * GA_B + mx) * GA_BZ + mz4;
             s_brick[tid] = b;
         }
         __syncthreads();
@@ -361,7 +367,7 @@ detector_affine_brick_kernel(const __grid_constant__ AffLaunch L, const __grid_c
             const uint32_t x1 = x0 + B.x, y1 = y0 + B.y, z1 = z0 + B.z;
             const uint32_t x2 = x0 + C.x, y2 = y0 + C.y, z2 = z0 + C.z;
             const uint32_t x3 = x2 + B.x, y3 = y2 + B.y, z3 = z2 + B.z;
-#define GA_LOCAL(X, Y, Z) ((((Y) >> F) * GA_B + ((X) >> F)) * GA_B + ((Z) >> F) - oc)
+#define GA_LOCAL(X, Y, Z) ((((Y) >> F) * GA_B + ((X) >> F)) * GA_BZ + ((Z) >> F) - oc)
             const uint32_t l0 = GA_LOCAL(x0, y0, z0), l1 = GA_LOCAL(x1, y1, z1);
             const uint32_t l2 = GA_LOCAL(x2, y2, z2), l3 = GA_LOCAL(x3, y3, z3);
 #undef GA_LOCAL
@@ -729,7 +735,7 @@ static int affine_launch(const float *d_iq, int Vy, int Vx, int Vz, double qx_mi
         CUtensorMap map;
         const cuuint64_t dims[3] = {(cuuint64_t)Vz, (cuuint64_t)Vx, (cuuint64_t)Vy};
         const cuuint64_t strides[2] = {(cuuint64_t)Vz_padded * 4, (cuuint64_t)Vz_padded * 4 * (cuuint64_t)Vx};
-        const cuuint32_t box[3] = {GA_B, GA_B, GA_B};
+        const cuuint32_t box[3] = {GA_BZ, GA_B, GA_B};
         const cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(d_iq_padded), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,

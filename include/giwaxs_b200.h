@@ -348,12 +348,13 @@ int gx_masked_fit_sums(const double *d_x, const double *d_y, const double *d_mas
                        double *d_out5, void *stream);
 
 /* The same accumulation as gx_detector_accumulate_affine with the gather fed by TMA: for every
- * (32 x 16-pixel tile, orientation) the 8 x 8 x 8 brick of voxels the tile can touch is
+ * (32 x 16-pixel tile, orientation) the 8 x 8 x 12 brick of voxels the tile can touch is
  * streamed into shared memory (cp.async.bulk.tensor.3d, mbarrier ring) and the pixels read
  * it there.  d_iq_padded: copy of d_iq with rows of Vz_padded floats (multiple of 4: tensor
  * map strides are multiples of 16 bytes).  Precondition (caller): (31 |U_a| + 15 |V_a|) / 2^F
  * < 7 for every record and axis, so that a tile's voxel span fits the brick.  A/B variant of
- * north_star's kernel (4); see DESIGN.md section 4.4 for the measured comparison.         */
+ * north_star's kernel (4): identical result, measured 45 % slower than the L1-fed gather
+ * (DESIGN.md section 4.4).                                                               */
 int gx_detector_accumulate_affine_brick(const float *d_iq, const float *d_iq_padded, int Vz_padded, int Vy,
                                         int Vx, int Vz, double qx_min, double qy_min, double qz_min, double dq,
                                         const double *d_px, const double *d_py, const double *d_pz, int rows,
