@@ -427,6 +427,7 @@ def run_ours(args):
 
     if rank != 0:
         if world > 1:
+            parallel.shutdown()
             dist.destroy_process_group()
         return
 
@@ -491,6 +492,7 @@ def run_ours(args):
     line["check"] = check
     emit(line)
     if world > 1:
+        parallel.shutdown()
         dist.destroy_process_group()
 
 

@@ -75,6 +75,17 @@ def comm(device):
     return handle
 
 
+def shutdown():
+    """Destroy the library's NCCL communicator (call before torch.distributed.destroy_process_group)."""
+    if _comm["handle"] is not None:
+        from ._lib import call
+        try:
+            torch.cuda.synchronize()
+            call("gx_comm_destroy", _comm["handle"])
+        finally:
+            _comm["handle"], _comm["key"] = None, None
+
+
 def padded_columns(q_out, world):
     """(columns per rank, elements of an accumulator padded so that `world` equal slabs of whole
     (iy, ix) columns cover it) for the reduce-scatter / sharded finalise / all-gather of stage A."""

@@ -22,54 +22,58 @@ from .tools.utilities import most_common_element, parse_config_file, save_config
 from .tools.voxelgrids import add_f0_q_3d, downselect_voxelgrid, generate_voxel_grid_low_mem
 
 
+# key -> (converter, default) of the reference's voxelgridmaker config (old_modules/voxelgridmaker.py:12-25);
+# a default that is a callable is evaluated when the key is absent
+SCHEMA = {
+    "input_folder": (str, None), "input_filepath": (str, None), "filetype": (str, "xyz"), "gen_name": (str, None),
+    "r_voxel_size": (float, 0.3), "q_voxel_size": (float, 0.01), "aff_num_qs": (int, 1), "energy": (float, 1),
+    "max_q": (float, 2.5), "output_dir": (str, os.getcwd), "num_cpus": (int, os.cpu_count),
+    "scratch_folder": (str, os.getcwd), "smooth": (int, 0), "fill_bkg": (str_to_bool, "False"),
+}
+GRID_FILES = ("iq", "qx", "qy", "qz")          # <gen_name>_<part>.npy: the hand-off both detectormakers read
+
+
+def read_settings(config):
+    """Typed settings from the key=value dictionary, reference defaults for missing keys."""
+    out = {}
+    for key, (convert, default) in SCHEMA.items():
+        raw = config.get(key, default() if callable(default) else default)
+        out[key] = raw if raw is None else convert(raw)
+    return out
+
+
+def structure_files(settings):
+    if settings["input_folder"]:
+        return glob.glob(f'{settings["input_folder"]}/*{settings["filetype"]}')
+    if settings["input_filepath"]:
+        return [settings["input_filepath"]]
+    raise Exception('Either input_folder or input_path must be specified')
+
+
+def averaged_cropped_grid(paths, s):
+    """Mean over the structure files of their cropped grids (:33-59)."""
+    total = axes = None
+    for path in paths:
+        grid = generate_voxel_grid_low_mem(path, s["r_voxel_size"], s["q_voxel_size"], s["max_q"], s["aff_num_qs"],
+                                           s["energy"], s["gen_name"], scratch_folder=s["scratch_folder"],
+                                           num_cpus=s["num_cpus"], fill_bkg=s["fill_bkg"], smooth=s["smooth"])
+        cropped, *axes = downselect_voxelgrid(*grid, s["max_q"])
+        total = np.ascontiguousarray(cropped) if total is None else total + cropped
+    return total / len(paths), axes
+
+
 def main(config):
-    input_folder = config.get('input_folder', None)
-    input_filepath = config.get('input_filepath', None)
-    filetype = config.get('filetype', 'xyz')
-    gen_name = config.get('gen_name')
-    r_voxel_size = float(config.get('r_voxel_size', 0.3))
-    q_voxel_size = float(config.get('q_voxel_size', 0.01))
-    aff_num_qs = int(config.get('aff_num_qs', 1))
-    energy = float(config.get('energy', 1))
-    max_q = float(config.get('max_q', 2.5))
-    output_dir = config.get('output_dir', os.getcwd())
-    num_cpus = int(config.get('num_cpus', os.cpu_count()))
-    scratch_folder = config.get('scratch_folder', os.getcwd())
-    smooth = int(config.get('smooth', 0))
-    fill_bkg = str_to_bool(config.get('fill_bkg', 'False'))
-
-    if input_folder:
-        input_paths = glob.glob(f'{input_folder}/*{filetype}')
-    elif input_filepath:
-        input_paths = [input_filepath]
-    else:
-        raise Exception('Either input_folder or input_path must be specified')
-
-    iq_sum = None
-    for input_path in input_paths:
-        iq, qx, qy, qz = generate_voxel_grid_low_mem(input_path, r_voxel_size, q_voxel_size, max_q, aff_num_qs,
-                                                     energy, gen_name, scratch_folder=scratch_folder,
-                                                     num_cpus=num_cpus, fill_bkg=fill_bkg, smooth=smooth)
-        iq_small, qx, qy, qz = downselect_voxelgrid(iq, qx, qy, qz, max_q)
-        del iq
-        if iq_sum is None:
-            iq_sum = np.ascontiguousarray(iq_small)
-        else:
-            iq_sum += iq_small
-    iq = iq_sum
-    iq /= len(input_paths)
-    if aff_num_qs == 1:
-        iq = add_f0_q_3d(iq, qx, qy, qz, most_common_element(input_paths[0]))
-
-    save_path = f'{output_dir}/{gen_name}_output_files'
+    s = read_settings(config)
+    paths = structure_files(s)
+    iq, (qx, qy, qz) = averaged_cropped_grid(paths, s)
+    if s["aff_num_qs"] == 1:
+        iq = add_f0_q_3d(iq, qx, qy, qz, most_common_element(paths[0]))          # (:66-68)
     if parallel.rank_world()[0] == 0:
-        if not os.path.exists(save_path):
-            os.mkdir(save_path)
-        np.save(f'{save_path}/{gen_name}_iq.npy', iq)
-        np.save(f'{save_path}/{gen_name}_qx.npy', qx)
-        np.save(f'{save_path}/{gen_name}_qy.npy', qy)
-        np.save(f'{save_path}/{gen_name}_qz.npy', qz)
-        save_config_to_txt(config, f'{save_path}/{gen_name}_config.txt')
+        folder = f'{s["output_dir"]}/{s["gen_name"]}_output_files'
+        os.makedirs(folder, exist_ok=True)
+        for part, array in zip(GRID_FILES, (iq, qx, qy, qz)):
+            np.save(f'{folder}/{s["gen_name"]}_{part}.npy', array)
+        save_config_to_txt(config, f'{folder}/{s["gen_name"]}_config.txt')
     return iq, qx, qy, qz
 
 

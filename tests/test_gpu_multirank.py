@@ -49,6 +49,8 @@ def _worker(rank, world, port, ret):
         out = _pipeline()
         ret[rank] = out
     finally:
+        from giwaxsim_b200 import parallel
+        parallel.shutdown()
         dist.destroy_process_group()
 
 
