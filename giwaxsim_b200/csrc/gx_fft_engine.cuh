@@ -326,47 +326,58 @@ GX_HD void gx_apply_twiddles(float2 *v, const float2 *twt)
     }
 }
 
-// ---- 4096 = 16 boxes x 256: the split transform of the TMA-fed column kernel -------------
-// z = 16 u + c: sample z lives in box c = z mod 16 at row u = z / 16 (slot 256 c + u of the work buffer).
-//   alpha + beta : Y_c[k'] = sum_u x[16 u + c] W_256^{u k'}   two radix-16 DIF passes INSIDE one box;
-//                  Y_c[k_a + 16 k_b] ends at padded slot 256 c + 16 k_a + k_b of the column buffer
-//   gamma        : X[k' + 256 m] = sum_c (W_4096^{c k'} Y_c[k']) W_16^{c m}   radix-16 DIT ACROSS the boxes
+// ---- N = 16 boxes x (N / 16): the split transform of the TMA-fed column kernel ------------
+// N = 2^L with a 16-16-R2 schedule (L = 10, 11, 12: R2 = 4, 8, 16), RB = N / 16 = 16 R2 rows per box.
+// z = 16 u + c: sample z lives in box c = z mod 16 at row u = z / 16 (slot RB c + u of the work buffer).
+//   alpha + beta : Y_c[k'] = sum_u x[16 u + c] W_RB^{u k'}    radix-16 (stride R2) and radix-R2 DIF passes
+//                  INSIDE one box; Y_c[k_a + 16 k_b] ends at padded slot RB c + R2 k_a + k_b of the column buffer
+//   gamma        : X[k' + RB m] = sum_c (W_N^{c k'} Y_c[k']) W_16^{c m}   radix-16 DIT ACROSS the boxes
+// The twiddle tables are those of passes 1 (W_RB^{t k}) and 0 (W_N^{t k}) of the N-point schedule.
 // The kernel and the host emulation (tests/host_emul) share these functions.
-GX_HD int gx_split_slot(int z) { return (z & 15) * 256 + (z >> 4); }
+template <int L> struct GxSplit {
+    enum { N = 1 << L, RB = N / 16, R2 = GxSched<L>::R2 };
+    static_assert(GxSched<L>::R0 == 16 && GxSched<L>::R1 == 16 && GxSched<L>::NP == 3 && RB == 16 * R2,
+                  "split transform needs a 16-16-R2 schedule");
+    static GX_HD int slot(int z) { return (z & 15) * RB + (z >> 4); }
+};
 
-// alpha for butterfly t (0..15) of box c: src[n * src_stride] = row t + 16 n of the dense box,
-// sb = column buffer + gx_phys(256 c + t); tw1 = twiddle table of pass 1 of the 4096 schedule (W_256^{t k})
-template <int TWP>
+// alpha for butterfly t (0..R2-1) of box c: src[n * src_stride] = row t + R2 n of the dense box,
+// sb = column buffer + gx_phys(RB c + t)
+template <int L, int TWP>
 GX_HD void gx_split_alpha(const float2 *src, int src_stride, float2 *sb, const float2 *tw1, int t)
 {
+    constexpr int R2 = GxSplit<L>::R2;
     float2 v[16];
 #pragma unroll
     for (int n = 0; n < 16; ++n) v[n] = src[n * src_stride];
     GxDft<16>::run(v);
-    gx_apply_twiddles<16, 16, TWP>(v, tw1 + t);
+    gx_apply_twiddles<16, R2, TWP>(v, tw1 + t);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) sb[gx_phys(16 * k)] = v[k];
+    for (int k = 0; k < 16; ++k) sb[gx_phys(R2 * k)] = v[k];
 }
 
-// beta for block blk of box c, in place: sb = column buffer + gx_phys(256 c + 16 blk)
+// beta for block blk (0..15) of box c, in place: sb = column buffer + gx_phys(RB c + R2 blk)
+template <int L>
 GX_HD void gx_split_beta(float2 *sb)
 {
-    float2 v[16];
+    constexpr int R2 = GxSplit<L>::R2;
+    float2 v[R2];
 #pragma unroll
-    for (int n = 0; n < 16; ++n) v[n] = sb[n];
-    GxDft<16>::run(v);
+    for (int n = 0; n < R2; ++n) v[n] = sb[n];
+    GxDft<R2>::run(v);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) sb[k] = v[k];
+    for (int k = 0; k < R2; ++k) sb[k] = v[k];
 }
 
-// inputs of the gamma butterfly of k' (twiddled): col = column buffer, tw0 = table of pass 0 (W_4096^{t k})
-template <int TWP>
+// inputs of the gamma butterfly of k' (0..RB-1), twiddled: col = column buffer, tw0 = table of pass 0
+template <int L, int TWP>
 GX_HD void gx_split_gamma_inputs(const float2 *col, const float2 *tw0, int kp, float2 *v)
 {
-    const float2 *sb = col + gx_phys(16 * (kp & 15) + (kp >> 4));
+    constexpr int RB = GxSplit<L>::RB, R2 = GxSplit<L>::R2;
+    const float2 *sb = col + gx_phys(R2 * (kp & 15) + (kp >> 4));
 #pragma unroll
-    for (int c = 0; c < 16; ++c) v[c] = sb[273 * c];        // gx_phys(256 c + s) = 273 c + gx_phys(s) for s < 256
-    gx_apply_twiddles<16, 256, TWP>(v, tw0 + kp);
+    for (int c = 0; c < 16; ++c) v[c] = sb[gx_phys(RB * c)];   // gx_phys(RB c + s) = gx_phys(RB c) + gx_phys(s) for s < RB
+    gx_apply_twiddles<16, RB, TWP>(v, tw0 + kp);
 }
 
 // ---- one pass over NBUF independent buffers of length M --------------------

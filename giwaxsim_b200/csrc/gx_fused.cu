@@ -5,8 +5,8 @@
 //         (ATOMS.ADD) -> complex row (background, edge blend, pedestal removed) ->
 //         1-D FFT along y in the same shared memory -> only the q-columns the voxel
 //         box keeps are written (N x Kc complex64 instead of N x N).
-//   F2  slice_cols_tma     N = 4096: persistent CTAs, column tiles streamed in by TMA
-//         (256-row x 4-column boxes through an mbarrier ring), split 16 x 256
+//   F2  slice_cols_tma     N = 1024, 2048, 4096: persistent CTAs, column tiles streamed in by TMA
+//         ((N/16)-row x 4-column boxes through an mbarrier ring), split 16 x N/16
 //         transform, only the kept outputs formed and binned at once;
 //       slice_cols_fused   other sizes: one CTA per (rotation, TC kept columns):
 //         column tile (rows of the atom band only; the rest is zero once the
@@ -385,7 +385,8 @@ slice_rows_fused(FusedArgs fa)
     if (full) gx_dft_block<L, 1, 0, BLUE ? 1 : 0, true>(buf, fa.lay, fa.plan, tid, NT);
 
     // kept q-columns only; shifted column j holds unshifted coefficient j - N/2 (mod N)
-    const int slot = ROWPERM ? gx_split_slot(z) : z;
+    int slot = z;
+    if constexpr (ROWPERM) slot = GxSplit<L>::slot(z);
     float2 *dst = fa.work + ((size_t)p * N + slot) * fa.KC;
     const int half = N / 2;
     for (int jj = tid; jj < jhi - jlo; jj += NT) {
@@ -492,41 +493,49 @@ slice_cols_fused(FusedArgs fa)
     }
 }
 
-// ------------------------------------------------------- F2, TMA-fed (L = 12) ----
-// Same result as slice_cols_fused for power-of-two 4096 grids, restructured around asynchronous tile
-// movement: the [n_phi N, KC] complex64 work buffer is a 2-D tensor map and a dedicated producer thread
-// streams 256-row x 4-column boxes (cp.async.bulk.tensor.2d -> UTMALDG, completion on mbarriers) through an
-// 8-slot ring while 16 consumer warps transform.  Persistent CTAs (one per SM) walk the (rotation, column
-// tile) list, so the boxes of the next tile are already landing while the current tile finishes.
+// ------------------------------------------- F2, TMA-fed (N = 1024, 2048, 4096) ----
+// Same result as slice_cols_fused for the power-of-two grids with a 16-16-R2 schedule, restructured around
+// asynchronous tile movement: the [n_phi N, KC] complex64 work buffer is a 2-D tensor map and a dedicated
+// producer thread streams (N/16)-row x 4-column boxes (cp.async.bulk.tensor.2d -> UTMALDG, completion on
+// mbarriers) through an 8-slot ring while 16 consumer warps transform.  Persistent CTAs (one per SM) walk the
+// (rotation, column tile) list, so the boxes of the next tile are already landing while the current tile finishes.
 //
-// The column transform is split so that two of its three passes need only ONE box:
-//   z = 16 u + c  (F1 writes row z to slot 256 c + u: ROWPERM)
-//   Y_c[k'] = sum_u x[16 u + c] W_256^{u k'}                       256-point DIF inside box c (passes alpha, beta)
-//   X[k' + 256 m] = sum_c W_4096^{c k'} Y_c[k'] W_16^{c m}         radix-16 DIT across the boxes   (pass gamma)
+// The column transform is split so that two of its three passes need only ONE box (gx_fft_engine.cuh, GxSplit):
+//   z = 16 u + c  (F1 writes row z to slot RB c + u, RB = N / 16: ROWPERM)
+//   Y_c[k'] = sum_u x[16 u + c] W_RB^{u k'}                        RB-point DIF inside box c (passes alpha, beta)
+//   X[k' + RB m] = sum_c W_N^{c k'} Y_c[k'] W_16^{c m}             radix-16 DIT across the boxes   (pass gamma)
 // alpha reads the dense box ([row][4 columns], 32 B per row: lanes = 4 rows x 4 columns of a half-warp are 128
-// contiguous bytes) and writes the padded per-column layout, beta is in place, gamma reads 16 values 273 slots
+// contiguous bytes) and writes the padded per-column layout, beta is in place, gamma reads 16 values one box
 // apart, forms only the outputs the voxel window keeps (m = 0, 15, sometimes 1, 14: gx_dft16_lowband) and adds
 // |X|^2 straight into the voxel sum: the transformed column is never stored, not even in shared memory.
 #define F2T_TC 4
-#define F2T_ROWS 256
 #define F2T_NBOX 16
 #define F2T_RING 8
 #define F2T_CONSUMERS 512
 #define F2T_THREADS (F2T_CONSUMERS + 32)
-#define F2T_BOX_BYTES (F2T_ROWS * F2T_TC * 8)
-#define F2T_BS 4372                     // float2 per column buffer: >= 4369 and == 4 (mod 16)
-#define F2T_SMEM (F2T_RING * F2T_BOX_BYTES + F2T_TC * F2T_BS * 8 + 2 * F2T_RING * 8)
 
+template <int L> struct F2T {
+    enum {
+        N = 1 << L, RB = GxSplit<L>::RB, R2 = GxSplit<L>::R2,
+        BOX_BYTES = RB * F2T_TC * 8,
+        BS0 = N + (N >> 4) + (N >> 8) + 1,
+        BS = BS0 + ((4 - (BS0 % 16)) + 16) % 16,       // float2 per column buffer: == 4 (mod 16), see alpha's stores
+        SMEM = F2T_RING * BOX_BYTES + F2T_TC * BS * 8 + 2 * F2T_RING * 8
+    };
+};
+
+template <int L>
 __global__ void __launch_bounds__(F2T_THREADS, 1)
 slice_cols_tma(FusedArgs fa, const __grid_constant__ CUtensorMap tmap)
 {
-    constexpr int M = 4096, BS = F2T_BS;
+    typedef F2T<L> G;
+    constexpr int N = G::N, RB = G::RB, R2 = G::R2, BS = G::BS, BOX_BYTES = G::BOX_BYTES;
     extern __shared__ __align__(128) unsigned char smem_tma[];
     float2 *ring = reinterpret_cast<float2 *>(smem_tma);
-    float2 *work = reinterpret_cast<float2 *>(smem_tma + F2T_RING * F2T_BOX_BYTES);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_tma + F2T_RING * F2T_BOX_BYTES + F2T_TC * BS * 8);
+    float2 *work = reinterpret_cast<float2 *>(smem_tma + F2T_RING * BOX_BYTES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_tma + F2T_RING * BOX_BYTES + F2T_TC * BS * 8);
     uint64_t *empty = full + F2T_RING;
-    const int tid = threadIdx.x, N = M;
+    const int tid = threadIdx.x;
     if (tid == 0) {
         for (int i = 0; i < F2T_RING; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -546,9 +555,9 @@ slice_cols_tma(FusedArgs fa, const __grid_constant__ CUtensorMap tmap)
                 for (int c = 0; c < F2T_NBOX; ++c) {
                     const int slot = c & (F2T_RING - 1);
                     mbar_wait(empty + slot, ((c >> 3) & 1) ^ 1);      // n-th refill of a slot: n = 2 tile_iter + c / 8
-                    mbar_expect_tx(full + slot, F2T_BOX_BYTES);
-                    tma_load_2d(reinterpret_cast<unsigned char *>(ring) + slot * F2T_BOX_BYTES, &tmap, tile * F2T_TC,
-                                p * N + c * F2T_ROWS, full + slot);
+                    mbar_expect_tx(full + slot, BOX_BYTES);
+                    tma_load_2d(reinterpret_cast<unsigned char *>(ring) + slot * BOX_BYTES, &tmap, tile * F2T_TC,
+                                p * N + c * RB, full + slot);
                 }
             }
         }
@@ -562,7 +571,7 @@ slice_cols_tma(FusedArgs fa, const __grid_constant__ CUtensorMap tmap)
     const float2 *tw0 = fa.plan + fa.lay.tw_off[0], *tw1 = fa.plan + fa.lay.tw_off[1];
     const int half = N / 2;
     const int klo = fa.row_lo - half, khi = fa.row_hi - half;
-    const bool lowband = klo >= -512 && khi <= 512;
+    const bool lowband = klo >= -2 * RB && khi <= 2 * RB;
     for (int f = blockIdx.x; f < total; f += gridDim.x) {
         const int p = f % fa.n_phi, tile = f / fa.n_phi;
         const int jlo = fa.colrange[2 * p];
@@ -572,40 +581,40 @@ slice_cols_tma(FusedArgs fa, const __grid_constant__ CUtensorMap tmap)
 #pragma unroll 1
         for (int r = 0; r < 2; ++r) {
             const int c = pair + 8 * r;
-            // alpha: radix-16 DIF, stride 16, of the 256-point sub-transform; dense box -> padded column buffers
-            {
+            // alpha: radix-16 DIF, stride R2, of the RB-point sub-transform; dense box -> padded column buffers
+            mbar_wait(full + pair, r);
+            if (e < R2 * F2T_TC) {
                 const int col = e & 3, t = e >> 2;
-                mbar_wait(full + pair, r);
-                const float2 *st = ring + pair * (F2T_ROWS * F2T_TC) + t * F2T_TC + col;
+                const float2 *st = ring + pair * (RB * F2T_TC) + t * F2T_TC + col;
                 float2 v[16];
 #pragma unroll
-                for (int n = 0; n < 16; ++n) v[n] = st[n * 16 * F2T_TC];
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty + pair);          // this warp has read its half of the box
-                gx_split_alpha<GX_PASS1_TWP>(v, 1, work + col * BS + gx_phys(c * F2T_ROWS + t), tw1, t);
+                for (int n = 0; n < 16; ++n) v[n] = st[n * R2 * F2T_TC];
+                gx_split_alpha<L, GX_PASS1_TWP>(v, 1, work + col * BS + gx_phys(c * RB + t), tw1, t);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + pair);              // this warp is done with the box
             named_barrier(1 + pair, 64);
-            // beta: radix-16, stride 1, in place
+            // beta: radix-R2, stride 1, in place
             {
                 const int blk = e & 15, col = e >> 4;
-                gx_split_beta(work + col * BS + gx_phys(c * F2T_ROWS + 16 * blk));
+                gx_split_beta<L>(work + col * BS + gx_phys(c * RB + R2 * blk));
             }
         }
         named_barrier(9, F2T_CONSUMERS);
         // gamma: radix-16 DIT across the boxes, only the kept outputs, binned at once
 #pragma unroll 1
-        for (int g = tid; g < F2T_TC * 256; g += F2T_CONSUMERS) {
-            const int col = g >> 8, kp = g & 255;
+        for (int g = tid; g < F2T_TC * RB; g += F2T_CONSUMERS) {
+            const int col = g / RB, kp = g - col * RB;
             if (jj0 + col >= kc) continue;
             const int j = jlo + jj0 + col;
             const int yx = fa.col[(size_t)p * N + j];
             if (yx < 0) continue;
             if (kp == 0) atomicAdd(&fa.count2[yx], 1u);
             float2 v[16];
-            gx_split_gamma_inputs<GX_TWP>(work + col * BS, tw0, kp, v);
+            gx_split_gamma_inputs<L, GX_TWP>(work + col * BS, tw0, kp, v);
             float *dst = fa.vsum + (size_t)yx * fa.q_num;
             if (lowband) {
-                const bool w1 = kp + 256 < khi, w14 = kp - 512 >= klo;
+                const bool w1 = kp + RB < khi, w14 = kp - 2 * RB >= klo;
                 float2 x0, x15, x1, x14;
                 gx_dft16_lowband_vals(v, w1 || w14, x0, x15, x1, x14);
                 int iz;
@@ -618,14 +627,14 @@ slice_cols_tma(FusedArgs fa, const __grid_constant__ CUtensorMap tmap)
                         atomicAdd(dst + iz, x0.x * x0.x + x0.y * x0.y);
                     }
                 }
-                if (kp - 256 >= klo && (iz = fa.row_index[kp - 256 + half]) >= 0) atomicAdd(dst + iz, x15.x * x15.x + x15.y * x15.y);
-                if (w1 && (iz = fa.row_index[kp + 256 + half]) >= 0) atomicAdd(dst + iz, x1.x * x1.x + x1.y * x1.y);
-                if (w14 && (iz = fa.row_index[kp - 512 + half]) >= 0) atomicAdd(dst + iz, x14.x * x14.x + x14.y * x14.y);
+                if (kp - RB >= klo && (iz = fa.row_index[kp - RB + half]) >= 0) atomicAdd(dst + iz, x15.x * x15.x + x15.y * x15.y);
+                if (w1 && (iz = fa.row_index[kp + RB + half]) >= 0) atomicAdd(dst + iz, x1.x * x1.x + x1.y * x1.y);
+                if (w14 && (iz = fa.row_index[kp - 2 * RB + half]) >= 0) atomicAdd(dst + iz, x14.x * x14.x + x14.y * x14.y);
             } else {
                 GxDft<16>::run(v);
 #pragma unroll
                 for (int m = 0; m < 16; ++m) {
-                    const int kz = kp + 256 * m;                       // unshifted coefficient index
+                    const int kz = kp + RB * m;                        // unshifted coefficient index
                     int i = kz + half;
                     if (i >= N) i -= N;
                     if (i < fa.row_lo || i >= fa.row_hi) continue;
@@ -670,13 +679,13 @@ extern "C" int gx_slice_col_range(const int32_t *d_col, int n_phi, int N, int32_
 
 // ---------------------------------------------------------------- launch ----
 // 2-D tensor map of the [rows, KC] complex64 work buffer, box = 256 rows x 4 columns (one ring slot)
-static int work_tensor_map(CUtensorMap *map, void *work, size_t rows, int KC)
+static int work_tensor_map(CUtensorMap *map, void *work, size_t rows, int KC, int box_rows)
 {
     gx_encode_tiled_fn encode = gx_tensor_map_encoder();
     if (!encode) return GX_ERR_UNSUPPORTED;
     const cuuint64_t dims[2] = {(cuuint64_t)KC, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)KC * 8};
-    const cuuint32_t box[2] = {F2T_TC, F2T_ROWS};
+    const cuuint32_t box[2] = {F2T_TC, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, work, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -687,10 +696,10 @@ static int work_tensor_map(CUtensorMap *map, void *work, size_t rows, int KC)
     return GX_OK;
 }
 
-// the TMA-fed column kernel covers the power-of-two 4096 grid (the headline size)
+// the TMA-fed column kernel covers the power-of-two grids with a 16-16-R2 schedule: N = 1024, 2048, 4096
 static bool cols_tma_ok(const FusedArgs &fa, int L, bool blue)
 {
-    return L == 12 && !blue && fa.KC % 8 == 0 && (reinterpret_cast<uintptr_t>(fa.work) & 15) == 0 &&
+    return L >= 10 && L <= 12 && !blue && fa.KC % 8 == 0 && (reinterpret_cast<uintptr_t>(fa.work) & 15) == 0 &&
            !getenv("GIWAXS_B200_NO_TMA");
 }
 
@@ -720,7 +729,7 @@ static int launch_fused(const FusedArgs &fa, bool species, int phases, cudaStrea
         slice_rows_fused<L, SP, BL, RP><<<grid1, PROJ_THREADS, smem1, st>>>(fa);                           \
     } while (0)
     if (phases & 1) {
-        if constexpr (L == 12) {
+        if constexpr (L >= 10 && L <= 12) {
             if (tma) { if (species) GX_LAUNCH_ROWS(true, false, true); else GX_LAUNCH_ROWS(false, false, true); }
         }
         if (!tma) {
@@ -733,9 +742,9 @@ static int launch_fused(const FusedArgs &fa, bool species, int phases, cudaStrea
     }
 #undef GX_LAUNCH_ROWS
     if (!(phases & 2)) return GX_OK;
-    if (tma) {
+    if constexpr (L >= 10 && L <= 12) if (tma) {
         CUtensorMap map;
-        if (int e = work_tensor_map(&map, fa.work, (size_t)fa.n_phi * N, fa.KC)) return e;
+        if (int e = work_tensor_map(&map, fa.work, (size_t)fa.n_phi * N, fa.KC, F2T<L>::RB)) return e;
         static int sms = 0;
         if (!sms) {
             int dev = 0;
@@ -743,8 +752,8 @@ static int launch_fused(const FusedArgs &fa, bool species, int phases, cudaStrea
             GX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         }
         const int total = fa.n_phi * (fa.KC / F2T_TC);
-        GX_CUDA(cudaFuncSetAttribute(slice_cols_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, F2T_SMEM));
-        slice_cols_tma<<<total < sms ? total : sms, F2T_THREADS, F2T_SMEM, st>>>(fa, map);
+        GX_CUDA(cudaFuncSetAttribute(slice_cols_tma<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2T<L>::SMEM));
+        slice_cols_tma<L><<<total < sms ? total : sms, F2T_THREADS, F2T<L>::SMEM, st>>>(fa, map);
         return gx_check_launch("slice_cols_tma");
     }
     int nt = TC * M / 16;

@@ -75,41 +75,53 @@ extern "C" int emul_dft_lowband(const float *plan, const float *in, float *out, 
     return 0;
 }
 
-// The split 4096-point transform of the TMA-fed column kernel (16 boxes of 256 rows; gx_split_*):
-// rows are placed at gx_split_slot(z) as the row kernel does, every box goes through alpha and beta,
+// The split N-point transform of the TMA-fed column kernel (16 boxes of N / 16 rows; gx_split_*), N = 1024, 2048,
+// 4096: rows are placed at GxSplit<L>::slot(z) as the row kernel does, every box goes through alpha and beta,
 // gamma forms all 16 outputs (full != 0) or only the kept band through gx_dft16_lowband_vals.
-// out[k - klo] for klo <= k < khi (negative k = coefficient 4096 + k).
-extern "C" int emul_dft_split(const float *plan, const float *in, float *out, int klo, int khi, int full)
+// out[k - klo] for klo <= k < khi (negative k = coefficient N + k).
+template <int L>
+static int run_split(const float2 *p, const float2 *x, float2 *o, int klo, int khi, int full)
 {
-    constexpr int M = 4096;
+    typedef GxSplit<L> Sp;
+    constexpr int M = Sp::N, RB = Sp::RB, R2 = Sp::R2;
     GxFftLayout g = gx_fft_layout(M);
-    const float2 *p = reinterpret_cast<const float2 *>(plan);
-    const float2 *x = reinterpret_cast<const float2 *>(in);
-    float2 *o = reinterpret_cast<float2 *>(out);
     std::vector<float2> dense(M), col(gx_phys_len(M));
-    for (int z = 0; z < M; ++z) dense[gx_split_slot(z)] = x[z];
+    for (int z = 0; z < M; ++z) dense[Sp::slot(z)] = x[z];
     for (int c = 0; c < 16; ++c) {
-        for (int t = 0; t < 16; ++t)
-            gx_split_alpha<1>(dense.data() + 256 * c + t, 16, col.data() + gx_phys(256 * c + t), p + g.tw_off[1], t);
-        for (int blk = 0; blk < 16; ++blk) gx_split_beta(col.data() + gx_phys(256 * c + 16 * blk));
+        for (int t = 0; t < R2; ++t)
+            gx_split_alpha<L, 1>(dense.data() + RB * c + t, R2, col.data() + gx_phys(RB * c + t), p + g.tw_off[1], t);
+        for (int blk = 0; blk < 16; ++blk) gx_split_beta<L>(col.data() + gx_phys(RB * c + R2 * blk));
     }
     std::vector<float2> X(M, make_float2(0.f, 0.f));
-    for (int kp = 0; kp < 256; ++kp) {
+    for (int kp = 0; kp < RB; ++kp) {
         float2 v[16];
-        gx_split_gamma_inputs<1>(col.data(), p + g.tw_off[0], kp, v);
+        gx_split_gamma_inputs<L, 1>(col.data(), p + g.tw_off[0], kp, v);
         if (full) {
             GxDft<16>::run(v);
-            for (int m = 0; m < 16; ++m) X[kp + 256 * m] = v[m];
+            for (int m = 0; m < 16; ++m) X[kp + RB * m] = v[m];
         } else {
-            if (klo < -512 || khi > 512) return -1;
-            const bool w1 = kp + 256 < khi, w14 = kp - 512 >= klo;
+            if (klo < -2 * RB || khi > 2 * RB) return -1;
+            const bool w1 = kp + RB < khi, w14 = kp - 2 * RB >= klo;
             float2 x0, x15, x1, x14;
             gx_dft16_lowband_vals(v, w1 || w14, x0, x15, x1, x14);
-            X[kp] = x0; X[kp + 3840] = x15;
-            if (w1) X[kp + 256] = x1;
-            if (w14) X[kp + 3584] = x14;
+            X[kp] = x0; X[kp + 15 * RB] = x15;
+            if (w1) X[kp + RB] = x1;
+            if (w14) X[kp + 14 * RB] = x14;
         }
     }
     for (int k = klo; k < khi; ++k) o[k - klo] = X[k < 0 ? k + M : k];
     return 0;
+}
+
+extern "C" int emul_dft_split(int N, const float *plan, const float *in, float *out, int klo, int khi, int full)
+{
+    const float2 *p = reinterpret_cast<const float2 *>(plan);
+    const float2 *x = reinterpret_cast<const float2 *>(in);
+    float2 *o = reinterpret_cast<float2 *>(out);
+    switch (N) {
+    case 1024: return run_split<10>(p, x, o, klo, khi, full);
+    case 2048: return run_split<11>(p, x, o, klo, khi, full);
+    case 4096: return run_split<12>(p, x, o, klo, khi, full);
+    }
+    return -2;
 }

@@ -69,17 +69,19 @@ def test_fft_engine_host_build_matches_numpy(fft_emul, N):
     assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("klo,khi,full", [(-288, 288, 0), (-512, 512, 0), (-200, 203, 0), (-2048, 2048, 1), (-257, 300, 0)])
-def test_split_transform_of_the_tma_column_kernel_matches_numpy(fft_emul, klo, khi, full):
-    """4096 = 16 boxes x 256 (gx_split_*): rows permuted as the row kernel writes them, two in-box DIF passes,
-    one DIT pass across the boxes with only the kept outputs - equals numpy.fft on the band."""
-    N = 4096
+@pytest.mark.parametrize("N,klo,khi,full", [(4096, -288, 288, 0), (4096, -512, 512, 0), (4096, -200, 203, 0),
+                                            (4096, -2048, 2048, 1), (4096, -257, 300, 0), (2048, -256, 256, 0),
+                                            (2048, -198, 199, 0), (2048, -1024, 1024, 1), (1024, -128, 128, 0),
+                                            (1024, -70, 75, 0), (1024, -512, 512, 1)])
+def test_split_transform_of_the_tma_column_kernel_matches_numpy(fft_emul, N, klo, khi, full):
+    """N = 16 boxes x N/16 (gx_split_*; N = 1024, 2048, 4096): rows permuted as the row kernel writes them, two
+    in-box DIF passes, one DIT pass across the boxes with only the kept outputs - equals numpy.fft on the band."""
     plan = np.zeros(_lib.cdll().gx_fft_plan_bytes(N) // 4, np.float32)
     _lib.call("gx_fft_plan_fill", N, _lib.ptr(plan))
-    rng = np.random.default_rng(abs(klo) * 7 + khi)
+    rng = np.random.default_rng(abs(klo) * 7 + khi + N)
     x = (rng.normal(size=N) + 1j * rng.normal(size=N) + 3.0).astype(np.complex64)
     out = np.zeros(khi - klo, np.complex64)
-    assert fft_emul.emul_dft_split(_lib.ptr(plan), _lib.ptr(x), _lib.ptr(out), klo, khi, full) == 0
+    assert fft_emul.emul_dft_split(N, _lib.ptr(plan), _lib.ptr(x), _lib.ptr(out), klo, khi, full) == 0
     ref = np.fft.fft(x.astype(np.complex128))
     want = np.array([ref[k % N] for k in range(klo, khi)])
     assert np.abs(out - want).max() <= 3e-6 * np.abs(ref).max()
