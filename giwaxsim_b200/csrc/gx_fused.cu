@@ -696,10 +696,19 @@ static int work_tensor_map(CUtensorMap *map, void *work, size_t rows, int KC, in
     return GX_OK;
 }
 
-// the TMA-fed column kernel covers the power-of-two grids with a 16-16-R2 schedule: N = 1024, 2048, 4096
+// The TMA-fed column kernel exists for the power-of-two grids with a 16-16-R2 schedule (N = 1024, 2048, 4096) and
+// is the default for 2048 and 4096: measured 18.3 vs 19.9 and 60.9 vs 65.2 us per slice against the LDG-fed
+// kernel (whole fused path, scripts/time_fused.py), but 10.2 vs 9.4 at N = 1024, where a tile is too small to fill
+// a persistent 544-thread CTA (GIWAXS_B200_TMA_MIN_L=10 selects it there too; GIWAXS_B200_NO_TMA=1 disables it).
 static bool cols_tma_ok(const FusedArgs &fa, int L, bool blue)
 {
-    return L >= 10 && L <= 12 && !blue && fa.KC % 8 == 0 && (reinterpret_cast<uintptr_t>(fa.work) & 15) == 0 &&
+    static int min_l = 0;
+    if (!min_l) {
+        const char *e = getenv("GIWAXS_B200_TMA_MIN_L");
+        min_l = e ? atoi(e) : 11;
+        if (min_l < 10) min_l = 10;
+    }
+    return L >= min_l && L <= 12 && !blue && fa.KC % 8 == 0 && (reinterpret_cast<uintptr_t>(fa.work) & 15) == 0 &&
            !getenv("GIWAXS_B200_NO_TMA");
 }
 

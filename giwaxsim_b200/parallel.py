@@ -174,7 +174,7 @@ def _upload_staged(flat, device, out=None):
         out = torch.empty(n, dtype=torch.uint8, device=device)
     stage = engine._pinned_staging(min(n, 2 * STAGED_UPLOAD_CHUNK))
     before = torch.get_num_threads()
-    want = max(1, min(8, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+    want = max(1, min(16, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
     events = [None, None]
     try:
         if want > before:
