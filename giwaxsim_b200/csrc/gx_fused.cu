@@ -702,12 +702,9 @@ static int work_tensor_map(CUtensorMap *map, void *work, size_t rows, int KC, in
 // a persistent 544-thread CTA (GIWAXS_B200_TMA_MIN_L=10 selects it there too; GIWAXS_B200_NO_TMA=1 disables it).
 static bool cols_tma_ok(const FusedArgs &fa, int L, bool blue)
 {
-    static int min_l = 0;
-    if (!min_l) {
-        const char *e = getenv("GIWAXS_B200_TMA_MIN_L");
-        min_l = e ? atoi(e) : 11;
-        if (min_l < 10) min_l = 10;
-    }
+    const char *e = getenv("GIWAXS_B200_TMA_MIN_L");
+    int min_l = e ? atoi(e) : 11;
+    if (min_l < 10) min_l = 10;
     return L >= min_l && L <= 12 && !blue && fa.KC % 8 == 0 && (reinterpret_cast<uintptr_t>(fa.work) & 15) == 0 &&
            !getenv("GIWAXS_B200_NO_TMA");
 }

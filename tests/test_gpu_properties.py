@@ -345,3 +345,34 @@ def test_tma_brick_detector_variant_is_identical_to_the_ldg_kernel():
         b, _ = det.accumulate(gx, gy, gz, R, w, kernel="affine_tma")
         assert det.last_kernel == "affine_tma"
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("grid", [1024, 2048])
+def test_tma_fed_column_kernel_equals_the_ldg_fed_one(monkeypatch, grid):
+    """slice_cols_tma<L> (N = 1024 through GIWAXS_B200_TMA_MIN_L=10, N = 2048 by default) against slice_cols_fused
+    (GIWAXS_B200_NO_TMA=1): identical counts, sums equal to fp32 accumulation order.  (N = 4096 is covered by the
+    full-size tests against the oracle.)"""
+    coords, el = synth.random_slab(200_000, (grid * 0.13, grid * 0.06, grid * 0.12), seed=21)
+    r, max_q = 0.15, 2.0
+    q = synth.pow2_q_voxel(r, grid)
+    codes, uniq, table = comparison.species_table(el, 12700.0)
+    dev = engine.resolve_device()
+    atoms = engine.AtomSet(coords, r, grid, dev, species=codes, table=table)
+    N, q_num, q_axis, phis = engine.stage_a_geometry(atoms.bounds, r, q, max_q)
+    assert N == grid
+    avg = np.sum(np.bincount(codes, minlength=len(table)) * np.asarray(table)) / np.prod(atoms.bounds) * r ** 3
+    window = engine.crop_range(q_axis, max_q)
+    sel = phis[:: max(1, len(phis) // 40)]
+
+    def run():
+        e = engine.SliceEngine(None, r, q_axis, N, avg, atoms.bounds[0], atoms.bounds[1], True, 9, atoms=atoms,
+                               window=window)
+        e.run(sel)
+        return e.counts(), e.sums().astype(np.float64)
+
+    monkeypatch.setenv("GIWAXS_B200_TMA_MIN_L", "10")
+    c_tma, s_tma = run()
+    monkeypatch.setenv("GIWAXS_B200_NO_TMA", "1")
+    c_ldg, s_ldg = run()
+    assert c_tma.sum() > 0 and np.array_equal(c_tma, c_ldg)
+    assert np.abs(s_tma - s_ldg).max() <= 2e-6 * s_ldg.max()
