@@ -415,11 +415,12 @@ def shared_result_f64(t, to_host_slice, group=None, min_bytes=16 << 20, single=F
     per = (n + world - 1) // world
     lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
     if hi > lo:
-        if t.is_cuda and _register_slab(seg, lo, hi):
+        if multi and t.is_cuda and _register_slab(seg, lo, hi):
             # the slab is widened on the device and DMA'd straight into its place in the (page-locked)
-            # segment: no host-side copy or conversion - 8 ranks would do those on the same cores, and even one
-            # rank moves fewer host bytes this way (0.52 GB written by DMA at 57 GB/s instead of 0.26 GB staged
-            # plus 0.79 GB of widening traffic at ~60 GB/s: 9 vs 12 ms for the 403^3 grid)
+            # segment: no host-side copy or conversion, which 8 ranks would do on the same cores.
+            # (One rank: measured 9.6 vs 12.1 ms per call for the 403^3 grid, but page-locking the whole 0.5 GB
+            # segment costs 215 ms once per pooled segment - 70 calls to amortise - so a single rank stages the
+            # fp32 grid through the pinned buffer and widens on the host.)
             import ctypes
             from . import engine
             from ._lib import call, ptr
