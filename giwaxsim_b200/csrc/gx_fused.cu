@@ -38,6 +38,9 @@
 #ifndef GX_PASS1_TWP
 #define GX_PASS1_TWP GX_TWP  // twiddles of the middle pass (16 distinct sets, 1.9 KB): 1 = four loads + products, 0 = fifteen loads
 #endif
+#ifndef GX_SCATTER_U
+#define GX_SCATTER_U 4      // atoms per thread in flight in the row kernel's scatter (2: measured in profiles/r04_summary.md)
+#endif
 #ifndef GX_F1_MINBLOCKS
 #define GX_F1_MINBLOCKS 4   // CTAs/SM the row kernel is compiled for (3 would leave ~84 KB of L1: measured no faster)
 #endif
@@ -180,9 +183,9 @@ __device__ __forceinline__ void scatter_fixed(const ProjArgs &a, const int2 *s_f
     const double r = a.r, inv_r = 1.0 / a.r;
     int i0 = beg + tid;
     int left = end - beg;
-    for (; left >= 4 * nt; left -= 4 * nt, i0 += 4 * nt)
-        scatter_fixed_batch<4, false, SPECIES>(a, s_ffx, sc_re, sc_im, i0, end, nt, s, c, shift, r, inv_r, acc, NP);
-    if (left >= 2 * nt) {
+    for (; left >= GX_SCATTER_U * nt; left -= GX_SCATTER_U * nt, i0 += GX_SCATTER_U * nt)
+        scatter_fixed_batch<GX_SCATTER_U, false, SPECIES>(a, s_ffx, sc_re, sc_im, i0, end, nt, s, c, shift, r, inv_r, acc, NP);
+    if (GX_SCATTER_U > 2 && left >= 2 * nt) {
         scatter_fixed_batch<2, false, SPECIES>(a, s_ffx, sc_re, sc_im, i0, end, nt, s, c, shift, r, inv_r, acc, NP);
         left -= 2 * nt; i0 += 2 * nt;
     }

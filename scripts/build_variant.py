@@ -14,5 +14,5 @@ subprocess.check_call([b.NVCC] + [f for f in b.FLAGS if f not in ("-Xptxas", "-v
 objs = [os.path.join(b.OBJ, s.replace(".cu", ".o")) for s in b.SOURCES if s != src] + [obj]
 lib = os.path.join(out_dir, "libgiwaxs_b200_%s.so" % name)
 subprocess.check_call([b.NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                               "-Xcompiler", "-fPIC"])
+                                                               "-Xcompiler", "-fPIC", "-ldl"])
 print(lib)
