@@ -39,10 +39,11 @@
 #define GX_PASS1_TWP GX_TWP  // twiddles of the middle pass (16 distinct sets, 1.9 KB): 1 = four loads + products, 0 = fifteen loads
 #endif
 #ifndef GX_SCATTER_U
-#define GX_SCATTER_U 4      // atoms per thread in flight in the row kernel's scatter (2: measured in profiles/r04_summary.md)
+#define GX_SCATTER_U 2      // atoms per thread in flight in the row kernel's scatter (1 .. 4 measured: profiles/r04_summary.md)
 #endif
 #ifndef GX_F1_MINBLOCKS
-#define GX_F1_MINBLOCKS 4   // CTAs/SM the row kernel is compiled for (3 would leave ~84 KB of L1: measured no faster)
+#define GX_F1_MINBLOCKS 5   // CTAs/SM the 4096-point row kernel is compiled for (others: 4): 48 registers, 4 bytes spilled with
+                            // two atoms in flight; 61.7 (4 CTAs, 64 registers) -> 59.8 us per slice, 6 CTAs: 68.3, 3: 66.3
 #endif
 
 // Per-rotation / per-row scalars of the row kernel, staged through constant memory by gx_slices_fused
@@ -244,7 +245,7 @@ __device__ __forceinline__ void flush_fixed(float2 (&px)[NB0][R0], const int32_t
 // ROWPERM: row z is written to slot 256 (z mod 16) + z / 16 of the work buffer, the order the
 // TMA-fed column kernel consumes (16 chunks of 256 rows, each a 256-point sub-transform).
 template <int L, bool SPECIES, bool BLUE, bool ROWPERM>
-__global__ void __launch_bounds__(PROJ_THREADS, (L >= 14) ? 1 : (L >= 13) ? 2 : GX_F1_MINBLOCKS)
+__global__ void __launch_bounds__(PROJ_THREADS, (L >= 14) ? 1 : (L >= 13) ? 2 : ((L == 12 && !BLUE) ? GX_F1_MINBLOCKS : 4))
 slice_rows_fused(FusedArgs fa)
 {
     typedef GxSched<L> Sc;
