@@ -188,7 +188,7 @@ def call(name, *args):
     if name not in _UNCHECKED and rc != GX_OK:
         raise GxError(rc, last_error())
     if name == "gx_slice_yrange":
-        _launch_count += 2 + (int(args[5]) + 255) // 256
+        _launch_count += 1 if int(args[2]) <= 65536 else 2 + (int(args[5]) + 255) // 256
     elif name == "gx_slices_fused":
         ph = getattr(getattr(args[0], "_obj", None), "phases", 0)
         _launch_count += 2 if ph in (0, 3) else 1

@@ -225,6 +225,30 @@ yrange_kernel(const double *__restrict__ xs, const double *__restrict__ ys, int6
     }
 }
 
+// Few atoms (the convex-hull candidates: ~1e3 .. 1e4), many rotations: one warp per rotation, lanes over the
+// atoms.  (yrange_kernel loops over the rotations inside every block: with five blocks' worth of atoms that was
+// 137 us per 256 rotations, latency-bound; min / max are exact whatever the order, so the result is the same.)
+#define YR_SMALL_MAX 65536
+__global__ void __launch_bounds__(ATOM_THREADS)
+yrange_small_kernel(const double *__restrict__ xs, const double *__restrict__ ys, int A,
+                    const double *__restrict__ d_sin, const double *__restrict__ d_cos, int n_phi, double *out)
+{
+    const int lane = threadIdx.x & 31;
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (p >= n_phi) return;
+    const double s = d_sin[p], c = d_cos[p];
+    double lo = INFINITY, hi = -INFINITY;
+    for (int i = lane; i < A; i += 32) {
+        const double v = gx_rot_y(xs[i], ys[i], s, c);
+        lo = fmin(lo, v); hi = fmax(hi, v);
+    }
+    for (int off = 16; off; off >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+    }
+    if (lane == 0) { out[2 * p] = lo; out[2 * p + 1] = hi; }
+}
+
 __global__ void yrange_decode_kernel(unsigned long long *o, int n_phi)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -238,6 +262,12 @@ extern "C" int gx_slice_yrange(const double *d_xs, const double *d_ys, int64_t A
     GX_REQUIRE(d_xs && d_ys && d_sin && d_cos && d_yrange, "NULL pointer");
     GX_REQUIRE(A > 0 && n_phi > 0, "empty input");
     cudaStream_t st = gx_stream(stream);
+    if (A <= YR_SMALL_MAX) {
+        const int warps_per_block = ATOM_THREADS / 32;
+        yrange_small_kernel<<<(n_phi + warps_per_block - 1) / warps_per_block, ATOM_THREADS, 0, st>>>(
+            d_xs, d_ys, (int)A, d_sin, d_cos, n_phi, d_yrange);
+        return gx_check_launch("gx_slice_yrange");
+    }
     unsigned long long *o = reinterpret_cast<unsigned long long *>(d_yrange);
     yrange_init_kernel<<<(2 * n_phi + 255) / 256, 256, 0, st>>>(o, n_phi);
     const int64_t tile = (int64_t)ATOM_THREADS * YR_K;
@@ -288,10 +318,12 @@ __global__ void __launch_bounds__(ATOM_THREADS)
 bbox_full_kernel(const double *__restrict__ xs, const double *__restrict__ ys,
                  const int32_t *__restrict__ row_start, int N, double r,
                  const double *__restrict__ d_sin, const double *__restrict__ d_cos,
-                 const double *__restrict__ yrange, const int32_t *__restrict__ need_full, int32_t *bbox)
+                 const double *__restrict__ yrange, const int32_t *__restrict__ need_full, int n_phi, int32_t *bbox)
 {
-    const int p = blockIdx.y;
-    if (!need_full[p]) return;
+    // grid.y is bounded (one launch used to carry n_phi x N/16 CTAs that exit at once when no rotation is
+    // clipped - the usual case: 241 us of empty blocks per 1800 rotations); a CTA walks its share of the rotations
+    for (int p = blockIdx.y; p < n_phi; p += gridDim.y) {
+    if (!need_full[p]) continue;
     const double s = d_sin[p], c = d_cos[p], shift = yrange[2 * p], inv_r = 1.0 / r;
     int ylo = INT_MAX, yhi = -1, zlo = INT_MAX, zhi = -1;
     const int z0 = blockIdx.x * BBOX_ROWS;
@@ -315,6 +347,7 @@ bbox_full_kernel(const double *__restrict__ xs, const double *__restrict__ ys,
         atomicMin(&bbox[4 * p + 0], ylo); atomicMax(&bbox[4 * p + 1], yhi);
         atomicMin(&bbox[4 * p + 2], zlo); atomicMax(&bbox[4 * p + 3], zhi);
     }
+    }
 }
 
 __global__ void bbox_empty_kernel(int32_t *bbox, int n_phi)
@@ -332,8 +365,8 @@ extern "C" int gx_slice_bbox(const double *d_xs, const double *d_ys, const int32
     cudaStream_t st = gx_stream(stream);
     int32_t *need_full = d_scratch;
     bbox_fast_kernel<<<1, 1024, 0, st>>>(d_yrange, d_row_start, N, r, n_phi, d_bbox, need_full);
-    bbox_full_kernel<<<dim3((N + BBOX_ROWS - 1) / BBOX_ROWS, n_phi), ATOM_THREADS, 0, st>>>(
-        d_xs, d_ys, d_row_start, N, r, d_sin, d_cos, d_yrange, need_full, d_bbox);
+    bbox_full_kernel<<<dim3((N + BBOX_ROWS - 1) / BBOX_ROWS, n_phi < 8 ? n_phi : 8), ATOM_THREADS, 0, st>>>(
+        d_xs, d_ys, d_row_start, N, r, d_sin, d_cos, d_yrange, need_full, n_phi, d_bbox);
     bbox_empty_kernel<<<(n_phi + 255) / 256, 256, 0, st>>>(d_bbox, n_phi);
     return gx_check_launch("gx_slice_bbox");
 }

@@ -704,6 +704,9 @@ class SliceEngine:
              n, N, self.qmin, self.qmax, self.dq, self.q_num, ptr(t["col"]), st)
         if self.window is not None:
             call("gx_window_indices", ptr(t["col"]), n * N, self.q_num, self.window[0], self.window[1], 1, st)
+        # first / one-past-last kept column of every rotation (one launch for the whole run)
+        t["colrange"] = torch.empty(2 * n, dtype=torch.int32, device=dev)
+        call("gx_slice_col_range", ptr(t["col"]), n, N, ptr(t["colrange"]), st)
         return t
 
     def project(self, t, grid):
@@ -736,8 +739,6 @@ class SliceEngine:
         """F1 + F2 for one prepared batch (gx_slices_fused)."""
         a = self.atoms
         n = t["n"]
-        t["colrange"] = torch.empty(2 * n, dtype=torch.int32, device=self.device)
-        call("gx_slice_col_range", ptr(t["col"]), n, self.N, ptr(t["colrange"]), _stream())
         args = _lib.FusedArgs()
         for name, tensor in (("d_xs", a.xs), ("d_ys", a.ys), ("d_species", a.species), ("d_f", a.f),
                              ("d_row_start", a.row_start), ("d_table", a.table), ("d_sin", t["sin"]),
@@ -789,19 +790,18 @@ class SliceEngine:
             # per-rotation tables for the whole run in one set of launches, then one
             # pair of fused launches per batch on views of them
             full = self._timed("prepare", self.prepare, phis)
-            per_phi = {"sin": 1, "cos": 1, "yrange": 2, "bbox": 4, "base": 2 * N, "my": N, "mz": N, "dmy": 2 * N, "col": N}
-            ranges = []
+            per_phi = {"sin": 1, "cos": 1, "yrange": 2, "bbox": 4, "base": 2 * N, "my": N, "mz": N, "dmy": 2 * N, "col": N,
+                       "colrange": 2}
             for i0 in range(0, len(phis), B):
                 n = min(B, len(phis) - i0)
                 t = {k: full[k][i0 * w:(i0 + n) * w] for k, w in per_phi.items()}
                 t["n"] = n
                 self.fused(t, work)
-                ranges.append(t["colrange"])
                 self.slices_done += n
             call("gx_fold_dc", ptr(self.dc), ptr(self.vsum), _stream())
             torch.cuda.current_stream().synchronize()
             self.check_bbox(full)
-            cr = torch.cat(ranges).cpu().numpy().reshape(-1, 2)
+            cr = full["colrange"].cpu().numpy().reshape(-1, 2)
             self.mean_kept_columns = float(np.maximum(cr[:, 1] - cr[:, 0], 0).mean())
 
     def run(self, phis, capture=None, staged=None):
