@@ -71,12 +71,20 @@ def workload(args):
     return cfg, coords, elements
 
 
+def combine_text(world):
+    from giwaxsim_b200 import parallel
+    if world == 1:
+        return "no collective"
+    if parallel.COMBINE == "scatter":
+        return "partial sums reduce-scattered, finalise sharded, iq all-gathered"
+    return "partial sums all-reduced in place, finalise replicated"
+
+
 def config_dict(cfg, world):
     return {"workload": "BASELINE configs[4]: synthetic random-atom slab, fill_bkg=True, smooth=25",
             "atoms": cfg["n_atoms"], "grid": cfg["grid_size"], "phi_slices": cfg["n_phi"], "q_num": 569,
             "detector_pixels": cfg["num_pixels"], "orientations": int(len(cfg["psis"])),
-            "parallelism": "phi/psi sharded over %d rank(s); partial sums reduce-scattered, finalise sharded, iq "
-                           "all-gathered (NCCL behind the C ABI)" % world,
+            "parallelism": "phi/psi sharded over %d rank(s); %s (NCCL behind the C ABI)" % (world, combine_text(world)),
             "l2": "inputs larger than L2 (atoms 170 MB, each slice grid 134 MB); no flush needed"}
 
 
@@ -89,10 +97,31 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
         self.t0 = self.t1 = None
+        self.nvml_rows, self._run = [], True
+
+    def _nvml(self):
+        """Second source, same counters read in-process through NVML (what nvidia-smi itself calls):
+        a fresh box can need more than a second for nvidia-smi's first row, longer than a short run."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = [(nv.nvmlClocksEventReasonHwSlowdown, "Active"), (nv.nvmlClocksEventReasonHwThermalSlowdown, "Active"),
+                    (nv.nvmlClocksEventReasonSwThermalSlowdown, "Active"), (nv.nvmlClocksEventReasonSwPowerCap, "Active")]
+            while self._run:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                row = [str(self.index), str(sm), str(mx), "0"] + [a if mask & b else "Not Active" for b, a in bits]
+                self.nvml_rows.append((time.perf_counter(), row))
+                time.sleep(0.01)
+        except Exception:
+            pass
 
     def start(self):
         """Launch nvidia-smi early (it needs ~0.1 s to produce its first row); rows are time-stamped
         and only those inside [mark_begin, mark_end] are reported."""
+        threading.Thread(target=self._nvml, daemon=True).start()
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "20"],
@@ -111,13 +140,21 @@ class ClockSampler:
     def mark_end(self):
         self.t1 = time.perf_counter()
 
+    def _inside(self, stamped):
+        good = [(t, r) for t, r in stamped if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        return good, [r for t, r in good if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e300)]
+
     def stop(self):
-        if self.proc is None:
+        self._run = False
+        if self.proc is None and not self.nvml_rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        good = [(t, r) for t, r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        rows = [r for t, r in good if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e300)]
-        window = "timed region"
+        if self.proc is not None:
+            self.proc.terminate()
+        good, rows = self._inside(self.rows)
+        window = "timed region (nvidia-smi -lms 20)"
+        if not rows:
+            good, rows = self._inside(self.nvml_rows)
+            window = "timed region (NVML in-process, 10 ms; nvidia-smi produced no row inside it)"
         if not rows:
             # a timed region shorter than the sampling period: report the rows of warm-up + timed region
             rows, window = [r for t, r in good], "warm-up + timed region (timed region shorter than one sample)"
@@ -540,6 +577,7 @@ def roofline_block(cfg, eng, kernel_ms, n_slices_timed, N, peak, peak_src, clock
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     issue_peak = 4.0 * SM_COUNT * sm_mhz * 1e6            # warp instructions / s
     fp32_peak = 2.0 * 128 * SM_COUNT * sm_mhz * 1e6       # FLOP/s
+    lsu_peak = 1.0 * SM_COUNT * sm_mhz * 1e6              # shared-memory / L1 wavefronts per s
     per = {}
     cols_kernel = "slice_cols_tma" if (N == 4096 and "slice_cols_tma" in metrics) else "slice_cols_fused"
     for name, kern in (("rows", "slice_rows_fused"), ("cols", cols_kernel)):
@@ -556,6 +594,11 @@ def roofline_block(cfg, eng, kernel_ms, n_slices_timed, N, peak, peak_src, clock
             if m.get("flop"):
                 k["fp32_tflops"] = m["flop"] / spl / (us * 1e-6) / 1e12
                 k["fp32_frac"] = k["fp32_tflops"] * 1e12 / fp32_peak
+            if m.get("lsu_wavefronts"):
+                # L1 / shared-memory data pipe: one 128-byte wavefront per SM per cycle
+                k["lsu_wavefronts_per_slice"] = m["lsu_wavefronts"] / spl
+                k["lsu_pipe_achieved"] = m["lsu_wavefronts"] / spl / (us * 1e-6)
+                k["lsu_pipe_frac"] = k["lsu_pipe_achieved"] / lsu_peak
             k["traffic_per_launch"] = m.get("dram_bytes")
             k["source"] = m.get("source")
         per[name] = k
@@ -565,9 +608,7 @@ def roofline_block(cfg, eng, kernel_ms, n_slices_timed, N, peak, peak_src, clock
     return {"bound": "hbm", "kernel": top["kernel"], "achieved": top["hbm_achieved"], "peak": peak, "unit": "GB/s",
             "frac": top["hbm_frac"], "traffic": top.get("traffic_per_launch"), "peak_source": peak_src,
             "slices_per_launch": B, "algorithmic_bytes_per_launch": fused_bytes["rows"] * B,
-            "binding_bound": {"bound": "issue", "achieved": top.get("issue_achieved"), "peak": issue_peak,
-                              "unit": "warp-inst/s", "frac": top.get("issue_frac"),
-                              "note": "the kernel is bound by instruction issue, not by DRAM: see per_kernel"},
+            "binding_bound": binding_bound(top, issue_peak, lsu_peak),
             "per_kernel": per,
             "kernel_ms_per_slice": {k: v / n_slices_timed for k, v in kernel_ms.items()},
             "unfused_floor": {"algorithmic_bytes_per_slice": unfused,
@@ -579,18 +620,40 @@ def roofline_block(cfg, eng, kernel_ms, n_slices_timed, N, peak, peak_src, clock
             "note": "frac = HBM bytes the fused design must move / CUDA-event time / measured copy peak"}
 
 
+def binding_bound(k, issue_peak, lsu_peak):
+    """The on-chip resource the row kernel saturates first: its shared-memory data pipe (accumulator zero /
+    read, two FFT exchanges, atomics with their bank conflicts) or instruction issue, whichever fraction is larger."""
+    cands = [("shared-memory data pipe", k.get("lsu_pipe_achieved"), lsu_peak, "wavefronts/s", k.get("lsu_pipe_frac")),
+             ("issue", k.get("issue_achieved"), issue_peak, "warp-inst/s", k.get("issue_frac"))]
+    cands = [c for c in cands if c[4]]
+    if not cands:
+        return None
+    b = max(cands, key=lambda c: c[4])
+    return {"bound": b[0], "achieved": b[1], "peak": b[2], "unit": b[3], "frac": b[4],
+            "others": {c[0]: c[4] for c in cands if c is not b},
+            "note": "the kernel is bound on chip, not by DRAM: counts from the ncu capture of the same build "
+                    "(profiles/r04_kernel_metrics.json) over the live CUDA-event time"}
+
+
+_REAL_STDOUT = None
+
+
+def divert_stdout():
+    """Libraries write banners to fd 1 (NCCL prints "NCCL version ..." on the first communicator): keep
+    the process's stdout for the single JSON line and send every other byte to stderr."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 def emit(line):
     """The ONE JSON line goes to the real stdout; everything else was diverted to stderr."""
-    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    os.write(1 if _REAL_STDOUT is None else _REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
-
-# Libraries write banners to fd 1 (NCCL prints "NCCL version ..." on the first communicator): keep
-# the process's stdout for the single JSON line and send every other byte to stderr.
-sys.stdout.flush()
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
 
 if __name__ == "__main__":
+    divert_stdout()
     a = parse()
     if a.impl == "reference":
         run_reference(a)

@@ -300,10 +300,12 @@ __global__ void bbox_fast_kernel(const double *__restrict__ yrange, const int32_
     __syncthreads();
     const bool z_clipped = row_start[N + 1] > row_start[N];
     const double inv_r = 1.0 / r;
+    int any = 0;
     for (int p = threadIdx.x; p < n_phi; p += blockDim.x) {
         double span = __dsub_rn(yrange[2 * p + 1], yrange[2 * p]);
         double top = gx_floordiv(span, r, inv_r);
         bool full = z_clipped || !(top < (double)N) || s_last < 0;
+        any |= full ? 1 : 0;
         need_full[p] = full ? 1 : 0;
         if (full) {
             bbox[4 * p + 0] = INT_MAX; bbox[4 * p + 1] = -1; bbox[4 * p + 2] = INT_MAX; bbox[4 * p + 3] = -1;
@@ -311,6 +313,8 @@ __global__ void bbox_fast_kernel(const double *__restrict__ yrange, const int32_
             bbox[4 * p + 0] = 0; bbox[4 * p + 1] = (int)top; bbox[4 * p + 2] = s_first; bbox[4 * p + 3] = s_last;
         }
     }
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) need_full[n_phi] = any;          // lets the full pass return at once when nothing is clipped
 }
 
 #define BBOX_ROWS 16
@@ -322,6 +326,7 @@ bbox_full_kernel(const double *__restrict__ xs, const double *__restrict__ ys,
 {
     // grid.y is bounded (one launch used to carry n_phi x N/16 CTAs that exit at once when no rotation is
     // clipped - the usual case: 241 us of empty blocks per 1800 rotations); a CTA walks its share of the rotations
+    if (!need_full[n_phi]) return;
     for (int p = blockIdx.y; p < n_phi; p += gridDim.y) {
     if (!need_full[p]) continue;
     const double s = d_sin[p], c = d_cos[p], shift = yrange[2 * p], inv_r = 1.0 / r;

@@ -679,7 +679,7 @@ class SliceEngine:
         cx, cy, cn = a.candidates()
         call("gx_slice_yrange", ptr(cx), ptr(cy), cn, ptr(t["sin"]), ptr(t["cos"]), n, ptr(t["yrange"]), st)
         t["bbox"] = torch.empty(4 * n, dtype=torch.int32, device=dev)
-        scratch = torch.empty(n, dtype=torch.int32, device=dev)
+        scratch = torch.empty(n + 1, dtype=torch.int32, device=dev)
         call("gx_slice_bbox", ptr(a.xs), ptr(a.ys), ptr(a.row_start), N, self.r, ptr(t["sin"]), ptr(t["cos"]),
              ptr(t["yrange"]), n, ptr(t["bbox"]), ptr(scratch), st)
         t["base"] = torch.empty(2 * n * N, dtype=torch.float32, device=dev)

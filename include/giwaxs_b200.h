@@ -123,7 +123,7 @@ int gx_hull_filter(const double *d_xs, const double *d_ys, int64_t A, const doub
                    void *stream);
 
 /* index bounding box {y_min,y_max,z_min,z_max} of the valid atoms of every
- * rotation; -1 entries when no atom is valid.  d_scratch: n_phi int32.
+ * rotation; -1 entries when no atom is valid.  d_scratch: n_phi + 1 int32.
  *                                                        (vg.py:332-349)   */
 int gx_slice_bbox(const double *d_xs, const double *d_ys, const int32_t *d_row_start, int N,
                   double r, const double *d_sin, const double *d_cos, const double *d_yrange,

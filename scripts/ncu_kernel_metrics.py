@@ -32,6 +32,12 @@ for arg in sys.argv[2:]:
             "dram_read": val("dram__bytes_read.sum"), "dram_write": val("dram__bytes_write.sum"),
             "issue_active_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active"),
             "registers": val("launch__registers_per_thread"),
+            # L1 / shared-memory data pipe (one 128-byte wavefront per SM per cycle): the limit of a kernel that
+            # lives in shared memory; wavefronts = pct x SM cycles, so bench.py can restate it for its own timing
+            "lsu_data_pipe_pct": val("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+            "lsu_wavefronts": val("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed") / 100.0 *
+                              val("sm__cycles_elapsed.avg") * val("launch__sm_count") if "launch__sm_count" in d else None,
+            "shared_wavefronts": val("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
             "warps_active_pct": val("sm__warps_active.avg.pct_of_peak_sustained_active"),
             "l1_hit_pct": val("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": val("lts__t_sector_hit_rate.pct"),
             "stalls_per_issue": {k.split("issue_stalled_")[1].split("_per_issue")[0]: float(d[k])

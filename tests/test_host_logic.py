@@ -324,6 +324,50 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["config"]["workload"].startswith("BASELINE configs[4]") and d["gpu_launches"] == 0
 
 
+def _bench_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_bench_binding_bound_is_the_larger_on_chip_fraction():
+    """`roofline.binding_bound` names the on-chip resource with the larger measured fraction (shared-memory
+    data pipe or instruction issue) and lists the other one beside it; without ncu counts there is none."""
+    b = _bench_module()
+    k = {"lsu_pipe_achieved": 2.5e11, "lsu_pipe_frac": 0.86, "issue_achieved": 8.1e11, "issue_frac": 0.70}
+    out = b.binding_bound(k, 1.163e12, 2.908e11)
+    assert out["bound"] == "shared-memory data pipe" and out["frac"] == 0.86 and out["unit"] == "wavefronts/s"
+    assert out["others"] == {"issue": 0.70} and out["frac"] <= 1.0
+    out = b.binding_bound({"issue_achieved": 8.1e11, "issue_frac": 0.70}, 1.163e12, 2.908e11)
+    assert out["bound"] == "issue" and out["others"] == {}
+    assert b.binding_bound({}, 1.163e12, 2.908e11) is None
+
+
+def test_bench_clock_sampler_windows():
+    """Rows are kept only inside [mark_begin, mark_end]; nvidia-smi rows win, the in-process NVML rows fill in
+    when nvidia-smi produced none inside the timed region, and throttle reasons are reported by name."""
+    b = _bench_module()
+    row = lambda sm, cap="Not Active": ["0", str(sm), "1965", "600.0", "Not Active", "Not Active", "Not Active", cap]
+    s = b.ClockSampler(0)
+    s.proc = type("P", (), {"terminate": lambda self: None})()
+    s.t0, s.t1 = 10.0, 20.0
+    s.rows = [(5.0, row(300)), (12.0, row(1965)), (15.0, row(1950, "Active")), (25.0, row(400))]
+    out = s.stop()
+    assert out["sm_mhz"] == 1957.5 and out["samples"] == 2 and out["reasons"] == ["sw_power_cap"]
+    assert out["window"].startswith("timed region (nvidia-smi")
+    s = b.ClockSampler(0)
+    s.proc = type("P", (), {"terminate": lambda self: None})()
+    s.t0, s.t1 = 10.0, 20.0
+    s.rows = [(5.0, row(300))]
+    s.nvml_rows = [(11.0, row(1965)), (30.0, row(500))]
+    out = s.stop()
+    assert out["sm_mhz"] == 1965.0 and out["samples"] == 1 and "NVML" in out["window"] and out["reasons"] == []
+    s = b.ClockSampler(0)
+    assert s.stop()["reasons"] == ["nvidia-smi unavailable"]
+
+
 def test_result_mapping_tracks_in_place_edits():
     """Large results are handed out as private copy-on-write mappings of a pooled memory file
     (parallel.shared_result_f64(single=True)): reading leaves them 'unmodified', any write - also through a
