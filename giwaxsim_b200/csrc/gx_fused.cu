@@ -41,10 +41,6 @@
 #ifndef GX_SCATTER_U
 #define GX_SCATTER_U 2      // atoms per thread in flight in the row kernel's scatter (1 .. 4 measured: profiles/r04_summary.md)
 #endif
-#ifndef GX_F1_YSKIP
-#define GX_F1_YSKIP 1       // row kernel: accumulators outside the rotation's atom range [y_min, y_max] are neither zeroed nor read,
-                            // (d, my) not fetched where the pedestal-free pixel is exactly 0: profiles/r04_summary.md
-#endif
 #ifndef GX_F1_MINBLOCKS
 #define GX_F1_MINBLOCKS 5   // CTAs/SM the 4096-point row kernel is compiled for (others: 4): 48 registers, 4 bytes spilled with
                             // two atoms in flight; 61.7 (4 CTAs, 64 registers) -> 59.8 us per slice, 6 CTAs: 68.3, 3: 66.3
@@ -207,11 +203,8 @@ __device__ __forceinline__ void scatter_fixed(const ProjArgs &a, const int2 *s_f
 // padding): every pixel index is in range, all loads are one base register plus immediates.
 template <int NB0, int R0, int S0, int NT, bool EXACT, bool FINISH>
 __device__ __forceinline__ void flush_fixed(float2 (&px)[NB0][R0], const int32_t *acc, int NP, int tid, int N,
-                                            float inv_re, float inv_im, float af_re, float af_im, float mzv,
-                                            int ya, unsigned yspan)
+                                            float inv_re, float inv_im, float af_re, float af_im, float mzv)
 {
-    // pixels outside [ya, ya + yspan] hold no atoms (and, FINISH, arrive with (d, my) = (0, 0)): their accumulators
-    // were not zeroed and are not read - a warp whose 32 pixels all lie outside issues no shared-memory access
     // FINISH: v = ((w0 + d af_re 2^k_re) m 2^-k_re, (w1 + d af_im 2^k_im) m 2^-k_im) - the scales ride on the
     // background coefficient and on the mask, so a pixel costs two conversions, two FFMA and three FMUL
     const float bg_re = af_re / inv_re, bg_im = af_im / inv_im;       // exact: the scales are powers of two
@@ -230,8 +223,7 @@ __device__ __forceinline__ void flush_fixed(float2 (&px)[NB0][R0], const int32_t
         for (int n = 0; n < R0; ++n) {
             const int y = t + S0 * n;
             const int yy = EXACT ? y : min(y, N - 1);
-            const bool in = !GX_F1_YSKIP || (unsigned)(y - ya) <= yspan;
-            const float w0 = in ? (float)acc[yy] : 0.f, w1 = in ? (float)acc[NP + yy] : 0.f;
+            const float w0 = (float)acc[yy], w1 = (float)acc[NP + yy];
             if (FINISH) {
                 const float2 dm = px[i][n];
                 const float my = (EXACT || y < N) ? dm.y : 0.f;
@@ -272,16 +264,14 @@ slice_rows_fused(FusedArgs fa)
     constexpr bool EXACT = !BLUE && NB0 * NT == S0;        // every pixel index t + S0 n is a pixel of the row
     // every per-rotation / per-row scalar is requested before the first branch, so the CTA
     // pays one L2 round trip for all of them instead of one per dependent use
-    int y_min, y_max, z_min, z_max, jlo, jhi, beg, end;
+    int z_min, z_max, jlo, jhi, beg, end;
     double s, c, shift;
     if (fa.use_const) {
-        y_min = c_bbox[4 * p]; y_max = c_bbox[4 * p + 1];
         z_min = c_bbox[4 * p + 2]; z_max = c_bbox[4 * p + 3];
         jlo = c_colrange[2 * p]; jhi = c_colrange[2 * p + 1];
         s = c_sn[p]; c = c_cs[p]; shift = c_yrange[2 * p];
         beg = c_row_start[z]; end = c_row_start[z + 1];
     } else {
-        y_min = __ldg(a.bbox + 4 * p); y_max = __ldg(a.bbox + 4 * p + 1);
         z_min = __ldg(a.bbox + 4 * p + 2); z_max = __ldg(a.bbox + 4 * p + 3);
         jlo = __ldg(fa.colrange + 2 * p); jhi = __ldg(fa.colrange + 2 * p + 1);
         s = __ldg(a.sn + p); c = __ldg(a.cs + p); shift = __ldg(a.yrange + 2 * p);
@@ -297,18 +287,6 @@ slice_rows_fused(FusedArgs fa)
     if (jhi <= jlo) return;
 
     const int NP = (N + 3) & ~3;                           // accumulator plane stride (words)
-    // y ranges of the rotation (slice_vectors_kernel): atoms fall on [y_min, y_max]; the pedestal-free pixel can be
-    // non-zero on (y_min, y_max) with the background fill (my = 0 elsewhere), anywhere under smoothing alone (the
-    // mask's fringe carries -pedestal), on [y_min, y_max] otherwise
-    int ya = 0, yb = N - 1, zlo = 0, zhi = N - 1;          // pixels fetched / accumulator words zeroed
-    if (GX_F1_YSKIP) {
-        if (a.fill_bkg) { ya = y_min + 1; yb = y_max - 1; zlo = y_min; zhi = y_max; }
-        else if (a.sigma <= 0) { ya = zlo = y_min; yb = zhi = y_max; }
-        if (ya < 0) ya = 0;
-        if (zlo < 0) zlo = 0;
-    }
-    const unsigned yspan = yb >= ya ? (unsigned)(yb - ya) : 0u;
-    if (GX_F1_YSKIP && yb < ya) ya = N;                    // empty range: nothing is inside
     const float2 *dmy = fa.dmy + (size_t)p * N;
     float2 px[NB0][R0];
     bool finished = false;                                 // px already holds the completed pixels
@@ -318,10 +296,7 @@ slice_rows_fused(FusedArgs fa)
     if constexpr (EXACT && (2 * M / 4) % NT == 0) {
         // plane length known at compile time: straight-line 16-byte stores, immediate offsets
 #pragma unroll
-        for (int k = 0; k < (2 * M / 4) / NT; ++k) {
-            const int v = tid + k * NT, w = (v & (M / 4 - 1)) * 4;      // first word of this int4 within its plane
-            if (!GX_F1_YSKIP || (w + 3 >= zlo && w <= zhi)) acc4[v] = make_int4(0, 0, 0, 0);
-        }
+        for (int k = 0; k < (2 * M / 4) / NT; ++k) acc4[tid + k * NT] = make_int4(0, 0, 0, 0);
     } else {
         for (int y = tid; y < 2 * (NP / 4); y += NT) acc4[y] = make_int4(0, 0, 0, 0);
     }
@@ -336,13 +311,10 @@ slice_rows_fused(FusedArgs fa)
 #pragma unroll
             for (int n = 0; n < R0; ++n) {
                 const int t = tid + i * NT, y = t + S0 * n;
-                const bool in = !GX_F1_YSKIP || (unsigned)(y - ya) <= yspan;
-                px[i][n] = in ? __ldg(dmy + (EXACT ? y : min(y, N - 1)))   // clamped: pixels beyond N are zeroed later
-                              : make_float2(0.f, 0.f);
+                px[i][n] = __ldg(dmy + (EXACT ? y : min(y, N - 1)));   // clamped: pixels beyond N are zeroed later
             }
         __syncthreads();
-        flush_fixed<NB0, R0, S0, NT, EXACT, true>(px, acc, NP, tid, N, fa.fx_inv_re, fa.fx_inv_im, fa.af_re, fa.af_im, mzv,
-                                                  ya, yspan);
+        flush_fixed<NB0, R0, S0, NT, EXACT, true>(px, acc, NP, tid, N, fa.fx_inv_re, fa.fx_inv_im, fa.af_re, fa.af_im, mzv);
         __syncthreads();   // every accumulator read is done before buf is written
         finished = true;
     } else {
@@ -355,9 +327,7 @@ slice_rows_fused(FusedArgs fa)
             const int c1 = min(c0 + fa.chunk_atoms, end);
             scatter_fixed<SPECIES>(a, s_ffx, fa.fx_scale_re, fa.fx_scale_im, c0, c1, s, c, shift, acc, NP);
             __syncthreads();
-            // chunked rows: the words atoms can fall on, [zlo, zhi], are read (the first zeroing covered only those)
-            flush_fixed<NB0, R0, S0, NT, EXACT, false>(px, acc, NP, tid, N, fa.fx_inv_re, fa.fx_inv_im, 0.f, 0.f, 0.f,
-                                                       zlo, zhi >= zlo ? (unsigned)(zhi - zlo) : 0u);
+            flush_fixed<NB0, R0, S0, NT, EXACT, false>(px, acc, NP, tid, N, fa.fx_inv_re, fa.fx_inv_im, 0.f, 0.f, 0.f);
             __syncthreads();   // every accumulator read is done before the next chunk / before buf is written
             if (c1 < end) {
                 for (int y = tid; y < 2 * (NP / 4); y += NT) acc4[y] = make_int4(0, 0, 0, 0);
