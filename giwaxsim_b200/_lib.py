@@ -17,7 +17,7 @@ GX_ERR_CUDA = -2
 GX_ERR_UNSUPPORTED = -3
 GX_ERR_NO_DEVICE = -4
 GX_MAX_SPECIES = 16
-ABI_VERSION = 4          # GX_ABI_VERSION of include/giwaxs_b200.h this binding was written for
+ABI_VERSION = 5          # GX_ABI_VERSION of include/giwaxs_b200.h this binding was written for
 
 
 class GxError(RuntimeError):
@@ -100,6 +100,7 @@ _PROTOTYPES = {
     "gx_host_register": (_i, [_p, _i64]),
     "gx_host_unregister": (_i, [_p]),
     "gx_copy_to_host_async": (_i, [_p, _p, _i64, _p]),
+    "gx_host_widen_f32_f64": (_i, [_p, _p, _i64, _i]),
     "gx_comm_unique_id": (_i, [_p]),
     "gx_comm_init": (_i, [_p, _i, _i, _p]),
     "gx_comm_destroy": (_i, [_p]),

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libgiwaxs_b200.so")
 SOURCES = ["gx_api.cu", "gx_atoms.cu", "gx_project.cu", "gx_fft.cu", "gx_bin.cu", "gx_detector.cu",
-           "gx_detector_affine.cu", "gx_fused.cu", "gx_slab.cu", "gx_comm.cu", "gx_compare.cu"]
+           "gx_detector_affine.cu", "gx_fused.cu", "gx_slab.cu", "gx_comm.cu", "gx_compare.cu", "gx_hostcopy.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=default", "--expt-relaxed-constexpr", "-DGX_TWP=1",
@@ -35,8 +35,12 @@ def _stale(target, sources):
     return any(os.path.getmtime(s) > t for s in sources if os.path.exists(s))
 
 
+def _obj_name(src):
+    return os.path.splitext(src)[0] + ".o"
+
+
 def _compile(src):
-    obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+    obj = os.path.join(OBJ, _obj_name(src))
     path = os.path.join(CSRC, src)
     if not _stale(obj, [path] + _deps()):
         return obj, ""
@@ -52,7 +56,7 @@ def build(force=False, verbose=False):
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     if force:
         for s in srcs:
-            o = os.path.join(OBJ, s.replace(".cu", ".o"))
+            o = os.path.join(OBJ, _obj_name(s))
             if os.path.exists(o):
                 os.remove(o)
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:

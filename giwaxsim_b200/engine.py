@@ -162,9 +162,14 @@ def to_host_f64(t, out=None, replicated=False):
                 ev = torch.cuda.Event()
                 ev.record()
                 marks.append((lo, hi, ev))
+            widen = t.dtype == torch.float32 and dst.dtype == torch.float64
             for lo, hi, ev in marks:
                 ev.synchronize()
-                dst[lo:hi].copy_(stg[lo:hi])
+                if widen:
+                    # library pool + non-temporal stores: torch's cast copy reads every destination line first
+                    call("gx_host_widen_f32_f64", stg.data_ptr() + 4 * lo, dst.data_ptr() + 8 * lo, hi - lo, want)
+                else:
+                    dst[lo:hi].copy_(stg[lo:hi])
         else:
             stage.copy_(t, non_blocking=True)
             torch.cuda.current_stream().synchronize()

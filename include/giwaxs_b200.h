@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define GX_ABI_VERSION 4   /* 4: gx_fused_args.phases, gx_comm_*, sharded finalise, device-side orientation model */
+#define GX_ABI_VERSION 5   /* 4: gx_fused_args.phases, gx_comm_*, sharded finalise, device-side orientation model; 5: gx_host_widen_f32_f64 */
 
 #define GX_OK 0
 #define GX_ERR_INVALID (-1)     /* bad argument                              */
@@ -370,6 +370,11 @@ int gx_detector_accumulate_affine_brick(const float *d_iq, const float *d_iq_pad
 int gx_host_register(void *h_ptr, int64_t nbytes);
 int gx_host_unregister(void *h_ptr);
 int gx_copy_to_host_async(void *h_dst, const void *d_src, int64_t nbytes, void *stream);
+/* One rank: the fp32 grid crosses PCIe chunk by chunk into a page-locked staging buffer and is
+ * widened there -> the float64 array the caller receives (comparison.py:769-786 returns float64):
+ * h_dst[i] = (double)h_src[i], i < n, on `threads` host threads (a persistent pool inside the
+ * library; the calling thread is one of them) with non-temporal stores.  Host-only: no CUDA call. */
+int gx_host_widen_f32_f64(const float *h_src, double *h_dst, int64_t n, int threads);
 
 /* ----------------------------------------------------- multi-GPU exchange */
 /* One process per GPU; the partial voxel sums / counts of stage A and the

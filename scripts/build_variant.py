@@ -11,7 +11,7 @@ os.makedirs(out_dir, exist_ok=True)
 obj = os.path.join(out_dir, src.replace(".cu", "_%s.o" % name))
 subprocess.check_call([b.NVCC] + [f for f in b.FLAGS if f not in ("-Xptxas", "-v")] + flags +
                       ["-c", os.path.join(b.CSRC, src), "-o", obj])
-objs = [os.path.join(b.OBJ, s.replace(".cu", ".o")) for s in b.SOURCES if s != src] + [obj]
+objs = [os.path.join(b.OBJ, b._obj_name(s)) for s in b.SOURCES if s != src] + [obj]
 lib = os.path.join(out_dir, "libgiwaxs_b200_%s.so" % name)
 subprocess.check_call([b.NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
                                                                "-Xcompiler", "-fPIC", "-ldl"])

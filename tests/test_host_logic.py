@@ -324,6 +324,27 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["config"]["workload"].startswith("BASELINE configs[4]") and d["gpu_launches"] == 0
 
 
+def test_host_widening_copy_matches_numpy():
+    """gx_host_widen_f32_f64 (the fp32 -> float64 pass of the result download, run on the library's host thread
+    pool with streaming stores): every element equals NumPy's cast, whatever the alignment, the length and the
+    number of threads; neighbours of the destination range are untouched; errors follow the C-ABI convention."""
+    import torch
+    from giwaxsim_b200 import _lib
+    rng = np.random.default_rng(3)
+    src = rng.standard_normal(3_000_017).astype(np.float32)
+    src[:4] = [0.0, -0.0, np.float32(1e-45), np.float32(3.4e38)]
+    for off, n, threads in ((0, len(src), 8), (1, 1_000_003, 3), (3, 9, 4), (2, 300_000, 1), (5, 0, 2)):
+        dst = np.full(n + 3, 7.0)
+        _lib.call("gx_host_widen_f32_f64", src.ctypes.data + 4 * off, dst.ctypes.data + 8, n, threads)
+        assert np.array_equal(dst[1:1 + n], src[off:off + n].astype(np.float64))
+        assert np.array_equal(np.signbit(dst[1:1 + n]), np.signbit(src[off:off + n]))
+        assert dst[0] == 7.0 and dst[n + 1] == 7.0 and dst[n + 2] == 7.0
+    with pytest.raises(_lib.GxError, match="NULL pointer"):
+        _lib.call("gx_host_widen_f32_f64", 0, src.ctypes.data, 4, 1)
+    with pytest.raises(_lib.GxError, match="negative length"):
+        _lib.call("gx_host_widen_f32_f64", src.ctypes.data, src.ctypes.data, -1, 1)
+
+
 def _bench_module():
     import importlib.util
     spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
