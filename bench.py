@@ -617,7 +617,20 @@ def roofline_block(cfg, eng, kernel_ms, n_slices_timed, N, peak, peak_src, clock
                               "note": "SURVEY 8(d) bytes of the scatter + 2-D FFT + binning kernels the fused "
                                       "pair replaces; the pair is faster than that floor because the N x N grid "
                                       "and image never reach HBM - it is not a fraction of this kernel's roofline"},
+            "summary": roofline_summary(per, top),
             "note": "frac = HBM bytes the fused design must move / CUDA-event time / measured copy peak"}
+
+
+def roofline_summary(per, top):
+    """One sentence a reader can check against per_kernel."""
+    r, c = per["rows"], per["cols"]
+    share = r["us_per_slice"] / (r["us_per_slice"] + c["us_per_slice"])
+    parts = ["row kernel = %.0f %% of the fused pair" % (100 * share), "HBM %.3f of peak" % r["hbm_frac"]]
+    if r.get("lsu_pipe_frac"):
+        parts.append("shared-memory data pipe %.2f of peak" % r["lsu_pipe_frac"])
+    if r.get("issue_frac"):
+        parts.append("issue slots %.2f" % r["issue_frac"])
+    return "; ".join(parts) + "; column kernel: HBM %.2f of peak" % c["hbm_frac"]
 
 
 def binding_bound(k, issue_peak, lsu_peak):
