@@ -737,7 +737,7 @@ class SliceEngine:
         return bb
 
     def fused_batch_size(self, budget_bytes=2 << 30):
-        cap = int(os.environ.get("GIWAXS_B200_FUSED_BATCH", "64"))
+        cap = int(os.environ.get("GIWAXS_B200_FUSED_BATCH", "128"))     # what the constant tables of the row kernel hold
         return int(max(1, min(cap, budget_bytes // (8 * self.N * self.KC))))
 
     def fused(self, t, work):
