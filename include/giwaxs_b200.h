@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define GX_ABI_VERSION 5   /* 4: gx_fused_args.phases, gx_comm_*, sharded finalise, device-side orientation model; 5: gx_host_widen_f32_f64 */
+#define GX_ABI_VERSION 5   /* 4: gx_fused_args.phases, gx_comm_*, column range of gx_voxel_finalize, host-boundary calls; 5: gx_host_widen_f32_f64 */
 
 #define GX_OK 0
 #define GX_ERR_INVALID (-1)     /* bad argument                              */
